@@ -1,0 +1,158 @@
+/* bloch_b200.h - C ABI of the B200-native Bloch Maxwell eigen path.
+ *
+ * The reference (mlstowell/mfem-bravais) has no FFI; its seam for this path is the C++ class
+ * mfem::bloch::MaxwellBlochWaveEquation (maxwell/maxwell_bloch.hpp:140-234).  Each entry
+ * point below names the member function it replaces.  All arrays are caller-allocated, plain
+ * pointers + sizes, no exceptions cross the boundary.  Every function returns 0 on success
+ * and a negative code on failure; bloch_last_error() gives the message (thread-local).
+ *
+ * Vector layout at the boundary is the reference's: one real vector of length 2N per complex
+ * field, [re(N); im(N)] (block offsets [0,N,2N], maxwell_bloch.cpp:112-120); nvec vectors
+ * are stored one after the other (vector v starts at x + v*2N).
+ *
+ * One handle = one eigenproblem object bound to one CUDA device and stream.  A handle is
+ * not thread-safe; different handles are fully independent (the k-point sweep relies on it).
+ * There is no CPU fallback: bloch_create fails if no CUDA device is usable.
+ */
+#ifndef BLOCH_B200_H
+#define BLOCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bloch_handle_s *bloch_handle;
+
+/* error codes */
+#define BLOCH_OK 0
+#define BLOCH_ERR_ARG (-1)
+#define BLOCH_ERR_CUDA (-2)
+#define BLOCH_ERR_STATE (-3)
+#define BLOCH_ERR_NOCONV (-4)
+#define BLOCH_ERR_INTERNAL (-5)
+
+/* lattice types: values of bravais::BRAVAIS_LATTICE_TYPE (lib/bravais.hpp:24-50) */
+#define BLOCH_LATTICE_CUB 7
+#define BLOCH_LATTICE_FCC 8
+#define BLOCH_LATTICE_BCC 9
+
+const char *bloch_last_error(void);
+int bloch_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int bloch_device_count(void);
+
+/* ---- lattice / k-path API (lib/bravais.hpp:64-181, factory :1175-1239) ---- */
+typedef struct bloch_lattice_s *bloch_lattice;
+int bloch_lattice_create(bloch_lattice *out, int lattice_type, double a, double b, double c,
+                         double alpha, double beta, double gamma);     /* BravaisLatticeFactory */
+int bloch_lattice_destroy(bloch_lattice lat);
+int bloch_lattice_label(bloch_lattice lat, char *buf, int buflen);     /* GetLatticeTypeLabel */
+double bloch_lattice_volume(bloch_lattice lat);                         /* GetUnitCellVolume */
+int bloch_lattice_vectors(bloch_lattice lat, double lat9[9], double rec9[9]); /* Get(Reciprocal)LatticeVectors */
+int bloch_lattice_num_translations(bloch_lattice lat);
+int bloch_lattice_translations(bloch_lattice lat, double *trn, double *face_radii); /* GetTranslationVectors, GetFaceRadii */
+int bloch_lattice_num_symmetry_points(bloch_lattice lat);               /* GetNumberSymmetryPoints */
+int bloch_lattice_symmetry_point(bloch_lattice lat, int i, double kappa[3], char *label, int buflen); /* GetSymmetryPoint(+Label): 2 pi sp */
+int bloch_lattice_symmetry_point_index(bloch_lattice lat, const char *label); /* GetSymmetryPointIndex; -1 if unknown */
+int bloch_lattice_num_paths(bloch_lattice lat);                         /* GetNumberPaths */
+int bloch_lattice_num_path_segments(bloch_lattice lat, int p);          /* GetNumberPathSegments */
+int bloch_lattice_path_segment(bloch_lattice lat, int p, int s, int *e0, int *e1); /* GetPathSegmentEndPointIndices */
+int bloch_lattice_intermediate_point(bloch_lattice lat, int p, int s, double kappa[3], char *label, int buflen); /* GetIntermediatePoint(+Label) */
+int bloch_lattice_map_to_primitive_cell(bloch_lattice lat, const double pt[3], double ipt[3]); /* MapToPrimitiveCell; returns 1 if mapped */
+
+/* ---- eigenproblem object ---- */
+
+/* MaxwellBlochWaveEquation(ParMesh&, int order) (maxwell_bloch.hpp:143, .cpp:34-140) on the
+ * periodic Wigner-Seitz hex mesh of `lat` with every coarse hex subdivided n_sub^3 times
+ * (n_sub = 2^r reproduces r uniform refinements, maxwell_dispersion.cpp:366-388).
+ * device == -1 selects the current CUDA device.  device == BLOCH_DEVICE_NONE builds a
+ * topology-only handle (mesh, dof maps and sizes can be queried without a GPU; every compute
+ * entry point fails with BLOCH_ERR_ARG) - used by the host-logic tests, never a fallback. */
+#define BLOCH_DEVICE_NONE (-2)
+int bloch_create(bloch_handle *out, bloch_lattice lat, int n_sub, int order, int device);
+/* same, for an arbitrary periodic mesh of parallelepiped hexes: vertices xyz[3*n_vert], hexes
+ * hex[8*n_hex] in MFEM vertex order, each subdivided n_sub^3; rec9 = reciprocal vectors (rows) */
+int bloch_create_from_hexes(bloch_handle *out, int n_vert, const double *xyz, int n_hex,
+                            const int *hex, const double rec9[9], int n_sub, int order, int device);
+int bloch_destroy(bloch_handle h);                                      /* ~MaxwellBlochWaveEquation */
+/* run on an externally owned stream (a cudaStream_t cast to void*); NULL = handle's own stream */
+int bloch_set_stream(bloch_handle h, void *cuda_stream);
+
+/* sizes: GetHCurlFESpace()->GlobalTrueVSize() etc. (maxwell_bloch.hpp:205-206) */
+int bloch_num_elements(bloch_handle h, int64_t *n_elem, int *n_class);
+int bloch_num_dofs(bloch_handle h, int64_t *n_nd, int64_t *n_rt, int64_t *n_h1);
+int bloch_mesh_counts(bloch_handle h, int64_t *n_vert, int64_t *n_edge, int64_t *n_face, double *volume);
+int bloch_element_centers(bloch_handle h, double *xyz /* 3*n_elem */);
+/* geometry of the affine elements: x0[3*n_elem], cls[n_elem], J[9*n_class] (row-major dx_i/dxhat_j) */
+int bloch_element_geometry(bloch_handle h, double *x0, int *cls, double *J);
+/* element -> signed 1-based global dof ids (+-(gid+1)) in the natural local order documented
+ * in DESIGN.md; space: 0 = H1, 1 = ND, 2 = RT.  out has n_elem * local_size entries. */
+int bloch_local_size(bloch_handle h, int space);
+int bloch_get_dofmap(bloch_handle h, int space, int32_t *out);
+
+/* SetMassCoef / SetStiffnessCoef (maxwell_bloch.hpp:164-165): one value per element, copied */
+int bloch_set_eps(bloch_handle h, const double *eps_per_elem);
+int bloch_set_muinv(bloch_handle h, const double *muinv_per_elem);
+/* SetKappa (maxwell_bloch.hpp:152; beta = |kappa|, zeta = kappa/beta, .cpp:200-210) */
+int bloch_set_kappa(bloch_handle h, const double kappa[3]);
+/* SetNumEigs counts REAL modes in the reference (2 per complex band); this takes complex bands */
+int bloch_set_num_bands(bloch_handle h, int n_complex_bands);
+/* SetAbsoluteTolerance (default 1e-6, .cpp:53) and lobpcg_->SetMaxIter(2000) (.cpp:543) */
+int bloch_set_tol(bloch_handle h, double abs_tol, int max_iter);
+/* Setup() (maxwell_bloch.hpp:167, .cpp:337-620): uploads the kappa-dependent class tables and
+ * (re)builds the preconditioner data.  Idempotent; only what changed is rebuilt. */
+int bloch_setup(bloch_handle h);
+/* SetInitialVectors (maxwell_bloch.hpp:169): m vectors of length 2N [re;im]; NULL or m == 0
+ * restores the built-in initial guess */
+int bloch_set_initial_vectors(bloch_handle h, int m, const double *vecs);
+/* Solve() (maxwell_bloch.hpp:176, .cpp:809-825) */
+int bloch_solve(bloch_handle h);
+/* GetEigenvalues (maxwell_bloch.hpp:179, .cpp:1052-1076): ascending lambda = omega^2, one per
+ * complex band (the C++ wrapper duplicates them to the reference's real-mode count) */
+int bloch_get_eigenvalues(bloch_handle h, double *lambda, int n);
+/* GetEigenvectorE / GetEigenvectorB (maxwell_bloch.hpp:187-197, .cpp:1371-1458): copy-out */
+int bloch_get_eigenvector_E(bloch_handle h, int i, double *re, double *im);
+int bloch_get_eigenvector_B(bloch_handle h, int i, double *re, double *im);
+
+typedef struct {
+  int iterations;          /* outer LOBPCG iterations of the last solve */
+  int converged_bands;
+  int inner_iterations;    /* total projector CG iterations */
+  double solve_seconds;    /* device time of the last Solve() */
+  double max_residual;     /* max_j || A x_j - lambda_j M x_j ||_2 over the wanted bands */
+  int64_t applies_A;       /* number of single-vector operator applications */
+  int64_t kernel_launches; /* kernels launched by this handle since creation */
+} bloch_stats;
+int bloch_get_stats(bloch_handle h, bloch_stats *st);                   /* GetSolverStats */
+
+/* GetAOperator()/GetMOperator()->Mult (maxwell_bloch.hpp:199-200) on nvec vectors of length
+ * 2N [re;im], HOST pointers (copies inside) */
+int bloch_apply_A(bloch_handle h, const double *x, double *y, int nvec);
+int bloch_apply_M(bloch_handle h, const double *x, double *y, int nvec);
+/* GetSubSpaceProjector()->Mult (maxwell_bloch.hpp:203, .cpp:2280-2290) */
+int bloch_apply_projector(bloch_handle h, const double *x, double *y, int nvec);
+/* C = [[T12, beta Z12], [-beta Z12, T12]] apply (maxwell_bloch.cpp:471-490): ND 2N -> RT 2N_rt */
+int bloch_apply_C(bloch_handle h, const double *x, double *y, int nvec);
+
+/* Device-resident variants: x, y are DEVICE pointers to the handle's internal block layout,
+ * interleaved complex [N][nvec] (element (dof i, vector v) at 2*(i*nvec+v), re then im).
+ * They launch on the handle's stream and do not synchronise. */
+int bloch_apply_A_device(bloch_handle h, const double *d_x, double *d_y, int nvec);
+int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nvec);
+/* layout conversion helpers between the boundary layout and the block layout (device ptrs) */
+int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
+int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
+
+/* Test hook for the H1 <-> ND operators inside the projector (MaxwellBlochWaveProjector::Setup,
+ * maxwell_bloch.cpp:2053-2158), host vectors [re;im]:
+ *   mode 0: y(2 N_h1) = S0 x(2 N_h1), S0 = G^T M G;  mode 1: y(2 N) = G x(2 N_h1);
+ *   mode 2: y(2 N_h1) = G^T M x(2 N) */
+int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y, int nvec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOCH_B200_H */

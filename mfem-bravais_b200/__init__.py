@@ -1,0 +1,10 @@
+"""B200-native Bloch Maxwell eigen path (drop-in for mfem-bravais' MaxwellBlochWaveEquation).
+
+The compute path lives in csrc/ (CUDA, sm_100a) behind the C ABI of include/bloch_b200.h;
+this package is the thin host-side mirror used by the tests, bench.py and the Python driver.
+There is no CPU fallback: creating an equation without the built library or without a CUDA
+device raises.
+"""
+from .capi import lib, lib_path, BlochError, LATTICE_TYPES  # noqa: F401
+from .equation import BravaisLattice, MaxwellBlochWaveEquation  # noqa: F401
+from .dispersion import k_path, sphere_eps, dispersion_sweep  # noqa: F401

@@ -1,0 +1,681 @@
+// Eigenproblem object + C ABI (include/bloch_b200.h).  Host logic mirrors
+// MaxwellBlochWaveEquation (maxwell/maxwell_bloch.cpp): constructor :34-140, SetKappa :200-210,
+// Setup :337-620, GetEigenvalues :1052-1076, GetEigenvectorE/B :1371-1458.
+#include "core.hpp"
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/bloch_b200.h"
+
+using namespace bloch_b200;
+using D2 = double2;
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END                                                   \
+  }                                                               \
+  catch (const CudaError &e) { g_last_error = e.what(); return BLOCH_ERR_CUDA; }      \
+  catch (const std::invalid_argument &e) { g_last_error = e.what(); return BLOCH_ERR_ARG; } \
+  catch (const std::exception &e) { g_last_error = e.what(); return BLOCH_ERR_INTERNAL; }   \
+  catch (...) { g_last_error = "unknown error"; return BLOCH_ERR_INTERNAL; }
+#define REQUIRE(cond, msg) \
+  do { if (!(cond)) throw std::invalid_argument(msg); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// handle internals
+// ------------------------------------------------------------------------------------------
+static void build_kernel_maps(bloch_handle_s *h) {
+  const int p = h->p, Q = p + 1, ne = h->mesh.n_elem;
+  const DofMaps &M = h->maps;
+  std::vector<int> perm_nd(M.l_nd), perm_rt(M.l_rt), perm_h1(M.l_h1);
+  const int nb = p * Q * Q, rb = p * p * Q;
+  for (int c = 0; c < 3; c++) {
+    for (int o = 0; o < p; o++)
+      for (int j1 = 0; j1 < Q; j1++)
+        for (int j2 = 0; j2 < Q; j2++) {
+          int a[3], dims[3] = {Q, Q, Q};
+          dims[c] = p;
+          a[c] = o; a[(c + 1) % 3] = j1; a[(c + 2) % 3] = j2;
+          perm_nd[c * nb + (o * Q + j1) * Q + j2] = c * nb + a[0] + dims[0] * (a[1] + dims[1] * a[2]);
+        }
+    for (int j = 0; j < Q; j++)
+      for (int o1 = 0; o1 < p; o1++)
+        for (int o2 = 0; o2 < p; o2++) {
+          int a[3], dims[3] = {p, p, p};
+          dims[c] = Q;
+          a[c] = j; a[(c + 1) % 3] = o1; a[(c + 2) % 3] = o2;
+          perm_rt[c * rb + (j * p + o1) * p + o2] = c * rb + a[0] + dims[0] * (a[1] + dims[1] * a[2]);
+        }
+  }
+  for (int i0 = 0; i0 < Q; i0++)
+    for (int i1 = 0; i1 < Q; i1++)
+      for (int i2 = 0; i2 < Q; i2++) perm_h1[(i0 * Q + i1) * Q + i2] = i0 + Q * (i1 + Q * i2);
+  std::vector<int32_t> knd((size_t)ne * M.l_nd), krt((size_t)ne * M.l_rt), kh1((size_t)ne * M.l_h1);
+  for (int e = 0; e < ne; e++) {
+    for (int k = 0; k < M.l_nd; k++) knd[(size_t)e * M.l_nd + k] = M.nd[(size_t)e * M.l_nd + perm_nd[k]];
+    for (int k = 0; k < M.l_rt; k++) krt[(size_t)e * M.l_rt + k] = M.rt[(size_t)e * M.l_rt + perm_rt[k]];
+    for (int k = 0; k < M.l_h1; k++) kh1[(size_t)e * M.l_h1 + k] = M.h1[(size_t)e * M.l_h1 + perm_h1[k]];
+  }
+  h->d_map_nd.upload(knd, h->stream);
+  h->d_map_rt.upload(krt, h->stream);
+  h->d_map_h1.upload(kh1, h->stream);
+  h->d_cls.upload(h->mesh.cls, h->stream);
+  BLOCH_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+static void fill_tabs(const Basis1D &B, Tabs &T) {
+  std::memset(&T, 0, sizeof(T));
+  const int p = B.p, q = p + 1;
+  for (int r = 0; r < q; r++)
+    for (int j = 0; j < q; j++) { T.TI[r][j] = B.TI[r * q + j]; T.TIinv[r][j] = B.TIinv[r * q + j]; }
+  for (int a = 0; a < p; a++)
+    for (int r = 0; r < q; r++) T.Dt[a][r] = B.Dt[a * q + r];
+  for (int r = 0; r < q; r++) T.om[r] = B.om[r];
+}
+
+static void class_params(const double *J, const double kappa[3], double out[kClassParDoubles]) {
+  double JtJ[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += J[3 * k + i] * J[3 * k + j];
+      JtJ[3 * i + j] = s;
+    }
+  const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) +
+                     J[2] * (J[3] * J[7] - J[4] * J[6]);
+  for (int d = 0; d < 3; d++) out[d] = J[d] * kappa[0] + J[3 + d] * kappa[1] + J[6 + d] * kappa[2];
+  for (int k = 0; k < 9; k++) out[3 + k] = JtJ[k] / det;
+  // H = det * (J^T J)^-1 via the adjugate of the symmetric JtJ (det(JtJ) = det^2)
+  const double *a = JtJ;
+  double adj[9];
+  adj[0] = a[4] * a[8] - a[5] * a[7]; adj[1] = a[2] * a[7] - a[1] * a[8]; adj[2] = a[1] * a[5] - a[2] * a[4];
+  adj[3] = a[5] * a[6] - a[3] * a[8]; adj[4] = a[0] * a[8] - a[2] * a[6]; adj[5] = a[2] * a[3] - a[0] * a[5];
+  adj[6] = a[3] * a[7] - a[4] * a[6]; adj[7] = a[1] * a[6] - a[0] * a[7]; adj[8] = a[0] * a[4] - a[1] * a[3];
+  for (int k = 0; k < 9; k++) out[12 + k] = adj[k] / det;
+}
+
+// element-local diagonals of A, M1 and S0 per class, obtained by running the production kernels
+// on a probe problem (one private copy of the element per local unit vector)
+static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vector<double> &dM,
+                            std::vector<double> &dS0) {
+  const int nc = h->mesh.n_class, Ln = h->L_nd, Lh = h->L_h1;
+  cudaStream_t s = h->stream;
+  auto run = [&](int L, bool h1space, std::vector<double> *outA, std::vector<double> *outM) {
+    const int ne = nc * L;
+    std::vector<int32_t> map((size_t)ne * L);
+    std::vector<int> cls(ne);
+    std::vector<double> one(ne, 1.0);
+    std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
+    for (int c = 0; c < nc; c++)
+      for (int k = 0; k < L; k++) {
+        const int e = c * L + k;
+        cls[e] = c;
+        for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
+        x[(size_t)e * L + k].x = 1.0;
+      }
+    DevBuf<int32_t> dmap; DevBuf<int> dcls; DevBuf<double> done; DevBuf<D2> dx, dy;
+    dmap.upload(map, s); dcls.upload(cls, s); done.upload(one, s); dx.upload(x, s);
+    dy.alloc(x.size());
+    ElemData E = h->E;
+    E.n_elem = ne; E.cls = dcls.p; E.eps = done.p; E.muinv = done.p;
+    if (h1space) E.map_h1 = dmap.p; else E.map_nd = dmap.p;
+    std::vector<D2> y(x.size());
+    auto fetch = [&](std::vector<double> *out) {
+      BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * y.size(), cudaMemcpyDeviceToHost, s));
+      BLOCH_CUDA(cudaStreamSynchronize(s));
+      out->resize((size_t)nc * L);
+      for (int c = 0; c < nc; c++)
+        for (int k = 0; k < L; k++) (*out)[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
+    };
+    if (h1space) {
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(launch_h1_op(h->p, 0, h->tabs, E, dx.p, 1, dy.p, 1, 1, s));
+      h->count_launch();
+      fetch(outA);
+    } else {
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 1.0, 0.0, s));
+      h->count_launch();
+      fetch(outA);
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 0.0, 1.0, s));
+      h->count_launch();
+      fetch(outM);
+    }
+  };
+  run(Ln, false, &dA, &dM);
+  run(Lh, true, &dS0, nullptr);
+}
+
+void bloch_handle_s::setup() {
+  if (device < 0) throw std::invalid_argument("topology-only handle (BLOCH_DEVICE_NONE): no compute available");
+  BLOCH_CUDA(cudaSetDevice(device));
+  if (dirty_coef) {
+    d_eps.upload(eps, stream);
+    d_muinv.upload(muinv, stream);
+  }
+  E.n_elem = mesh.n_elem;
+  E.n_class = mesh.n_class;
+  E.cls = d_cls.p;
+  E.eps = d_eps.p;
+  E.muinv = d_muinv.p;
+  E.map_nd = d_map_nd.p;
+  E.map_h1 = d_map_h1.p;
+  E.map_rt = d_map_rt.p;
+  if (dirty_kappa) {
+    std::vector<double> cp((size_t)mesh.n_class * kClassParDoubles);
+    for (int c = 0; c < mesh.n_class; c++) class_params(&mesh.J[9 * c], kappa, &cp[(size_t)c * kClassParDoubles]);
+    d_cpar.upload(cp, stream);
+    beta = std::sqrt(kappa[0] * kappa[0] + kappa[1] * kappa[1] + kappa[2] * kappa[2]);
+  }
+  E.cpar = d_cpar.p;
+  if (dirty_kappa || dirty_coef) {
+    // Jacobi diagonals of A, M and S0 = G^H M G (element-local diagonals from a probe launch)
+    std::vector<double> dA, dM, dS0;
+    probe_diagonals(this, dA, dM, dS0);
+    DevBuf<double> dl;
+    d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0);
+    BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagM.p, 0, sizeof(double) * N, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagS0.p, 0, sizeof(double) * N0, stream));
+    dl.upload(dA, stream);
+    BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagA.p, stream));
+    BLOCH_CUDA(cudaStreamSynchronize(stream));
+    dl.upload(dM, stream);
+    BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagM.p, stream));
+    BLOCH_CUDA(cudaStreamSynchronize(stream));
+    dl.upload(dS0, stream);
+    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagS0.p, stream));
+    BLOCH_CUDA(cudaStreamSynchronize(stream));
+    count_launch(3);
+  }
+  dirty_coef = dirty_kappa = false;
+}
+
+void bloch_handle_s::apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm) {
+  BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * (size_t)N * nvec, stream));
+  BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, nvec, y, nvec, nvec, ca, cm, stream));
+  count_launch();
+  if (ca != 0.0) stats.applies_A += nvec;
+}
+void bloch_handle_s::apply_h1(int mode, const D2 *x, D2 *y, int nvec) {
+  if (mode != 1) BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * (size_t)N0 * nvec, stream));
+  else BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * (size_t)N * nvec, stream));
+  BLOCH_CUDA(launch_h1_op(p, mode, tabs, E, x, nvec, y, nvec, nvec, stream));
+  count_launch();
+}
+void bloch_handle_s::apply_curl(const D2 *x, D2 *y, int nvec) {
+  BLOCH_CUDA(launch_curl(p, tabs, E, x, nvec, y, nvec, nvec, stream));
+  count_launch();
+}
+
+static bloch_handle_s *make_handle(const std::vector<std::array<double, 3>> &vert,
+                                   const std::vector<std::array<int, 8>> &hex, const double rec[9],
+                                   int n_sub, int order, int device) {
+  REQUIRE(order >= 1 && order <= 3, "order must be 1, 2 or 3");
+  REQUIRE(n_sub >= 1, "n_sub must be >= 1");
+  REQUIRE((int)hex.size() <= kMaxClasses, "too many coarse hexes (element classes)");
+  const bool host_only = (device == BLOCH_DEVICE_NONE);
+  if (!host_only) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw CudaError("no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) BLOCH_CUDA(cudaGetDevice(&device));
+    REQUIRE(device < ndev, "device index out of range");
+    BLOCH_CUDA(cudaSetDevice(device));
+  }
+  bloch_handle_s *h = new bloch_handle_s();
+  try {
+    h->device = device;
+    if (!host_only) {
+      BLOCH_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+      h->stream = h->own_stream;
+    }
+    h->p = order;
+    build_mesh(vert, hex, rec, n_sub, h->mesh);
+    build_dofmaps(h->mesh, order, h->maps);
+    h->N = h->maps.n_nd; h->N0 = h->maps.n_h1; h->Nrt = h->maps.n_rt;
+    h->L_nd = h->maps.l_nd; h->L_h1 = h->maps.l_h1; h->L_rt = h->maps.l_rt;
+    h->basis = make_basis(order);
+    fill_tabs(h->basis, h->tabs);
+    h->eps.assign(h->mesh.n_elem, 1.0);
+    h->muinv.assign(h->mesh.n_elem, 1.0);
+    if (!host_only) build_kernel_maps(h);
+  } catch (...) {
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    throw;
+  }
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *bloch_last_error(void) { return g_last_error.c_str(); }
+int bloch_version(void) { return 100; }
+int bloch_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---- lattice ----
+int bloch_lattice_create(bloch_lattice *out, int type, double a, double b, double c, double alpha,
+                         double beta, double gamma) {
+  API_BEGIN
+  REQUIRE(out, "null output");
+  bravais::BravaisLattice *L = bravais::BravaisLatticeFactory((bravais::BRAVAIS_LATTICE_TYPE)type, a, b, c, alpha, beta, gamma);
+  REQUIRE(L, "lattice type not available (CUB=7, FCC=8, BCC=9)");
+  *out = new bloch_lattice_s{L};
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_destroy(bloch_lattice lat) {
+  if (lat) { delete lat->lat; delete lat; }
+  return BLOCH_OK;
+}
+static int copy_label(const std::string &s, char *buf, int buflen) {
+  if (buf && buflen > 0) {
+    std::strncpy(buf, s.c_str(), buflen - 1);
+    buf[buflen - 1] = 0;
+  }
+  return (int)s.size();
+}
+int bloch_lattice_label(bloch_lattice lat, char *buf, int buflen) {
+  API_BEGIN
+  REQUIRE(lat, "null lattice");
+  copy_label(lat->lat->GetLatticeTypeLabel(), buf, buflen);
+  return BLOCH_OK;
+  API_END
+}
+double bloch_lattice_volume(bloch_lattice lat) { return lat ? lat->lat->GetUnitCellVolume() : 0.0; }
+int bloch_lattice_vectors(bloch_lattice lat, double lat9[9], double rec9[9]) {
+  API_BEGIN
+  REQUIRE(lat, "null lattice");
+  std::vector<bravais::Vec3> a, b;
+  lat->lat->GetLatticeVectors(a);
+  lat->lat->GetReciprocalLatticeVectors(b);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      if (lat9) lat9[3 * i + j] = a[i][j];
+      if (rec9) rec9[3 * i + j] = b[i][j];
+    }
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_num_translations(bloch_lattice lat) {
+  if (!lat) return BLOCH_ERR_ARG;
+  std::vector<bravais::Vec3> t;
+  lat->lat->GetTranslationVectors(t);
+  return (int)t.size();
+}
+int bloch_lattice_translations(bloch_lattice lat, double *trn, double *radii) {
+  API_BEGIN
+  REQUIRE(lat, "null lattice");
+  std::vector<bravais::Vec3> t;
+  std::vector<double> r;
+  lat->lat->GetTranslationVectors(t);
+  lat->lat->GetFaceRadii(r);
+  for (size_t i = 0; i < t.size(); i++) {
+    if (trn) for (int j = 0; j < 3; j++) trn[3 * i + j] = t[i][j];
+    if (radii) radii[i] = r[i];
+  }
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_num_symmetry_points(bloch_lattice lat) { return lat ? (int)lat->lat->GetNumberSymmetryPoints() : BLOCH_ERR_ARG; }
+int bloch_lattice_symmetry_point(bloch_lattice lat, int i, double kappa[3], char *label, int buflen) {
+  API_BEGIN
+  REQUIRE(lat && i >= 0 && i < (int)lat->lat->GetNumberSymmetryPoints(), "bad symmetry point index");
+  bravais::Vec3 k;
+  lat->lat->GetSymmetryPoint(i, k);
+  if (kappa) for (int j = 0; j < 3; j++) kappa[j] = k[j];
+  copy_label(lat->lat->GetSymmetryPointLabel(i), label, buflen);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_symmetry_point_index(bloch_lattice lat, const char *label) {
+  if (!lat || !label) return -1;
+  return lat->lat->GetSymmetryPointIndex(label);
+}
+int bloch_lattice_num_paths(bloch_lattice lat) { return lat ? (int)lat->lat->GetNumberPaths() : BLOCH_ERR_ARG; }
+int bloch_lattice_num_path_segments(bloch_lattice lat, int p) {
+  if (!lat || p < 0 || p >= (int)lat->lat->GetNumberPaths()) return BLOCH_ERR_ARG;
+  return (int)lat->lat->GetNumberPathSegments(p);
+}
+int bloch_lattice_path_segment(bloch_lattice lat, int p, int s, int *e0, int *e1) {
+  API_BEGIN
+  REQUIRE(lat && p >= 0 && p < (int)lat->lat->GetNumberPaths(), "bad path index");
+  REQUIRE(s >= 0 && s < (int)lat->lat->GetNumberPathSegments(p), "bad segment index");
+  int a, b;
+  lat->lat->GetPathSegmentEndPointIndices(p, s, a, b);
+  if (e0) *e0 = a;
+  if (e1) *e1 = b;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_intermediate_point(bloch_lattice lat, int p, int s, double kappa[3], char *label, int buflen) {
+  API_BEGIN
+  REQUIRE(lat && p >= 0 && p < (int)lat->lat->GetNumberPaths(), "bad path index");
+  REQUIRE(s >= 0 && s < (int)lat->lat->GetNumberPathSegments(p), "bad segment index");
+  bravais::Vec3 k;
+  lat->lat->GetIntermediatePoint(p, s, k);
+  if (kappa) for (int j = 0; j < 3; j++) kappa[j] = k[j];
+  copy_label(lat->lat->GetIntermediatePointLabel(p, s), label, buflen);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_lattice_map_to_primitive_cell(bloch_lattice lat, const double pt[3], double ipt[3]) {
+  if (!lat || !pt || !ipt) return BLOCH_ERR_ARG;
+  bravais::Vec3 a{pt[0], pt[1], pt[2]}, b;
+  bool m = lat->lat->MapToPrimitiveCell(a, b);
+  for (int j = 0; j < 3; j++) ipt[j] = b[j];
+  return m ? 1 : 0;
+}
+
+// ---- eigenproblem object ----
+int bloch_create(bloch_handle *out, bloch_lattice lat, int n_sub, int order, int device) {
+  API_BEGIN
+  REQUIRE(out && lat, "null argument");
+  std::vector<bravais::Vec3> b;
+  lat->lat->GetReciprocalLatticeVectors(b);
+  double rec[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) rec[3 * i + j] = b[i][j];
+  *out = make_handle(lat->lat->WignerSeitzVertices(), lat->lat->WignerSeitzHexes(), rec, n_sub, order, device);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_create_from_hexes(bloch_handle *out, int n_vert, const double *xyz, int n_hex, const int *hex,
+                            const double rec9[9], int n_sub, int order, int device) {
+  API_BEGIN
+  REQUIRE(out && xyz && hex && rec9 && n_vert > 0 && n_hex > 0, "bad mesh description");
+  std::vector<std::array<double, 3>> v(n_vert);
+  std::vector<std::array<int, 8>> hx(n_hex);
+  for (int i = 0; i < n_vert; i++) v[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  for (int i = 0; i < n_hex; i++)
+    for (int k = 0; k < 8; k++) {
+      REQUIRE(hex[8 * i + k] >= 0 && hex[8 * i + k] < n_vert, "hex vertex index out of range");
+      hx[i][k] = hex[8 * i + k];
+    }
+  *out = make_handle(v, hx, rec9, n_sub, order, device);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_destroy(bloch_handle h) {
+  if (!h) return BLOCH_OK;
+  if (h->device < 0) { delete h; return BLOCH_OK; }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaStream_t own = h->own_stream;
+  delete h;
+  if (own) cudaStreamDestroy(own);
+  return BLOCH_OK;
+}
+int bloch_set_stream(bloch_handle h, void *s) {
+  if (!h || h->device < 0) return BLOCH_ERR_ARG;
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return BLOCH_OK;
+}
+int bloch_num_elements(bloch_handle h, int64_t *n_elem, int *n_class) {
+  if (!h) return BLOCH_ERR_ARG;
+  if (n_elem) *n_elem = h->mesh.n_elem;
+  if (n_class) *n_class = h->mesh.n_class;
+  return BLOCH_OK;
+}
+int bloch_num_dofs(bloch_handle h, int64_t *n_nd, int64_t *n_rt, int64_t *n_h1) {
+  if (!h) return BLOCH_ERR_ARG;
+  if (n_nd) *n_nd = h->N;
+  if (n_rt) *n_rt = h->Nrt;
+  if (n_h1) *n_h1 = h->N0;
+  return BLOCH_OK;
+}
+int bloch_mesh_counts(bloch_handle h, int64_t *nv, int64_t *ne, int64_t *nf, double *vol) {
+  if (!h) return BLOCH_ERR_ARG;
+  if (nv) *nv = h->mesh.n_vert;
+  if (ne) *ne = h->mesh.n_edge;
+  if (nf) *nf = h->mesh.n_face;
+  if (vol) *vol = h->mesh.volume;
+  return BLOCH_OK;
+}
+int bloch_element_centers(bloch_handle h, double *xyz) {
+  if (!h || !xyz) return BLOCH_ERR_ARG;
+  std::vector<double> c;
+  h->mesh.centers(c);
+  std::memcpy(xyz, c.data(), sizeof(double) * c.size());
+  return BLOCH_OK;
+}
+int bloch_element_geometry(bloch_handle h, double *x0, int *cls, double *J) {
+  if (!h) return BLOCH_ERR_ARG;
+  if (x0) std::memcpy(x0, h->mesh.x0.data(), sizeof(double) * h->mesh.x0.size());
+  if (cls) std::memcpy(cls, h->mesh.cls.data(), sizeof(int) * h->mesh.cls.size());
+  if (J) std::memcpy(J, h->mesh.J.data(), sizeof(double) * h->mesh.J.size());
+  return BLOCH_OK;
+}
+int bloch_local_size(bloch_handle h, int space) {
+  if (!h) return BLOCH_ERR_ARG;
+  return space == 0 ? h->L_h1 : (space == 1 ? h->L_nd : (space == 2 ? h->L_rt : BLOCH_ERR_ARG));
+}
+int bloch_get_dofmap(bloch_handle h, int space, int32_t *out) {
+  if (!h || !out || space < 0 || space > 2) return BLOCH_ERR_ARG;
+  const std::vector<int32_t> &m = space == 0 ? h->maps.h1 : (space == 1 ? h->maps.nd : h->maps.rt);
+  std::memcpy(out, m.data(), sizeof(int32_t) * m.size());
+  return BLOCH_OK;
+}
+int bloch_set_eps(bloch_handle h, const double *eps) {
+  API_BEGIN
+  REQUIRE(h && eps, "null argument");
+  for (int e = 0; e < h->mesh.n_elem; e++) REQUIRE(eps[e] > 0.0, "eps must be positive");
+  h->eps.assign(eps, eps + h->mesh.n_elem);
+  h->dirty_coef = true;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_set_muinv(bloch_handle h, const double *mu) {
+  API_BEGIN
+  REQUIRE(h && mu, "null argument");
+  for (int e = 0; e < h->mesh.n_elem; e++) REQUIRE(mu[e] > 0.0, "1/mu must be positive");
+  h->muinv.assign(mu, mu + h->mesh.n_elem);
+  h->dirty_coef = true;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_set_kappa(bloch_handle h, const double kappa[3]) {
+  if (!h || !kappa) return BLOCH_ERR_ARG;
+  for (int i = 0; i < 3; i++) h->kappa[i] = kappa[i];
+  h->dirty_kappa = true;
+  return BLOCH_OK;
+}
+int bloch_set_num_bands(bloch_handle h, int n) {
+  API_BEGIN
+  REQUIRE(h && n >= 1 && n <= 64, "number of bands must be in [1,64]");
+  if (n != h->nbands) h->have_vectors = 0;
+  h->nbands = n;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_set_tol(bloch_handle h, double tol, int max_iter) {
+  API_BEGIN
+  REQUIRE(h && tol > 0.0 && max_iter > 0, "bad tolerance / iteration limit");
+  h->tol = tol;
+  h->max_iter = max_iter;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_setup(bloch_handle h) {
+  API_BEGIN
+  REQUIRE(h, "null handle");
+  h->setup();
+  return BLOCH_OK;
+  API_END
+}
+int bloch_set_initial_vectors(bloch_handle h, int m, const double *vecs) {
+  API_BEGIN
+  REQUIRE(h, "null handle");
+  if (m <= 0 || !vecs) { h->n_init = 0; h->init_vecs.clear(); return BLOCH_OK; }
+  h->n_init = m;
+  h->init_vecs.assign(vecs, vecs + (size_t)m * 2 * h->N);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_solve(bloch_handle h) {
+  API_BEGIN
+  REQUIRE(h, "null handle");
+  h->setup();
+  h->solve();
+  return h->stats.converged >= h->nbands ? BLOCH_OK : BLOCH_ERR_NOCONV;
+  API_END
+}
+int bloch_get_eigenvalues(bloch_handle h, double *lambda, int n) {
+  API_BEGIN
+  REQUIRE(h && lambda, "null argument");
+  REQUIRE(n >= 0 && n <= (int)h->eigenvalues.size(), "more eigenvalues requested than computed");
+  std::memcpy(lambda, h->eigenvalues.data(), sizeof(double) * n);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_get_stats(bloch_handle h, bloch_stats *st) {
+  if (!h || !st) return BLOCH_ERR_ARG;
+  st->iterations = h->stats.iterations;
+  st->converged_bands = h->stats.converged;
+  st->inner_iterations = h->stats.inner_iterations;
+  st->solve_seconds = h->stats.seconds;
+  st->max_residual = h->stats.max_residual;
+  st->applies_A = h->stats.applies_A;
+  st->kernel_launches = h->stats.launches;
+  return BLOCH_OK;
+}
+
+// host-pointer operator applications: H2D, pack, kernel, unpack, D2H
+enum { OP_A, OP_M, OP_PROJ, OP_C };
+static int apply_host(bloch_handle h, int op, const double *x, double *y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && x && y && nvec >= 1, "bad argument");
+  h->setup();
+  const long N = h->N, Nout = (op == OP_C) ? h->Nrt : h->N;
+  cudaStream_t s = h->stream;
+  h->d_io_a.alloc((size_t)2 * N * nvec);
+  h->d_io_b.alloc((size_t)2 * Nout * nvec);
+  h->d_blk_a.alloc((size_t)N * nvec);
+  h->d_blk_b.alloc((size_t)Nout * nvec);
+  BLOCH_CUDA(cudaMemcpyAsync(h->d_io_a.p, x, sizeof(double) * 2 * N * nvec, cudaMemcpyHostToDevice, s));
+  BLOCH_CUDA(launch_pack(h->d_io_a.p, h->d_blk_a.p, N, nvec, s));
+  h->count_launch();
+  switch (op) {
+    case OP_A: h->apply_nd(h->d_blk_a.p, h->d_blk_b.p, nvec, 1.0, 0.0); break;
+    case OP_M: h->apply_nd(h->d_blk_a.p, h->d_blk_b.p, nvec, 0.0, 1.0); break;
+    case OP_C: h->apply_curl(h->d_blk_a.p, h->d_blk_b.p, nvec); break;
+    case OP_PROJ:
+      BLOCH_CUDA(cudaMemcpyAsync(h->d_blk_b.p, h->d_blk_a.p, sizeof(D2) * N * nvec, cudaMemcpyDeviceToDevice, s));
+      h->project(h->d_blk_b.p, nvec, 1e-13, nullptr);
+      break;
+  }
+  BLOCH_CUDA(launch_unpack(h->d_blk_b.p, h->d_io_b.p, Nout, nvec, s));
+  h->count_launch();
+  BLOCH_CUDA(cudaMemcpyAsync(y, h->d_io_b.p, sizeof(double) * 2 * Nout * nvec, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+int bloch_apply_A(bloch_handle h, const double *x, double *y, int nvec) { return apply_host(h, OP_A, x, y, nvec); }
+int bloch_apply_M(bloch_handle h, const double *x, double *y, int nvec) { return apply_host(h, OP_M, x, y, nvec); }
+int bloch_apply_projector(bloch_handle h, const double *x, double *y, int nvec) { return apply_host(h, OP_PROJ, x, y, nvec); }
+int bloch_apply_C(bloch_handle h, const double *x, double *y, int nvec) { return apply_host(h, OP_C, x, y, nvec); }
+
+int bloch_apply_A_device(bloch_handle h, const double *d_x, double *d_y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && d_x && d_y && nvec >= 1, "bad argument");
+  if (h->device < 0 || h->dirty_coef || h->dirty_kappa) h->setup();
+  h->apply_nd((const D2 *)d_x, (D2 *)d_y, nvec, 1.0, 0.0);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && d_x && d_y && nvec >= 1, "bad argument");
+  if (h->device < 0 || h->dirty_coef || h->dirty_kappa) h->setup();
+  h->apply_nd((const D2 *)d_x, (D2 *)d_y, nvec, 0.0, 1.0);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec) {
+  API_BEGIN
+  REQUIRE(h && d_reim && d_block && nvec >= 1 && h->device >= 0, "bad argument");
+  BLOCH_CUDA(launch_pack(d_reim, (D2 *)d_block, h->N, nvec, h->stream));
+  h->count_launch();
+  return BLOCH_OK;
+  API_END
+}
+int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec) {
+  API_BEGIN
+  REQUIRE(h && d_reim && d_block && nvec >= 1 && h->device >= 0, "bad argument");
+  BLOCH_CUDA(launch_unpack((const D2 *)d_block, d_reim, h->N, nvec, h->stream));
+  h->count_launch();
+  return BLOCH_OK;
+  API_END
+}
+
+// test hook: H1 <-> ND operators of the projector on host vectors.
+// mode 0: y(2 N0) = S0 x(2 N0); mode 1: y(2 N) = G x(2 N0); mode 2: y(2 N0) = G^H M x(2 N)
+int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && x && y && nvec >= 1 && mode >= 0 && mode <= 2, "bad argument");
+  h->setup();
+  const long nin = (mode == 2) ? h->N : h->N0, nout = (mode == 1) ? h->N : h->N0;
+  cudaStream_t s = h->stream;
+  DevBuf<double> ia, ib;
+  DevBuf<D2> ba, bb;
+  ia.alloc((size_t)2 * nin * nvec); ib.alloc((size_t)2 * nout * nvec);
+  ba.alloc((size_t)nin * nvec); bb.alloc((size_t)nout * nvec);
+  BLOCH_CUDA(cudaMemcpyAsync(ia.p, x, sizeof(double) * 2 * nin * nvec, cudaMemcpyHostToDevice, s));
+  BLOCH_CUDA(launch_pack(ia.p, ba.p, nin, nvec, s));
+  h->apply_h1(mode, ba.p, bb.p, nvec);
+  BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
+  BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+int bloch_get_eigenvector_E(bloch_handle h, int i, double *re, double *im) {
+  API_BEGIN
+  REQUIRE(h && re && im, "null argument");
+  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  BLOCH_CUDA(cudaSetDevice(h->device));
+  std::vector<D2> col(h->N);
+  BLOCH_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(D2), h->d_X.p + i, sizeof(D2) * h->block, sizeof(D2), h->N,
+                               cudaMemcpyDeviceToHost, h->stream));
+  BLOCH_CUDA(cudaStreamSynchronize(h->stream));
+  for (long k = 0; k < h->N; k++) { re[k] = col[k].x; im[k] = col[k].y; }
+  return BLOCH_OK;
+  API_END
+}
+int bloch_get_eigenvector_B(bloch_handle h, int i, double *re, double *im) {
+  API_BEGIN
+  REQUIRE(h && re && im, "null argument");
+  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  BLOCH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DevBuf<D2> e, b;
+  e.alloc(h->N); b.alloc(h->Nrt);
+  BLOCH_CUDA(cudaMemcpy2DAsync(e.p, sizeof(D2), h->d_X.p + i, sizeof(D2) * h->block, sizeof(D2), h->N,
+                               cudaMemcpyDeviceToDevice, s));
+  h->apply_curl(e.p, b.p, 1);
+  std::vector<D2> col(h->Nrt);
+  BLOCH_CUDA(cudaMemcpyAsync(col.data(), b.p, sizeof(D2) * h->Nrt, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  // B = C E / sqrt|lambda| (maxwell_bloch.cpp:1432-1457).  In the reference's real block form
+  // C E = [Cr; Ci] and it returns Bi = block 0, Br = -block 1.
+  const double lam = std::fabs(h->eigenvalues[i]);
+  const double sc = lam > 0 ? 1.0 / std::sqrt(lam) : 1.0;
+  for (long k = 0; k < h->Nrt; k++) { im[k] = sc * col[k].x; re[k] = -sc * col[k].y; }
+  return BLOCH_OK;
+  API_END
+}
+
+}  // extern "C"

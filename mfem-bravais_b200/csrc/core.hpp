@@ -1,0 +1,110 @@
+// Internal definition of the eigenproblem object behind the C ABI (include/bloch_b200.h).
+// Mirrors the state of mfem::bloch::MaxwellBlochWaveEquation (maxwell/maxwell_bloch.hpp:236-390):
+// spaces, coefficients, kappa = beta*zeta, dirty flags, solver controls and results.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "basis.hpp"
+#include "bravais.hpp"
+#include "kernels.hpp"
+#include "mesh.hpp"
+
+struct bloch_lattice_s {
+  bloch_b200::bravais::BravaisLattice *lat = nullptr;
+};
+
+namespace bloch_b200 {
+
+struct CudaError : std::runtime_error {
+  explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+#define BLOCH_CUDA(call)                                                                     \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess)                                                                \
+      throw ::bloch_b200::CudaError(std::string(#call) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+template <class T>
+struct DevBuf {   // owning device buffer
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    BLOCH_CUDA(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+    n = count;
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) {
+    alloc(h.size());
+    BLOCH_CUDA(cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s));
+  }
+};
+
+struct SolverStats {
+  int iterations = 0, converged = 0, inner_iterations = 0;
+  double seconds = 0, max_residual = 0;
+  int64_t applies_A = 0, launches = 0;
+};
+
+}  // namespace bloch_b200
+
+struct bloch_handle_s {
+  using D2 = double2;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int p = 1;
+  bloch_b200::HexMesh mesh;
+  bloch_b200::DofMaps maps;
+  bloch_b200::Basis1D basis;
+  bloch_b200::Tabs tabs;
+  long N = 0, N0 = 0, Nrt = 0;
+  int L_nd = 0, L_h1 = 0, L_rt = 0;
+
+  std::vector<double> eps, muinv;
+  double kappa[3] = {0, 0, 0};
+  double beta = 0;
+  bool dirty_coef = true, dirty_kappa = true;
+
+  bloch_b200::DevBuf<int> d_cls;
+  bloch_b200::DevBuf<double> d_eps, d_muinv, d_cpar;
+  bloch_b200::DevBuf<int32_t> d_map_nd, d_map_h1, d_map_rt;
+  bloch_b200::DevBuf<double> d_diagA, d_diagM, d_diagS0;   // Jacobi diagonals (real)
+  bloch_b200::DevBuf<double> d_jac, d_jac0;                // 1/(diagA + sigma diagM), 1/diagS0
+  bloch_b200::ElemData E{};
+
+  // solver controls / results
+  int nbands = 10, block = 0, max_iter = 2000;
+  double tol = 1e-6;
+  double sigma = 0;                 // shift of the preconditioner A + sigma M
+  int cheb_degree = 8;
+  double lmaxA = 0;                 // estimate of lambda_max(D^-1 (A + sigma M))
+  std::vector<double> eigenvalues;  // ascending
+  bloch_b200::DevBuf<D2> d_X;       // eigenvectors, block layout [N][block]
+  int have_vectors = 0;             // number of valid columns in d_X
+  std::vector<double> init_vecs;    // user supplied [m][2N]
+  int n_init = 0;
+  bloch_b200::SolverStats stats;
+
+  // scratch for host-pointer entry points
+  bloch_b200::DevBuf<double> d_io_a, d_io_b;
+  bloch_b200::DevBuf<D2> d_blk_a, d_blk_b, d_blk_c;
+
+  void setup();                                 // Setup()
+  void apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm);   // y = ca A x + cm M x (zeroes y)
+  void apply_h1(int mode, const D2 *x, D2 *y, int nvec);               // zeroes y for modes 0, 2
+  void apply_curl(const D2 *x, D2 *y, int nvec);
+  void project(D2 *x, int nvec, double rel_tol, int *iters);           // in place x <- P x
+  void solve();
+  void count_launch(int n = 1) { stats.launches += n; }
+};

@@ -1,0 +1,230 @@
+// Small dense complex Hermitian algebra for the Rayleigh-Ritz step of the block eigensolver
+// (the reference delegates this to hypre's LOBPCG / LAPACK dsygv, meta_material_solver.cpp:3285).
+// Sizes are <= 3 * block (a few dozen), so clarity beats blocking.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+namespace bloch_b200 {
+namespace dense {
+
+using cplx = std::complex<double>;
+using Mat = std::vector<cplx>;   // row-major n x n (or n x m)
+
+// In-place lower Cholesky A = L L^H (upper part ignored / left untouched).  Returns false if a
+// pivot is <= tol * max diagonal.
+inline bool cholesky(int n, Mat &A, double tol = 1e-14) {
+  double dmax = 0;
+  for (int i = 0; i < n; i++) dmax = std::max(dmax, A[i * n + i].real());
+  for (int j = 0; j < n; j++) {
+    double d = A[j * n + j].real();
+    for (int k = 0; k < j; k++) d -= std::norm(A[j * n + k]);
+    if (!(d > tol * dmax)) return false;
+    d = std::sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      cplx s = A[i * n + j];
+      for (int k = 0; k < j; k++) s -= A[i * n + k] * std::conj(A[j * n + k]);
+      A[i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+
+// B <- L^-1 B L^-H for Hermitian B (full storage), L lower from cholesky()
+inline void reduce_to_standard(int n, const Mat &L, Mat &B) {
+  // X = L^-1 B  (forward substitution on columns)
+  for (int c = 0; c < n; c++)
+    for (int i = 0; i < n; i++) {
+      cplx s = B[i * n + c];
+      for (int k = 0; k < i; k++) s -= L[i * n + k] * B[k * n + c];
+      B[i * n + c] = s / L[i * n + i].real();
+    }
+  // Y = X L^-H : solve Y L^H = X row by row  (Y[r][i] = (X[r][i] - sum_{k<i} Y[r][k] conj(L[i][k])) / L[i][i])
+  for (int r = 0; r < n; r++)
+    for (int i = 0; i < n; i++) {
+      cplx s = B[r * n + i];
+      for (int k = 0; k < i; k++) s -= B[r * n + k] * std::conj(L[i * n + k]);
+      B[r * n + i] = s / L[i * n + i].real();
+    }
+  for (int i = 0; i < n; i++) {   // symmetrise
+    B[i * n + i] = B[i * n + i].real();
+    for (int j = i + 1; j < n; j++) {
+      cplx a = 0.5 * (B[i * n + j] + std::conj(B[j * n + i]));
+      B[i * n + j] = a;
+      B[j * n + i] = std::conj(a);
+    }
+  }
+}
+
+// C (n x m) <- L^-H C   (back substitution with the conjugate transpose of L)
+inline void back_transform(int n, int m, const Mat &L, Mat &C) {
+  for (int c = 0; c < m; c++)
+    for (int i = n - 1; i >= 0; i--) {
+      cplx s = C[i * m + c];
+      for (int k = i + 1; k < n; k++) s -= std::conj(L[k * n + i]) * C[k * m + c];
+      C[i * m + c] = s / L[i * n + i].real();
+    }
+}
+
+// Real symmetric tridiagonal QL with implicit shifts; d (diag, n), e (sub-diag, e[i] couples i and
+// i+1, e[n-1] unused); Z (n x n real, row-major) is post-multiplied by the rotations.
+inline bool tridiag_ql(int n, std::vector<double> &d, std::vector<double> &e, std::vector<double> &Z) {
+  for (int l = 0; l < n; l++) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; m++) {
+        double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+        if (std::fabs(e[m]) <= 2.3e-16 * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 200) return false;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; i--) {
+          double f = s * e[i], b = c * e[i];
+          r = std::hypot(f, g);
+          e[i + 1] = r;
+          if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+          s = f / r; c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - b;
+          for (int k = 0; k < n; k++) {
+            double f2 = Z[k * n + i + 1];
+            Z[k * n + i + 1] = s * Z[k * n + i] + c * f2;
+            Z[k * n + i] = c * Z[k * n + i] - s * f2;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  return true;
+}
+
+// Hermitian eigen-decomposition A = V diag(w) V^H, w ascending, V (n x n) columns = eigenvectors.
+// Householder tridiagonalisation, phase normalisation to a real tridiagonal, QL.
+inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V) {
+  Mat Q(n * n, cplx(0));
+  for (int i = 0; i < n; i++) Q[i * n + i] = 1.0;
+  std::vector<cplx> v(n), pv(n), qv(n);
+  for (int k = 0; k + 2 < n; k++) {
+    double xn = 0;
+    for (int i = k + 1; i < n; i++) xn += std::norm(A[i * n + k]);
+    xn = std::sqrt(xn);
+    double tail = 0;
+    for (int i = k + 2; i < n; i++) tail += std::norm(A[i * n + k]);
+    if (tail < 1e-300) continue;
+    cplx x0 = A[(k + 1) * n + k];
+    cplx ph = std::abs(x0) > 0 ? x0 / std::abs(x0) : cplx(1.0);
+    cplx alpha = -ph * xn;
+    double vn = 0;
+    for (int i = k + 1; i < n; i++) {
+      v[i] = A[i * n + k];
+      if (i == k + 1) v[i] -= alpha;
+      vn += std::norm(v[i]);
+    }
+    vn = std::sqrt(vn);
+    if (vn < 1e-300) continue;
+    for (int i = k + 1; i < n; i++) v[i] /= vn;
+    // A <- H A H with H = I - 2 v v^H on the trailing block (and the k-th row/column)
+    // column k / row k
+    {
+      cplx s = 0;
+      for (int i = k + 1; i < n; i++) s += std::conj(v[i]) * A[i * n + k];
+      for (int i = k + 1; i < n; i++) {
+        A[i * n + k] -= 2.0 * v[i] * s;
+        A[k * n + i] = std::conj(A[i * n + k]);
+      }
+    }
+    // trailing block: p = A v ; K = v^H p ; q = p - K v ; A -= 2 (v q^H + q v^H)
+    for (int i = k + 1; i < n; i++) {
+      cplx s = 0;
+      for (int j = k + 1; j < n; j++) s += A[i * n + j] * v[j];
+      pv[i] = s;
+    }
+    cplx K = 0;
+    for (int i = k + 1; i < n; i++) K += std::conj(v[i]) * pv[i];
+    for (int i = k + 1; i < n; i++) qv[i] = pv[i] - K * v[i];
+    for (int i = k + 1; i < n; i++)
+      for (int j = k + 1; j < n; j++)
+        A[i * n + j] -= 2.0 * (v[i] * std::conj(qv[j]) + qv[i] * std::conj(v[j]));
+    // Q <- Q H
+    for (int r = 0; r < n; r++) {
+      cplx s = 0;
+      for (int j = k + 1; j < n; j++) s += Q[r * n + j] * v[j];
+      for (int j = k + 1; j < n; j++) Q[r * n + j] -= 2.0 * s * std::conj(v[j]);
+    }
+  }
+  std::vector<double> d(n), e(n, 0.0);
+  std::vector<cplx> ph(n);
+  ph[0] = 1.0;
+  for (int i = 0; i < n; i++) d[i] = A[i * n + i].real();
+  for (int i = 0; i + 1 < n; i++) {
+    cplx ek = A[(i + 1) * n + i];
+    double a = std::abs(ek);
+    e[i] = a;
+    ph[i + 1] = a > 0 ? ph[i] * ek / a : ph[i];
+  }
+  std::vector<double> Z(n * n, 0.0);
+  for (int i = 0; i < n; i++) Z[i * n + i] = 1.0;
+  if (!tridiag_ql(n, d, e, Z)) return false;
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; i++) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](int a, int b) { return d[a] < d[b]; });
+  w.resize(n);
+  V.assign(n * n, cplx(0));
+  for (int c = 0; c < n; c++) {
+    const int src = ord[c];
+    w[c] = d[src];
+    for (int r = 0; r < n; r++) {
+      cplx s = 0;
+      for (int j = 0; j < n; j++) s += Q[r * n + j] * ph[j] * Z[j * n + src];
+      V[r * n + c] = s;
+    }
+  }
+  return true;
+}
+
+// Generalised Hermitian problem GA c = lambda GM c (GM positive definite), lowest m pairs.
+// C is n x m (row-major).  Returns false if GM is numerically not PD or QL fails.
+inline bool hegv_lowest(int n, int m, const Mat &GA, const Mat &GM, std::vector<double> &lam, Mat &C) {
+  Mat L = GM;
+  // scale-aware: normalise by the diagonal first (D^-1/2 GM D^-1/2) for a meaningful pivot test
+  std::vector<double> sc(n);
+  for (int i = 0; i < n; i++) {
+    double dii = GM[i * n + i].real();
+    if (!(dii > 0)) return false;
+    sc[i] = 1.0 / std::sqrt(dii);
+  }
+  Mat B = GA;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) { L[i * n + j] *= sc[i] * sc[j]; B[i * n + j] *= sc[i] * sc[j]; }
+  if (!cholesky(n, L, 1e-13)) return false;
+  reduce_to_standard(n, L, B);
+  std::vector<double> w;
+  Mat V;
+  if (!heev(n, B, w, V)) return false;
+  lam.assign(w.begin(), w.begin() + m);
+  C.assign((size_t)n * m, cplx(0));
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) C[i * m + j] = V[i * n + j];
+  back_transform(n, m, L, C);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) C[i * m + j] *= sc[i];
+  return true;
+}
+
+}  // namespace dense
+}  // namespace bloch_b200

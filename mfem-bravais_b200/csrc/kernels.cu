@@ -1,0 +1,928 @@
+// sm_100a kernels of the Bloch Maxwell path: matrix-free, sum-factorised element operators in
+// fp64 with the element tensors staged in shared memory, signed periodic gather/scatter, and the
+// tall-skinny block algebra of the eigensolver.
+//
+// Element kernels ("mode space" formulation):
+//   * one CTA processes 32 work items (element, vector); lane <-> item, so every shared-memory
+//     access is a conflict-free 16-byte-per-lane row and all tensor indices are compile time;
+//   * warps split the independent slabs / pencils / grid points of each phase;
+//   * closed 1-D directions are mapped nodal -> mode (values at the p Gauss points + top
+//     Legendre coefficient), where all 1-D mass matrices are diagonal and the Bloch shift
+//     -i kappa_hat is pointwise, so A = (C - i Z)^H M2 (C - i Z) costs 24 real 1-D contractions.
+// Local storage is "cyclic": ND component c is [open dir c][closed c+1][closed c+2], RT component
+// c is [closed dir c][open c+1][open c+2], which makes the three components share one code path.
+#include "kernels.hpp"
+
+#include <cstdio>
+
+namespace bloch_b200 {
+
+namespace {
+
+__device__ __forceinline__ double2 ld2(const double2 *p) { return *p; }
+
+#define CFMA(acc, a, z)            \
+  {                                \
+    (acc).x = fma((a), (z).x, (acc).x); \
+    (acc).y = fma((a), (z).y, (acc).y); \
+  }
+
+template <int P>
+struct Dim {
+  static constexpr int Q = P + 1;
+  static constexpr int NB = P * Q * Q;   // ND dofs per component
+  static constexpr int RB = Q * P * P;   // RT dofs per component
+  static constexpr int LND = 3 * NB, LRT = 3 * RB, LH1 = Q * Q * Q;
+  __host__ __device__ static constexpr int nd(int c, int o, int j1, int j2) {
+    return c * NB + (o * Q + j1) * Q + j2;
+  }
+  __host__ __device__ static constexpr int rt(int c, int j, int o1, int o2) {
+    return c * RB + (j * P + o1) * P + o2;
+  }
+};
+
+// ---- in-register slab transforms: s[a][b] (Q x Q), apply matrix along both indices ----
+// FWD: out[r] = sum_j Mx[r][j] in[j] ; ADJ: out[j] = sum_r Mx[r][j] in[r]
+template <int P, bool ADJ>
+__device__ __forceinline__ void slab_transform(double2 (&s)[P + 1][P + 1], const double (&Mx)[kMaxP + 1][kMaxP + 1]) {
+  constexpr int Q = P + 1;
+  double2 u[Q][Q];
+#pragma unroll
+  for (int a = 0; a < Q; a++)
+#pragma unroll
+    for (int r = 0; r < Q; r++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double m = ADJ ? Mx[j][r] : Mx[r][j];
+        CFMA(acc, m, s[a][j]);
+      }
+      u[a][r] = acc;
+    }
+#pragma unroll
+  for (int r = 0; r < Q; r++)
+#pragma unroll
+    for (int b = 0; b < Q; b++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double m = ADJ ? Mx[j][r] : Mx[r][j];
+        CFMA(acc, m, u[j][b]);
+      }
+      s[r][b] = acc;
+    }
+}
+
+// ND buffer: transform every (c, o) slab along its two closed directions
+template <int P, int NW, int WHICH>   // WHICH: 0 = TI fwd, 1 = TI adjoint, 2 = TIinv fwd
+__device__ __forceinline__ void nd_transform_all(double2 *sND, const Tabs &T, int warp, int lane) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  for (int t = warp; t < 3 * P; t += NW) {
+    const int c = t / P, o = t - c * P;
+    double2 s[Q][Q];
+    const int base = D::nd(c, o, 0, 0);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) s[a][b] = sND[(base + a * Q + b) * 32 + lane];
+    if (WHICH == 0) slab_transform<P, false>(s, T.TI);
+    else if (WHICH == 1) slab_transform<P, true>(s, T.TI);
+    else slab_transform<P, false>(s, T.TIinv);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) sND[(base + a * Q + b) * 32 + lane] = s[a][b];
+  }
+}
+
+// pointwise ND mass in mode space, in place:  F_c(i) <- coef * Omega(i) * sum_d H[c][d] F_d(i)
+template <int P, int NW>
+__device__ __forceinline__ void nd_mass_pointwise(double2 *sND, const Tabs &T, const double *cp,
+                                                  double coef, int warp, int lane) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  const double *H = cp + 12;
+  for (int g = warp; g < Q * Q * Q; g += NW) {
+    int i[3];
+    i[0] = g / (Q * Q);
+    i[1] = (g / Q) % Q;
+    i[2] = g % Q;
+    double w = coef;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double o = T.om[0];
+#pragma unroll
+      for (int r = 1; r < Q; r++) o = (i[d] == r) ? T.om[r] : o;
+      w *= o;
+    }
+    double2 f[3];
+    int loc[3];
+    bool ex[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      ex[c] = i[c] < P;
+      loc[c] = D::nd(c, i[c], i[(c + 1) % 3], i[(c + 2) % 3]);
+      f[c] = ex[c] ? sND[loc[c] * 32 + lane] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (ex[c]) {
+        double2 r;
+        r.x = w * (H[3 * c] * f[0].x + H[3 * c + 1] * f[1].x + H[3 * c + 2] * f[2].x);
+        r.y = w * (H[3 * c] * f[0].y + H[3 * c + 1] * f[1].y + H[3 * c + 2] * f[2].y);
+        sND[loc[c] * 32 + lane] = r;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// y = ca * A x + cm * M x on ND block vectors
+// ------------------------------------------------------------------------------------------
+template <int P, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
+           double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca, double cm) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sND = reinterpret_cast<double2 *>(smem_raw);
+  double2 *sRT = sND + D::LND * 32;
+  double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  const long item = (long)blockIdx.x * 32 + lane;
+  const bool active = item < n_items;
+  const int e = active ? (int)(item / m) : 0;
+  const int v = active ? (int)(item - (long)e * m) : 0;
+  const int32_t *mp = E.map_nd + (long)e * D::LND;
+  // ---- gather (signed, periodic identification is in the map) ----
+  for (int j = warp; j < D::LND; j += NW) {
+    double2 val = make_double2(0.0, 0.0);
+    if (active) {
+      const int s = __ldg(mp + j);
+      const long g = (s < 0 ? -s : s) - 1;
+      val = ld2(X + g * ldx + v);
+      if (s < 0) { val.x = -val.x; val.y = -val.y; }
+    }
+    sND[j * 32 + lane] = val;
+  }
+  __syncthreads();
+  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
+  const double eps = active ? E.eps[e] : 0.0, mui = active ? E.muinv[e] : 0.0;
+  // ---- nodal -> mode in the closed directions ----
+  nd_transform_all<P, NW, 0>(sND, T, warp, lane);
+  __syncthreads();
+  // ---- Bloch curl: R_c = K_{c+1} F_{c+2} - K_{c+2} F_{c+1},  K_d = Dt - i kh_d (pointwise) ----
+  if (ca != 0.0) {
+    for (int t = warp; t < 3 * Q; t += NW) {
+      const int c = t / Q, j = t - c * Q;
+      const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+      const double k1 = cp[c1], k2 = cp[c2];
+      double2 A[P][Q], B[P][Q];
+#pragma unroll
+      for (int o = 0; o < P; o++)
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          A[o][r] = sND[D::nd(c2, o, j, r) * 32 + lane];   // F_{c+2}[o2=o, j1=j, j2=r]
+          B[o][r] = sND[D::nd(c1, o, r, j) * 32 + lane];   // F_{c+1}[o1=o, j1=r, j2=j]
+        }
+#pragma unroll
+      for (int o1 = 0; o1 < P; o1++)
+#pragma unroll
+        for (int o2 = 0; o2 < P; o2++) {
+          double2 acc;
+          acc.x = k1 * A[o2][o1].y - k2 * B[o1][o2].y;
+          acc.y = -k1 * A[o2][o1].x + k2 * B[o1][o2].x;
+#pragma unroll
+          for (int r = 0; r < Q; r++) {
+            CFMA(acc, T.Dt[o1][r], A[o2][r]);
+            CFMA(acc, -T.Dt[o2][r], B[o1][r]);
+          }
+          sRT[D::rt(c, j, o1, o2) * 32 + lane] = acc;
+        }
+    }
+  }
+  __syncthreads();
+  // ---- pointwise RT mass (scaled by ca * muinv) and ND mass (scaled by cm * eps) ----
+  if (ca != 0.0) {
+    const double *G = cp + 3;
+    for (int g = warp; g < Q * Q * Q; g += NW) {
+      int i[3];
+      i[0] = g / (Q * Q);
+      i[1] = (g / Q) % Q;
+      i[2] = g % Q;
+      double w = ca * mui;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double o = T.om[0];
+#pragma unroll
+        for (int r = 1; r < Q; r++) o = (i[d] == r) ? T.om[r] : o;
+        w *= o;
+      }
+      double2 f[3];
+      int loc[3];
+      bool ex[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        ex[c] = (i[(c + 1) % 3] < P) && (i[(c + 2) % 3] < P);
+        loc[c] = ex[c] ? D::rt(c, i[c], i[(c + 1) % 3], i[(c + 2) % 3]) : 0;
+        f[c] = ex[c] ? sRT[loc[c] * 32 + lane] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        if (ex[c]) {
+          double2 r;
+          r.x = w * (G[3 * c] * f[0].x + G[3 * c + 1] * f[1].x + G[3 * c + 2] * f[2].x);
+          r.y = w * (G[3 * c] * f[0].y + G[3 * c + 1] * f[1].y + G[3 * c + 2] * f[2].y);
+          sRT[loc[c] * 32 + lane] = r;
+        }
+      }
+    }
+  }
+  if (cm != 0.0) nd_mass_pointwise<P, NW>(sND, T, cp, cm * eps, warp, lane);
+  __syncthreads();
+  // ---- adjoint curl accumulated onto the mass part, then mode -> nodal (adjoint) ----
+  for (int t = warp; t < 3 * P; t += NW) {
+    const int c = t / P, o = t - c * P;
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    double2 f[Q][Q];
+    const int base = D::nd(c, o, 0, 0);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++)
+        f[a][b] = (cm != 0.0) ? sND[(base + a * Q + b) * 32 + lane] : make_double2(0.0, 0.0);
+    if (ca != 0.0) {
+      const double k1 = cp[c1], k2 = cp[c2];
+      double2 Y1[Q][P], Y2[Q][P];
+#pragma unroll
+      for (int a = 0; a < Q; a++)
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+          Y1[a][q] = sRT[D::rt(c1, a, q, o) * 32 + lane];   // Y_{c+1}[j=j1, o1, o2=o]
+          Y2[a][q] = sRT[D::rt(c2, a, o, q) * 32 + lane];   // Y_{c+2}[j=j2, o1=o, o2]
+        }
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) {
+          double2 acc = f[j1][j2];
+#pragma unroll
+          for (int q = 0; q < P; q++) {
+            CFMA(acc, T.Dt[q][j2], Y1[j1][q]);
+            CFMA(acc, -T.Dt[q][j1], Y2[j2][q]);
+          }
+          if (j2 < P) { acc.x -= k2 * Y1[j1][j2].y; acc.y += k2 * Y1[j1][j2].x; }
+          if (j1 < P) { acc.x += k1 * Y2[j2][j1].y; acc.y -= k1 * Y2[j2][j1].x; }
+          f[j1][j2] = acc;
+        }
+    }
+    slab_transform<P, true>(f, T.TI);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) sND[(base + a * Q + b) * 32 + lane] = f[a][b];
+  }
+  __syncthreads();
+  // ---- signed scatter-add ----
+  if (active) {
+    double *Yd = reinterpret_cast<double *>(Y);
+    for (int j = warp; j < D::LND; j += NW) {
+      const int s = __ldg(mp + j);
+      const long g = (s < 0 ? -s : s) - 1;
+      double2 val = sND[j * 32 + lane];
+      if (s < 0) { val.x = -val.x; val.y = -val.y; }
+      double *dst = Yd + 2 * (g * ldy + v);
+      atomicAdd(dst, val.x);
+      atomicAdd(dst + 1, val.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// H1 <-> ND operators: mode 0: y_h1 += G^H M1 G x_h1 ; 1: y_nd = G x_h1 ; 2: y_h1 += G^H M1 x_nd
+// G = T01 - i Z01_kappa.  In mode space: F_c = (Dt - i kh_c) along direction c of Phi~.
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ int h1_idx(int i0, int i1, int i2) {
+  return (i0 * (P + 1) + i1) * (P + 1) + i2;
+}
+
+template <int P, int NW, bool ADJ>
+__device__ __forceinline__ void h1_transform_dir(double2 *sH, const Tabs &T, int dir, int warp, int lane) {
+  constexpr int Q = P + 1;
+  const int sd = dir == 0 ? Q * Q : (dir == 1 ? Q : 1);
+  const int s1 = dir == 0 ? Q : Q * Q, s2 = dir == 2 ? Q : 1;   // strides of the other two dirs
+  for (int t = warp; t < Q * Q; t += NW) {
+    const int a = t / Q, b = t - a * Q;
+    const int base = a * s1 + b * s2;
+    double2 in[Q], out[Q];
+#pragma unroll
+    for (int j = 0; j < Q; j++) in[j] = sH[(base + j * sd) * 32 + lane];
+#pragma unroll
+    for (int r = 0; r < Q; r++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double mm = ADJ ? T.TI[j][r] : T.TI[r][j];
+        CFMA(acc, mm, in[j]);
+      }
+      out[r] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) sH[(base + j * sd) * 32 + lane] = out[j];
+  }
+}
+
+template <int P, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32)
+k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
+        double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sND = reinterpret_cast<double2 *>(smem_raw);
+  double2 *sH = sND + D::LND * 32;
+  double *sCP = reinterpret_cast<double *>(sH + D::LH1 * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  const long item = (long)blockIdx.x * 32 + lane;
+  const bool active = item < n_items;
+  const int e = active ? (int)(item / m) : 0;
+  const int v = active ? (int)(item - (long)e * m) : 0;
+  const int32_t *mh = E.map_h1 + (long)e * D::LH1;
+  const int32_t *mn = E.map_nd + (long)e * D::LND;
+  if (MODE == 2) {
+    for (int j = warp; j < D::LND; j += NW) {
+      double2 val = make_double2(0.0, 0.0);
+      if (active) {
+        const int s = __ldg(mn + j);
+        const long g = (s < 0 ? -s : s) - 1;
+        val = ld2(X + g * ldx + v);
+        if (s < 0) { val.x = -val.x; val.y = -val.y; }
+      }
+      sND[j * 32 + lane] = val;
+    }
+  } else {
+    for (int j = warp; j < D::LH1; j += NW) {
+      double2 val = make_double2(0.0, 0.0);
+      if (active) val = ld2(X + (long)(__ldg(mh + j) - 1) * ldx + v);
+      sH[j * 32 + lane] = val;
+    }
+  }
+  __syncthreads();
+  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
+  const double eps = active ? E.eps[e] : 0.0;
+  if (MODE == 2) {
+    nd_transform_all<P, NW, 0>(sND, T, warp, lane);
+    __syncthreads();
+  } else {
+    for (int d = 0; d < 3; d++) {
+      h1_transform_dir<P, NW, false>(sH, T, d, warp, lane);
+      __syncthreads();
+    }
+    // gradient in mode space: F_c[o][j1][j2] = sum_t Dt[o][t] Phi[i_c = t] - i kh_c Phi[i_c = o]
+    for (int t = warp; t < 3 * Q * Q; t += NW) {
+      const int c = t / (Q * Q), r = t - c * Q * Q;
+      const int j1 = r / Q, j2 = r - j1 * Q;
+      const int sc = c == 0 ? Q * Q : (c == 1 ? Q : 1);
+      int idx[3];
+      idx[c] = 0; idx[(c + 1) % 3] = j1; idx[(c + 2) % 3] = j2;
+      const int base = h1_idx<P>(idx[0], idx[1], idx[2]);
+      const double kc = cp[c];
+      double2 in[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) in[q] = sH[(base + q * sc) * 32 + lane];
+#pragma unroll
+      for (int o = 0; o < P; o++) {
+        double2 acc;
+        acc.x = kc * in[o].y;
+        acc.y = -kc * in[o].x;
+#pragma unroll
+        for (int q = 0; q < Q; q++) CFMA(acc, T.Dt[o][q], in[q]);
+        sND[D::nd(c, o, j1, j2) * 32 + lane] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (MODE == 1) {
+    // mode -> nodal ND dofs (inverse transform), plain signed stores
+    nd_transform_all<P, NW, 2>(sND, T, warp, lane);
+    __syncthreads();
+    if (active) {
+      for (int j = warp; j < D::LND; j += NW) {
+        const int s = __ldg(mn + j);
+        const long g = (s < 0 ? -s : s) - 1;
+        double2 val = sND[j * 32 + lane];
+        if (s < 0) { val.x = -val.x; val.y = -val.y; }
+        Y[g * ldy + v] = val;
+      }
+    }
+    return;
+  }
+  nd_mass_pointwise<P, NW>(sND, T, cp, eps, warp, lane);
+  __syncthreads();
+  // adjoint gradient: Phi'[i_c = t] (+)= sum_o Dt[o][t] F_c[o] + i kh_c F_c[t] (t < P)
+  for (int c = 0; c < 3; c++) {
+    const int sc = c == 0 ? Q * Q : (c == 1 ? Q : 1);
+    const double kc = cp[c];
+    for (int t = warp; t < Q * Q; t += NW) {
+      const int j1 = t / Q, j2 = t - j1 * Q;
+      int idx[3];
+      idx[c] = 0; idx[(c + 1) % 3] = j1; idx[(c + 2) % 3] = j2;
+      const int base = h1_idx<P>(idx[0], idx[1], idx[2]);
+      double2 in[P];
+#pragma unroll
+      for (int o = 0; o < P; o++) in[o] = sND[D::nd(c, o, j1, j2) * 32 + lane];
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        double2 acc = (c == 0) ? make_double2(0.0, 0.0) : sH[(base + q * sc) * 32 + lane];
+#pragma unroll
+        for (int o = 0; o < P; o++) CFMA(acc, T.Dt[o][q], in[o]);
+        if (q < P) { acc.x -= kc * in[q].y; acc.y += kc * in[q].x; }
+        sH[(base + q * sc) * 32 + lane] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int d = 0; d < 3; d++) {
+    h1_transform_dir<P, NW, true>(sH, T, d, warp, lane);
+    __syncthreads();
+  }
+  if (active) {
+    double *Yd = reinterpret_cast<double *>(Y);
+    for (int j = warp; j < D::LH1; j += NW) {
+      const long g = __ldg(mh + j) - 1;
+      const double2 val = sH[j * 32 + lane];
+      double *dst = Yd + 2 * (g * ldy + v);
+      atomicAdd(dst, val.x);
+      atomicAdd(dst + 1, val.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// y_rt = (C - i Z_kappa) x_nd : nodal RT dofs of the Bloch curl (B field), plain stores
+// ------------------------------------------------------------------------------------------
+template <int P, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_curl(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
+       double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sND = reinterpret_cast<double2 *>(smem_raw);
+  double2 *sRT = sND + D::LND * 32;
+  double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  const long item = (long)blockIdx.x * 32 + lane;
+  const bool active = item < n_items;
+  const int e = active ? (int)(item / m) : 0;
+  const int v = active ? (int)(item - (long)e * m) : 0;
+  const int32_t *mp = E.map_nd + (long)e * D::LND;
+  for (int j = warp; j < D::LND; j += NW) {
+    double2 val = make_double2(0.0, 0.0);
+    if (active) {
+      const int s = __ldg(mp + j);
+      const long g = (s < 0 ? -s : s) - 1;
+      val = ld2(X + g * ldx + v);
+      if (s < 0) { val.x = -val.x; val.y = -val.y; }
+    }
+    sND[j * 32 + lane] = val;
+  }
+  __syncthreads();
+  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
+  nd_transform_all<P, NW, 0>(sND, T, warp, lane);
+  __syncthreads();
+  for (int t = warp; t < 3 * Q; t += NW) {
+    const int c = t / Q, j = t - c * Q;
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    const double k1 = cp[c1], k2 = cp[c2];
+    double2 A[P][Q], B[P][Q];
+#pragma unroll
+    for (int o = 0; o < P; o++)
+#pragma unroll
+      for (int r = 0; r < Q; r++) {
+        A[o][r] = sND[D::nd(c2, o, j, r) * 32 + lane];
+        B[o][r] = sND[D::nd(c1, o, r, j) * 32 + lane];
+      }
+#pragma unroll
+    for (int o1 = 0; o1 < P; o1++)
+#pragma unroll
+      for (int o2 = 0; o2 < P; o2++) {
+        double2 acc;
+        acc.x = k1 * A[o2][o1].y - k2 * B[o1][o2].y;
+        acc.y = -k1 * A[o2][o1].x + k2 * B[o1][o2].x;
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          CFMA(acc, T.Dt[o1][r], A[o2][r]);
+          CFMA(acc, -T.Dt[o2][r], B[o1][r]);
+        }
+        sRT[D::rt(c, j, o1, o2) * 32 + lane] = acc;
+      }
+  }
+  __syncthreads();
+  // mode -> nodal along the single closed direction of each RT component (pencils)
+  for (int t = warp; t < 3 * P * P; t += NW) {
+    const int c = t / (P * P), r = t - c * P * P;
+    const int o1 = r / P, o2 = r - o1 * P;
+    double2 in[Q], out[Q];
+#pragma unroll
+    for (int j = 0; j < Q; j++) in[j] = sRT[D::rt(c, j, o1, o2) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) CFMA(acc, T.TIinv[k][j], in[j]);
+      out[k] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) sRT[D::rt(c, j, o1, o2) * 32 + lane] = out[j];
+  }
+  __syncthreads();
+  if (active) {
+    const int32_t *mr = E.map_rt + (long)e * D::LRT;
+    for (int j = warp; j < D::LRT; j += NW) {
+      const int s = __ldg(mr + j);
+      const long g = (s < 0 ? -s : s) - 1;
+      double2 val = sRT[j * 32 + lane];
+      if (s < 0) { val.x = -val.x; val.y = -val.y; }
+      Y[g * ldy + v] = val;
+    }
+  }
+}
+
+template <int P, int NW>
+cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
+                       int nvec, double ca, double cm, cudaStream_t s) {
+  using D = Dim<P>;
+  const size_t smem = (size_t)(D::LND + D::LRT) * 32 * sizeof(double2) +
+                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(k_nd_apply<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  const long n_items = (long)E.n_elem * nvec;
+  const long grid = (n_items + 31) / 32;
+  k_nd_apply<P, NW><<<(unsigned)grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca, cm);
+  return cudaGetLastError();
+}
+
+template <int P, int NW>
+cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
+                    int ldy, int nvec, cudaStream_t s) {
+  using D = Dim<P>;
+  const size_t smem = (size_t)(D::LND + D::LH1) * 32 * sizeof(double2) +
+                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err;
+    err = cudaFuncSetAttribute(k_h1_op<P, NW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(k_h1_op<P, NW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(k_h1_op<P, NW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  const long n_items = (long)E.n_elem * nvec;
+  const unsigned grid = (unsigned)((n_items + 31) / 32);
+  if (mode == 0) k_h1_op<P, NW, 0><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
+  else if (mode == 1) k_h1_op<P, NW, 1><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
+  else k_h1_op<P, NW, 2><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
+  return cudaGetLastError();
+}
+
+template <int P, int NW>
+cudaError_t curl_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
+                   int nvec, cudaStream_t s) {
+  using D = Dim<P>;
+  const size_t smem = (size_t)(D::LND + D::LRT) * 32 * sizeof(double2) +
+                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(k_curl<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  const long n_items = (long)E.n_elem * nvec;
+  k_curl<P, NW><<<(unsigned)((n_items + 31) / 32), NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
+                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s) {
+  switch (p) {
+    case 1: return nd_apply_t<1, 6>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 2: return nd_apply_t<2, 9>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 3: return nd_apply_t<3, 12>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
+                         double2 *y, int ldy, int nvec, cudaStream_t s) {
+  switch (p) {
+    case 1: return h1_op_t<1, 4>(mode, T, E, x, ldx, y, ldy, nvec, s);
+    case 2: return h1_op_t<2, 9>(mode, T, E, x, ldx, y, ldy, nvec, s);
+    case 3: return h1_op_t<3, 12>(mode, T, E, x, ldx, y, ldy, nvec, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
+                        int ldy, int nvec, cudaStream_t s) {
+  switch (p) {
+    case 1: return curl_t<1, 6>(T, E, x, ldx, y, ldy, nvec, s);
+    case 2: return curl_t<2, 9>(T, E, x, ldx, y, ldy, nvec, s);
+    case 3: return curl_t<3, 12>(T, E, x, ldx, y, ldy, nvec, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ==========================================================================================
+// layout conversion and block algebra
+// ==========================================================================================
+namespace {
+
+__global__ void k_pack(const double *__restrict__ reim, double2 *__restrict__ blk, long n, int nvec) {
+  const long total = n * nvec;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long i = t / nvec;
+    const int v = (int)(t - i * nvec);
+    const double *src = reim + (long)v * 2 * n;
+    blk[t] = make_double2(src[i], src[n + i]);
+  }
+}
+__global__ void k_unpack(const double2 *__restrict__ blk, double *__restrict__ reim, long n, int nvec) {
+  const long total = n * nvec;
+  // iterate in output order for coalesced stores
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(t / n);
+    const long i = t - (long)v * n;
+    const double2 z = blk[i * nvec + v];
+    double *dst = reim + (long)v * 2 * n;
+    dst[i] = z.x;
+    dst[n + i] = z.y;
+  }
+}
+
+// Gram: each CTA reduces a row chunk into a register tile, then atomically adds into C.
+// thread (ti, tj) owns C entries (i, j) with i = ti + k*TI... simple generic version.
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_ROWS = 64;   // rows staged per iteration
+__global__ void k_gram(const double2 *__restrict__ A, int ma, int lda, const double2 *__restrict__ B, int mb,
+                       int ldb, long n, double2 *__restrict__ C, long rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sA = reinterpret_cast<double2 *>(smem_raw);   // [GRAM_ROWS][ma]
+  double2 *sB = sA + GRAM_ROWS * ma;                      // [GRAM_ROWS][mb]
+  const long r0 = blockIdx.x * rows_per_cta;
+  const long r1 = min(n, r0 + rows_per_cta);
+  const int nout = ma * mb;
+  // each thread accumulates outputs t, t+256, ... (at most 8 -> ma*mb <= 2048)
+  double2 acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = make_double2(0.0, 0.0);
+  for (long r = r0; r < r1; r += GRAM_ROWS) {
+    const int nr = (int)min((long)GRAM_ROWS, r1 - r);
+    for (int t = threadIdx.x; t < nr * ma; t += GRAM_THREADS) sA[t] = A[(r + t / ma) * lda + t % ma];
+    for (int t = threadIdx.x; t < nr * mb; t += GRAM_THREADS) sB[t] = B[(r + t / mb) * ldb + t % mb];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int o = threadIdx.x + k * GRAM_THREADS;
+      if (o < nout) {
+        const int i = o / mb, j = o - i * mb;
+        double2 a = acc[k];
+        for (int q = 0; q < nr; q++) {
+          const double2 x = sA[q * ma + i], y = sB[q * mb + j];
+          a.x = fma(x.x, y.x, a.x); a.x = fma(x.y, y.y, a.x);
+          a.y = fma(x.x, y.y, a.y); a.y = fma(-x.y, y.x, a.y);
+        }
+        acc[k] = a;
+      }
+    }
+    __syncthreads();
+  }
+  double *Cd = reinterpret_cast<double *>(C);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int o = threadIdx.x + k * GRAM_THREADS;
+    if (o < nout) {
+      atomicAdd(Cd + 2 * o, acc[k].x);
+      atomicAdd(Cd + 2 * o + 1, acc[k].y);
+    }
+  }
+}
+
+// Y = beta*Y + X*C : one thread per (row, output column)
+__global__ void k_block_mult(const double2 *__restrict__ X, int k, const double2 *__restrict__ C, int m,
+                             double2 *__restrict__ Y, double beta, long n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sC = reinterpret_cast<double2 *>(smem_raw);
+  for (int t = threadIdx.x; t < k * m; t += blockDim.x) sC[t] = C[t];
+  __syncthreads();
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long r = t / m;
+    const int j = (int)(t - r * m);
+    double2 acc = make_double2(0.0, 0.0);
+    if (beta != 0.0) { const double2 y = Y[t]; acc.x = beta * y.x; acc.y = beta * y.y; }
+    const double2 *xr = X + r * k;
+    for (int i = 0; i < k; i++) {
+      const double2 x = xr[i], c = sC[i * m + j];
+      acc.x = fma(x.x, c.x, acc.x); acc.x = fma(-x.y, c.y, acc.x);
+      acc.y = fma(x.x, c.y, acc.y); acc.y = fma(x.y, c.x, acc.y);
+    }
+    Y[t] = acc;
+  }
+}
+
+__global__ void k_residual(const double2 *__restrict__ AX, const double2 *__restrict__ MX,
+                           const double *__restrict__ lam, double2 *__restrict__ R, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % m);
+    const double l = lam[j];
+    const double2 a = AX[t], b = MX[t];
+    R[t] = make_double2(a.x - l * b.x, a.y - l * b.y);
+  }
+}
+__global__ void k_axpby(double a, const double2 *__restrict__ X, double b, double2 *__restrict__ Y, long total) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double2 x = X[t];
+    double2 y = make_double2(0.0, 0.0);
+    if (b != 0.0) y = Y[t];
+    Y[t] = make_double2(a * x.x + b * y.x, a * x.y + b * y.y);
+  }
+}
+__global__ void k_diag_scale(const double *__restrict__ d, const double2 *__restrict__ X,
+                             double2 *__restrict__ Y, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = d[t / m];
+    const double2 x = X[t];
+    Y[t] = make_double2(s * x.x, s * x.y);
+  }
+}
+__global__ void k_col_axpy(const double *__restrict__ alpha, double sign, const double2 *__restrict__ X,
+                           double2 *__restrict__ Y, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double a = sign * alpha[t % m];
+    const double2 x = X[t];
+    double2 y = Y[t];
+    y.x = fma(a, x.x, y.x); y.y = fma(a, x.y, y.y);
+    Y[t] = y;
+  }
+}
+__global__ void k_col_xpby(const double2 *__restrict__ Z, const double *__restrict__ beta,
+                           double2 *__restrict__ Pp, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double b = beta[t % m];
+    const double2 z = Z[t], p = Pp[t];
+    Pp[t] = make_double2(fma(b, p.x, z.x), fma(b, p.y, z.y));
+  }
+}
+// column dots: CTA-level reduction per column then atomicAdd
+__global__ void k_col_dot(const double2 *__restrict__ A, const double2 *__restrict__ B, long n, int m,
+                          double *__restrict__ d) {
+  // only the first `usable` threads work, usable a multiple of m, so that the grid stride keeps
+  // every thread on one fixed column
+  extern __shared__ double sred[];
+  const int tid = threadIdx.x;
+  const long total = n * m;
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long usable = (nthreads / m) * m;
+  double acc = 0.0;
+  const long start = blockIdx.x * (long)blockDim.x + tid;
+  if (start < usable) {
+    for (long t = start; t < total; t += usable) {
+      const double2 a = A[t], b = B[t];
+      acc = fma(a.x, b.x, acc);
+      acc = fma(a.y, b.y, acc);
+    }
+  }
+  for (int j = tid; j < m; j += blockDim.x) sred[j] = 0.0;
+  __syncthreads();
+  if (start < usable) atomicAdd(&sred[start % m], acc);
+  __syncthreads();
+  for (int j = tid; j < m; j += blockDim.x) atomicAdd(d + j, sred[j]);
+}
+__global__ void k_scalar_div(const double *num, const double *den, double *out, int m) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) out[j] = (den[j] != 0.0) ? num[j] / den[j] : 0.0;
+}
+__global__ void k_scatter_diag(const int32_t *__restrict__ map, int L, const int *__restrict__ cls,
+                               const double *__restrict__ coef, const double *__restrict__ dloc,
+                               int n_elem, double *__restrict__ d) {
+  const long total = (long)n_elem * L;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int e = (int)(t / L), l = (int)(t - (long)e * L);
+    const int s = map[t];
+    const long g = (s < 0 ? -s : s) - 1;
+    atomicAdd(d + g, coef[e] * dloc[(long)cls[e] * L + l]);
+  }
+}
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_fill_random(double2 *X, long total, unsigned long long seed) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const unsigned long long a = splitmix(seed + 2 * (unsigned long long)t);
+    const unsigned long long b = splitmix(seed + 2 * (unsigned long long)t + 1);
+    X[t] = make_double2((double)(a >> 11) * (2.0 / 9007199254740992.0) - 1.0,
+                        (double)(b >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+  }
+}
+
+inline unsigned grid_for(long total, int threads) {
+  long g = (total + threads - 1) / threads;
+  const long cap = 148L * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+cudaError_t launch_pack(const double *reim, double2 *blk, long n, int nvec, cudaStream_t s) {
+  k_pack<<<grid_for(n * nvec, 256), 256, 0, s>>>(reim, blk, n, nvec);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack(const double2 *blk, double *reim, long n, int nvec, cudaStream_t s) {
+  k_unpack<<<grid_for(n * nvec, 256), 256, 0, s>>>(blk, reim, n, nvec);
+  return cudaGetLastError();
+}
+cudaError_t launch_gram(const double2 *A, int ma, int lda, const double2 *B, int mb, int ldb, long n,
+                        double2 *C, cudaStream_t s) {
+  if (ma * mb > 8 * GRAM_THREADS) return cudaErrorInvalidValue;
+  cudaError_t err = cudaMemsetAsync(C, 0, sizeof(double2) * ma * mb, s);
+  if (err != cudaSuccess) return err;
+  long ctas = 148 * 2;
+  long rows = (n + ctas - 1) / ctas;
+  rows = ((rows + GRAM_ROWS - 1) / GRAM_ROWS) * GRAM_ROWS;
+  ctas = (n + rows - 1) / rows;
+  const size_t smem = (size_t)GRAM_ROWS * (ma + mb) * sizeof(double2);
+  k_gram<<<(unsigned)ctas, GRAM_THREADS, smem, s>>>(A, ma, lda, B, mb, ldb, n, C, rows);
+  return cudaGetLastError();
+}
+cudaError_t launch_block_mult(const double2 *X, int k, const double2 *C, int m, double2 *Y,
+                              double beta, long n, cudaStream_t s) {
+  k_block_mult<<<grid_for(n * m, 256), 256, (size_t)k * m * sizeof(double2), s>>>(X, k, C, m, Y, beta, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_residual(const double2 *AX, const double2 *MX, const double *lambda, double2 *R,
+                            long n, int m, cudaStream_t s) {
+  k_residual<<<grid_for(n * m, 256), 256, 0, s>>>(AX, MX, lambda, R, n, m);
+  return cudaGetLastError();
+}
+cudaError_t launch_axpby(double a, const double2 *X, double b, double2 *Y, long total, cudaStream_t s) {
+  k_axpby<<<grid_for(total, 256), 256, 0, s>>>(a, X, b, Y, total);
+  return cudaGetLastError();
+}
+cudaError_t launch_diag_scale(const double *d, const double2 *X, double2 *Y, long n, int m, cudaStream_t s) {
+  k_diag_scale<<<grid_for(n * m, 256), 256, 0, s>>>(d, X, Y, n, m);
+  return cudaGetLastError();
+}
+cudaError_t launch_col_axpy(const double *alpha, double sign, const double2 *X, double2 *Y, long n,
+                            int m, cudaStream_t s) {
+  k_col_axpy<<<grid_for(n * m, 256), 256, 0, s>>>(alpha, sign, X, Y, n, m);
+  return cudaGetLastError();
+}
+cudaError_t launch_col_xpby(const double2 *Z, const double *beta, double2 *P, long n, int m,
+                            cudaStream_t s) {
+  k_col_xpby<<<grid_for(n * m, 256), 256, 0, s>>>(Z, beta, P, n, m);
+  return cudaGetLastError();
+}
+cudaError_t launch_col_dot(const double2 *A, const double2 *B, long n, int m, double *d,
+                           cudaStream_t s) {
+  cudaError_t err = cudaMemsetAsync(d, 0, sizeof(double) * m, s);
+  if (err != cudaSuccess) return err;
+  k_col_dot<<<grid_for(n * m, 256) > 296 ? 296 : grid_for(n * m, 256), 256, sizeof(double) * m, s>>>(A, B, n, m, d);
+  return cudaGetLastError();
+}
+cudaError_t launch_scalar_div(const double *num, const double *den, double *out, int m, cudaStream_t s) {
+  k_scalar_div<<<(m + 63) / 64, 64, 0, s>>>(num, den, out, m);
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const double *coef,
+                                const double *dloc, int n_elem, double *d, cudaStream_t s) {
+  k_scatter_diag<<<grid_for((long)n_elem * L, 256), 256, 0, s>>>(map, L, cls, coef, dloc, n_elem, d);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s) {
+  k_fill_random<<<grid_for(total, 256), 256, 0, s>>>(X, total, seed);
+  return cudaGetLastError();
+}
+
+}  // namespace bloch_b200

@@ -1,0 +1,85 @@
+// Launch wrappers of the sm_100a kernels (definitions in kernels.cu).
+//
+// Device block-vector layout: interleaved complex, dof-major:  X[(dof*ld + v)] is a double2
+// (re, im) for dof < n, v < nvec <= ld (ld = row pitch in double2 units, so a kernel can work
+// on a column sub-block of a wider array).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace bloch_b200 {
+
+constexpr int kMaxP = 4;
+constexpr int kMaxClasses = 64;
+constexpr int kClassParDoubles = 21;   // kh[3], G[3][3], H[3][3]
+
+// 1-D tables, sized for the largest supported order; indexed with compile-time indices in the
+// kernels so they are read straight from the constant bank holding the kernel parameters.
+struct Tabs {
+  double TI[kMaxP + 1][kMaxP + 1];      // nodal(closed) -> mode
+  double TIinv[kMaxP + 1][kMaxP + 1];
+  double Dt[kMaxP][kMaxP + 1];          // derivative at Gauss points, from mode space
+  double om[kMaxP + 1];                 // diagonal 1-D mass weights in mode space
+};
+
+struct ElemData {            // device pointers, element order = mesh order
+  int n_elem, n_class;
+  const int *cls;            // [n_elem]
+  const double *eps;         // [n_elem]
+  const double *muinv;       // [n_elem]
+  const double *cpar;        // [n_class][21]   (kappa dependent)
+  const int32_t *map_nd;     // [n_elem][L_nd]  kernel ("cyclic") local order, signed 1-based
+  const int32_t *map_h1;     // [n_elem][L_h1]  kernel local order, 1-based
+  const int32_t *map_rt;     // [n_elem][L_rt]  kernel local order, signed 1-based
+};
+
+// y = ca * A x + cm * M x   (ND -> ND), A = (C - i Z_kappa)^H M2(muinv) (C - i Z_kappa), M = M1(eps)
+// y must be zero-initialised by the caller unless accumulate semantics are wanted.
+cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
+                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s);
+// H1 <-> ND operators of the projector.  mode 0: y_h1 += S0 x_h1 (S0 = G^H M1 G);
+// mode 1: y_nd = G x_h1 (interpolation, plain stores); mode 2: y_h1 += G^H M1 x_nd
+cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
+                         double2 *y, int ldy, int nvec, cudaStream_t s);
+// y_rt = (C - i Z_kappa) x_nd  (interpolation into nodal RT dofs, plain stores)
+cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
+                        int ldy, int nvec, cudaStream_t s);
+
+// ---- layout conversion: boundary [re(N); im(N)] per vector  <->  block [N][nvec] complex ----
+cudaError_t launch_pack(const double *reim, double2 *blk, long n, int nvec, cudaStream_t s);
+cudaError_t launch_unpack(const double2 *blk, double *reim, long n, int nvec, cudaStream_t s);
+
+// ---- dense block-vector algebra (tall-skinny), all complex ----
+// C[i][j] = sum_r conj(A[r][i]) B[r][j]  (ma x mb, row-major, double2) ; C is overwritten
+cudaError_t launch_gram(const double2 *A, int ma, int lda, const double2 *B, int mb, int ldb, long n,
+                        double2 *C, cudaStream_t s);
+// Y[r][j] = beta*Y[r][j] + sum_i X[r][i] * C[i][j]   (X: n x k, C: k x m row-major, Y: n x m)
+cudaError_t launch_block_mult(const double2 *X, int k, const double2 *C, int m, double2 *Y,
+                              double beta, long n, cudaStream_t s);
+// R[r][j] = AX[r][j] - lambda[j] * MX[r][j]
+cudaError_t launch_residual(const double2 *AX, const double2 *MX, const double *lambda, double2 *R,
+                            long n, int m, cudaStream_t s);
+// Y[r][j] = a*X[r][j] + b*Y[r][j]   (real scalars)
+cudaError_t launch_axpby(double a, const double2 *X, double b, double2 *Y, long total, cudaStream_t s);
+// Y[r][j] = X[r][j] * d[r]     (real diagonal scaling, e.g. Jacobi)
+cudaError_t launch_diag_scale(const double *d, const double2 *X, double2 *Y, long n, int m, cudaStream_t s);
+// per-column CG style updates with per-column device scalars:
+//   Y[r][j] += sign * alpha[j] * X[r][j]      (alpha real)
+cudaError_t launch_col_axpy(const double *alpha, double sign, const double2 *X, double2 *Y, long n,
+                            int m, cudaStream_t s);
+//   P[r][j] = Z[r][j] + beta[j] * P[r][j]
+cudaError_t launch_col_xpby(const double2 *Z, const double *beta, double2 *P, long n, int m,
+                            cudaStream_t s);
+// d[j] = sum_r Re(conj(A[r][j]) B[r][j])   (column-wise real dot), d overwritten
+cudaError_t launch_col_dot(const double2 *A, const double2 *B, long n, int m, double *d,
+                           cudaStream_t s);
+// tiny helpers on per-column scalars (device side, avoids host round trips in CG)
+//   out[j] = (den[j] != 0) ? num[j]/den[j] : 0
+cudaError_t launch_scalar_div(const double *num, const double *den, double *out, int m, cudaStream_t s);
+// diagonal accumulation: d[gid] += coef_e * dloc[cls][l] over elements (real)
+cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const double *coef,
+                                const double *dloc, int n_elem, double *d, cudaStream_t s);
+// fill with deterministic pseudo-random complex numbers in (-1,1)
+cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s);
+
+}  // namespace bloch_b200

@@ -1,0 +1,549 @@
+// Native complex block eigensolver behind Solve() (maxwell/maxwell_bloch.cpp:809-825): what the
+// reference delegates to hypre's LOBPCG with preconditioner = Projector o blockdiag(AMS) and a
+// MINRES-based divergence projector (maxwell_bloch.cpp:531-551, 1923-1937, 2280-2290).
+//
+//   * block LOBPCG on m complex vectors (the reference's 2m real ones), basis S = [X W P] kept in
+//     ONE row-major array [N][3m] so both Gram matrices are a single tall-skinny contraction each;
+//   * preconditioner T = Chebyshev polynomial in D^-1 (A + sigma M) (Jacobi D from the same
+//     element kernels); eigenvalues do not depend on T, only the iteration count does;
+//   * constraint G^H M x = 0 imposed by projecting W (and the initial block) with a block
+//     Jacobi-PCG on S0 = G^H M G whose per-column scalars live on the device.
+// On the affine WS meshes (C - iZ)(G - iZ0) = 0 holds exactly, so the projected residual equals
+// the plain residual and the convergence test is || A x - lambda M x ||_2 <= atol like hypre's.
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "core.hpp"
+#include "dense.hpp"
+
+using namespace bloch_b200;
+using D2 = double2;
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned grid_for(long total) {
+  long g = (total + TPB - 1) / TPB;
+  const long cap = 148L * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// R = AS[:, :m] - lam .* MS[:, :m]  (AS, MS with pitch ld);  rn2[j] += |R[:, j]|^2
+__global__ void k_resid_norm(const D2 *__restrict__ AS, const D2 *__restrict__ MS, int ld,
+                             const double *__restrict__ lam, D2 *__restrict__ R, long n, int m,
+                             double *__restrict__ rn2) {
+  extern __shared__ double sred[];
+  for (int j = threadIdx.x; j < m; j += blockDim.x) sred[j] = 0.0;
+  __syncthreads();
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long usable = (nthreads / m) * m;
+  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (start < usable) {
+    const int j = (int)(start % m);
+    const double l = lam[j];
+    double acc = 0.0;
+    for (long t = start; t < n * m; t += usable) {
+      const long r = t / m;
+      const D2 a = AS[r * ld + j], b = MS[r * ld + j];
+      const D2 v = make_double2(a.x - l * b.x, a.y - l * b.y);
+      R[t] = v;
+      acc = fma(v.x, v.x, acc);
+      acc = fma(v.y, v.y, acc);
+    }
+    atomicAdd(&sred[j], acc);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(rn2 + j, sred[j]);
+}
+
+// Rayleigh-Ritz rotation, in place on the basis arrays (pitch ld = 3m):
+//   P_new = sum_{i>=m} S_i C[i][:],  X_new = sum_{i<m} S_i C[i][:] + P_new
+// one warp per row, lane = output column; k = number of active basis columns (m, 2m or 3m)
+__global__ void k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k,
+                            int m, const D2 *__restrict__ C, long n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  D2 *sC = reinterpret_cast<D2 *>(smem_raw);
+  for (int t = threadIdx.x; t < k * m; t += blockDim.x) sC[t] = C[t];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long r = warp; r < n; r += nwarps) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      D2 *row = (a == 0 ? S : (a == 1 ? AS : MS)) + r * ld;
+      D2 x = make_double2(0.0, 0.0), pn = make_double2(0.0, 0.0);
+      if (lane < m) {
+        for (int i = 0; i < m; i++) {
+          const D2 s = row[i], c = sC[i * m + lane];
+          x.x = fma(s.x, c.x, x.x); x.x = fma(-s.y, c.y, x.x);
+          x.y = fma(s.x, c.y, x.y); x.y = fma(s.y, c.x, x.y);
+        }
+        for (int i = m; i < k; i++) {
+          const D2 s = row[i], c = sC[i * m + lane];
+          pn.x = fma(s.x, c.x, pn.x); pn.x = fma(-s.y, c.y, pn.x);
+          pn.y = fma(s.x, c.y, pn.y); pn.y = fma(s.y, c.x, pn.y);
+        }
+      }
+      __syncwarp();
+      if (lane < m) {
+        row[lane] = make_double2(x.x + pn.x, x.y + pn.y);
+        row[2 * m + lane] = pn;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Chebyshev: d = c0 * jac .* r ; x = d
+__global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ d,
+                             D2 *__restrict__ x, double c0, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[t / m];
+    const D2 v = r[t];
+    const D2 o = make_double2(s * v.x, s * v.y);
+    d[t] = o;
+    x[t] = o;
+  }
+}
+// r -= q ; d = a*d + b * jac .* r ; x += d
+__global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict__ q, D2 *__restrict__ r,
+                            D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = b * jac[t / m];
+    const D2 qq = q[t];
+    D2 rr = r[t];
+    rr.x -= qq.x; rr.y -= qq.y;
+    r[t] = rr;
+    D2 dd = d[t];
+    dd.x = a * dd.x + s * rr.x;
+    dd.y = a * dd.y + s * rr.y;
+    d[t] = dd;
+    D2 xx = x[t];
+    xx.x += dd.x; xx.y += dd.y;
+    x[t] = xx;
+  }
+}
+
+// jac[i] = 1 / (dA[i] + sigma * dM[i])
+__global__ void k_make_jacobi(const double *dA, const double *dM, double sigma, double *jac, long n) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    const double d = dA[t] + sigma * dM[t];
+    jac[t] = d > 0 ? 1.0 / d : 0.0;
+  }
+}
+
+// PCG on S0 (columns independent).  scal layout (device doubles, m each):
+//   [0] rz  [1] pq  [2] rz_new  [3] rr
+// step1: alpha = rz/pq ; phi += alpha p ; r -= alpha q ; z = jac .* r ; rz_new += <r,z> ; rr += <r,r>
+__global__ void k_cg_step1(const double *__restrict__ jac, const D2 *__restrict__ p, const D2 *__restrict__ q,
+                           D2 *__restrict__ phi, D2 *__restrict__ r, D2 *__restrict__ z,
+                           double *__restrict__ scal, long n, int m) {
+  extern __shared__ double sred[];   // [2][m]
+  for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) sred[j] = 0.0;
+  __syncthreads();
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long usable = (nthreads / m) * m;
+  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (start < usable) {
+    const int j = (int)(start % m);
+    const double pq = scal[m + j];
+    const double alpha = pq != 0.0 ? scal[j] / pq : 0.0;
+    double a_rz = 0.0, a_rr = 0.0;
+    for (long t = start; t < n * m; t += usable) {
+      const D2 pp = p[t], qq = q[t];
+      D2 f = phi[t], rr = r[t];
+      f.x = fma(alpha, pp.x, f.x); f.y = fma(alpha, pp.y, f.y);
+      rr.x = fma(-alpha, qq.x, rr.x); rr.y = fma(-alpha, qq.y, rr.y);
+      phi[t] = f;
+      r[t] = rr;
+      const double s = jac[t / m];
+      const D2 zz = make_double2(s * rr.x, s * rr.y);
+      z[t] = zz;
+      a_rz = fma(rr.x, zz.x, a_rz); a_rz = fma(rr.y, zz.y, a_rz);
+      a_rr = fma(rr.x, rr.x, a_rr); a_rr = fma(rr.y, rr.y, a_rr);
+    }
+    atomicAdd(&sred[j], a_rz);
+    atomicAdd(&sred[m + j], a_rr);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    atomicAdd(scal + 2 * m + j, sred[j]);
+    atomicAdd(scal + 3 * m + j, sred[m + j]);
+  }
+}
+// step2: beta = rz_new / rz ; p = z + beta p
+__global__ void k_cg_step2(const D2 *__restrict__ z, D2 *__restrict__ p, const double *__restrict__ scal,
+                           long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % m);
+    const double rz = scal[j];
+    const double beta = rz != 0.0 ? scal[2 * m + j] / rz : 0.0;
+    const D2 zz = z[t], pp = p[t];
+    p[t] = make_double2(fma(beta, pp.x, zz.x), fma(beta, pp.y, zz.y));
+  }
+}
+// rz <- rz_new ; pq, rz_new, rr <- 0
+__global__ void k_cg_roll(double *scal, int m) {
+  const int j = threadIdx.x;
+  if (j < m) {
+    scal[j] = scal[2 * m + j];
+    scal[m + j] = 0.0; scal[2 * m + j] = 0.0; scal[3 * m + j] = 0.0;
+  }
+}
+// z = jac .* r ; p = z ; rz += <r,z> ; rr += <r,r>
+__global__ void k_cg_init(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ z,
+                          D2 *__restrict__ p, double *__restrict__ scal, long n, int m) {
+  extern __shared__ double sred[];
+  for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) sred[j] = 0.0;
+  __syncthreads();
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long usable = (nthreads / m) * m;
+  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (start < usable) {
+    const int j = (int)(start % m);
+    double a_rz = 0.0, a_rr = 0.0;
+    for (long t = start; t < n * m; t += usable) {
+      const D2 rr = r[t];
+      const double s = jac[t / m];
+      const D2 zz = make_double2(s * rr.x, s * rr.y);
+      z[t] = zz;
+      p[t] = zz;
+      a_rz = fma(rr.x, zz.x, a_rz); a_rz = fma(rr.y, zz.y, a_rz);
+      a_rr = fma(rr.x, rr.x, a_rr); a_rr = fma(rr.y, rr.y, a_rr);
+    }
+    atomicAdd(&sred[j], a_rz);
+    atomicAdd(&sred[m + j], a_rr);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    atomicAdd(scal + j, sred[j]);
+    atomicAdd(scal + 3 * m + j, sred[m + j]);
+  }
+}
+// pq[j] += Re <p_j, q_j>
+__global__ void k_cg_pq(const D2 *__restrict__ p, const D2 *__restrict__ q, double *__restrict__ scal,
+                        long n, int m) {
+  extern __shared__ double sred[];
+  for (int j = threadIdx.x; j < m; j += blockDim.x) sred[j] = 0.0;
+  __syncthreads();
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long usable = (nthreads / m) * m;
+  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (start < usable) {
+    double acc = 0.0;
+    for (long t = start; t < n * m; t += usable) {
+      const D2 a = p[t], b = q[t];
+      acc = fma(a.x, b.x, acc); acc = fma(a.y, b.y, acc);
+    }
+    atomicAdd(&sred[start % m], acc);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(scal + m + j, sred[j]);
+}
+// X[:, :m] (pitch ld) -= G (contiguous n x m)
+__global__ void k_sub_strided(D2 *__restrict__ X, int ld, const D2 *__restrict__ G, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long r = t / m;
+    const int j = (int)(t - r * m);
+    D2 x = X[r * ld + j];
+    const D2 g = G[t];
+    x.x -= g.x; x.y -= g.y;
+    X[r * ld + j] = x;
+  }
+}
+
+double env_double(const char *name, double dflt) {
+  const char *s = std::getenv(name);
+  return s ? std::atof(s) : dflt;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// x (n x nvec, pitch ldx) <- x - G S0^-1 G^H M x      (maxwell_bloch.cpp:2280-2290)
+// ------------------------------------------------------------------------------------------
+struct ProjWork {
+  DevBuf<D2> rhs, phi, z, p, q, g;
+  DevBuf<double> scal;
+};
+static ProjWork &proj_work(bloch_handle_s *h) {
+  static thread_local std::vector<std::pair<bloch_handle_s *, ProjWork *>> pool;
+  for (auto &e : pool) if (e.first == h) return *e.second;
+  pool.emplace_back(h, new ProjWork());
+  return *pool.back().second;
+}
+
+static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_tol, int max_it, int *iters) {
+  cudaStream_t s = h->stream;
+  const long N = h->N, N0 = h->N0;
+  const int m = nvec;
+  ProjWork &w = proj_work(h);
+  w.rhs.alloc((size_t)N0 * m); w.phi.alloc((size_t)N0 * m); w.z.alloc((size_t)N0 * m);
+  w.p.alloc((size_t)N0 * m); w.q.alloc((size_t)N0 * m); w.g.alloc((size_t)N * m);
+  w.scal.alloc(4 * m);
+  // rhs = G^H M x
+  BLOCH_CUDA(cudaMemsetAsync(w.rhs.p, 0, sizeof(D2) * N0 * m, s));
+  BLOCH_CUDA(launch_h1_op(h->p, 2, h->tabs, h->E, x, ldx, w.rhs.p, m, m, s));
+  BLOCH_CUDA(cudaMemsetAsync(w.phi.p, 0, sizeof(D2) * N0 * m, s));
+  BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * 4 * m, s));
+  const unsigned g0 = grid_for(N0 * m);
+  k_cg_init<<<g0, TPB, sizeof(double) * 2 * m, s>>>(h->d_jac0.p, w.rhs.p, w.z.p, w.p.p, w.scal.p, N0, m);
+  h->count_launch(2);
+  std::vector<double> hs(4 * m), rr0(m);
+  BLOCH_CUDA(cudaMemcpyAsync(hs.data(), w.scal.p, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  for (int j = 0; j < m; j++) rr0[j] = hs[3 * m + j];
+  double rmax0 = 0;
+  for (int j = 0; j < m; j++) rmax0 = std::max(rmax0, rr0[j]);
+  int it = 0;
+  if (rmax0 > 0) {
+    // rr slot was used for the initial norm; clear it
+    BLOCH_CUDA(cudaMemsetAsync(w.scal.p + 3 * m, 0, sizeof(double) * m, s));
+    const int check_every = 8;
+    for (it = 1; it <= max_it; it++) {
+      BLOCH_CUDA(cudaMemsetAsync(w.q.p, 0, sizeof(D2) * N0 * m, s));
+      BLOCH_CUDA(launch_h1_op(h->p, 0, h->tabs, h->E, w.p.p, m, w.q.p, m, m, s));
+      k_cg_pq<<<g0, TPB, sizeof(double) * m, s>>>(w.p.p, w.q.p, w.scal.p, N0, m);
+      k_cg_step1<<<g0, TPB, sizeof(double) * 2 * m, s>>>(h->d_jac0.p, w.p.p, w.q.p, w.phi.p, w.rhs.p, w.z.p, w.scal.p, N0, m);
+      k_cg_step2<<<g0, TPB, 0, s>>>(w.z.p, w.p.p, w.scal.p, N0, m);
+      h->count_launch(4);
+      const bool check = (it % check_every == 0) || it == max_it;
+      if (check) BLOCH_CUDA(cudaMemcpyAsync(hs.data(), w.scal.p, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+      k_cg_roll<<<1, 64, 0, s>>>(w.scal.p, m);
+      h->count_launch();
+      if (check) {
+        BLOCH_CUDA(cudaStreamSynchronize(s));
+        bool done = true;
+        for (int j = 0; j < m; j++)
+          if (hs[3 * m + j] > rel_tol * rel_tol * rr0[j]) done = false;
+        if (done) break;
+      }
+    }
+    // x -= G phi
+    BLOCH_CUDA(launch_h1_op(h->p, 1, h->tabs, h->E, w.phi.p, m, w.g.p, m, m, s));
+    k_sub_strided<<<grid_for(N * m), TPB, 0, s>>>(x, ldx, w.g.p, N, m);
+    h->count_launch(2);
+  }
+  h->stats.inner_iterations += it;
+  if (iters) *iters = it;
+}
+
+void bloch_handle_s::project(D2 *x, int nvec, double rel_tol, int *iters) {
+  if (d_jac0.n < (size_t)N0) {
+    d_jac0.alloc(N0);
+  }
+  k_make_jacobi<<<grid_for(N0), TPB, 0, stream>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
+  count_launch();
+  project_ld(this, x, nvec, nvec, rel_tol, 3000, iters);
+}
+
+// ------------------------------------------------------------------------------------------
+// Solve(): block LOBPCG
+// ------------------------------------------------------------------------------------------
+void bloch_handle_s::solve() {
+  using dense::cplx;
+  using dense::Mat;
+  cudaStream_t s = stream;
+  const int nb = nbands;
+  int mb = nb + std::max(4, nb / 4);
+  if (mb > 32) mb = 32;
+  if (3L * mb > N) mb = (int)(N / 3);
+  if (nb > mb) throw std::invalid_argument("problem too small for the requested number of bands");
+  if (block != mb) { have_vectors = 0; block = mb; }
+  const int ld = 3 * mb;
+  const long Nl = N;
+
+  cudaEvent_t ev0, ev1;
+  BLOCH_CUDA(cudaEventCreate(&ev0));
+  BLOCH_CUDA(cudaEventCreate(&ev1));
+  BLOCH_CUDA(cudaEventRecord(ev0, s));
+  stats.iterations = 0;
+  stats.converged = 0;
+  stats.inner_iterations = 0;
+
+  // ---- preconditioner data: sigma, Jacobi, lambda_max estimate ----
+  const double vol23 = std::cbrt(mesh.volume) * std::cbrt(mesh.volume);
+  sigma = env_double("BLOCH_SIGMA_SCALE", 4.0) / vol23 + beta * beta;
+  cheb_degree = (int)env_double("BLOCH_CHEB_DEGREE", 10);
+  const double cheb_ratio = env_double("BLOCH_CHEB_RATIO", 50.0);
+  const double proj_tol = env_double("BLOCH_PROJ_TOL", 1e-9);
+  const bool warm = env_double("BLOCH_WARM_START", 1.0) != 0.0;
+  const bool verbose = env_double("BLOCH_VERBOSE", 0.0) != 0.0;
+  d_jac.alloc(Nl);
+  d_jac0.alloc(N0);
+  k_make_jacobi<<<grid_for(Nl), TPB, 0, s>>>(d_diagA.p, d_diagM.p, sigma, d_jac.p, Nl);
+  k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
+  count_launch(2);
+
+  DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb;
+  DevBuf<D2> dC, dGA, dGM;
+  DevBuf<double> dlam, drn;
+  S.alloc((size_t)Nl * ld); AS.alloc((size_t)Nl * ld); MS.alloc((size_t)Nl * ld);
+  R.alloc((size_t)Nl * mb); Wc.alloc((size_t)Nl * mb); Dd.alloc((size_t)Nl * mb);
+  Tq.alloc((size_t)Nl * mb); Qb.alloc((size_t)Nl * mb);
+  dC.alloc((size_t)ld * mb); dGA.alloc((size_t)ld * ld); dGM.alloc((size_t)ld * ld);
+  dlam.alloc(mb); drn.alloc(mb);
+
+  auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
+    BLOCH_CUDA(cudaMemset2DAsync(y, sizeof(D2) * ldy, 0, sizeof(D2) * nvec, Nl, s));
+    BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, s));
+    count_launch();
+    if (ca != 0.0) stats.applies_A += nvec;
+  };
+
+  // lambda_max(D^-1 (A + sigma M)) by power iteration on one vector
+  {
+    DevBuf<double> dn;
+    dn.alloc(1);
+    BLOCH_CUDA(launch_fill_random(Wc.p, Nl, 0x5eedULL, s));
+    double lam = 1.0;
+    for (int itp = 0; itp < 12; itp++) {
+      op(Wc.p, 1, Tq.p, 1, 1, 1.0, sigma);
+      BLOCH_CUDA(launch_diag_scale(d_jac.p, Tq.p, Tq.p, Nl, 1, s));
+      double n2[2];
+      BLOCH_CUDA(launch_col_dot(Tq.p, Tq.p, Nl, 1, dn.p, s));
+      BLOCH_CUDA(cudaMemcpyAsync(&n2[0], dn.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      BLOCH_CUDA(launch_col_dot(Wc.p, Wc.p, Nl, 1, dn.p, s));
+      BLOCH_CUDA(cudaMemcpyAsync(&n2[1], dn.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      BLOCH_CUDA(cudaStreamSynchronize(s));
+      count_launch(3);
+      lam = std::sqrt(n2[0] / n2[1]);
+      BLOCH_CUDA(launch_axpby(1.0 / std::sqrt(n2[0]), Tq.p, 0.0, Wc.p, Nl, s));
+      count_launch();
+    }
+    lmaxA = 1.1 * lam;
+  }
+  const double lmax = lmaxA, lmin = lmaxA / cheb_ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+
+  // out = T r_in (both contiguous N x mb, r_in preserved): Chebyshev iteration on A + sigma M
+  auto precondition = [&](const D2 *r_in, D2 *out) {
+    BLOCH_CUDA(cudaMemcpyAsync(Tq.p, r_in, sizeof(D2) * Nl * mb, cudaMemcpyDeviceToDevice, s));
+    const unsigned g = grid_for(Nl * mb);
+    k_cheb_first<<<g, TPB, 0, s>>>(d_jac.p, Tq.p, Dd.p, out, 1.0 / theta, Nl, mb);
+    count_launch();
+    double rho = 1.0 / sigma1;
+    for (int k = 1; k < cheb_degree; k++) {
+      op(Dd.p, mb, Qb.p, mb, mb, 1.0, sigma);
+      const double rho_n = 1.0 / (2.0 * sigma1 - rho);
+      k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / delta, Nl, mb);
+      count_launch();
+      rho = rho_n;
+    }
+  };
+
+  // Rayleigh-Ritz on the first k basis columns; returns false if the Gram matrix is not PD
+  std::vector<D2> hGA((size_t)ld * ld), hGM((size_t)ld * ld);
+  std::vector<double> lam(mb, 0.0), rn(mb, 0.0);
+  auto rayleigh_ritz = [&](int k) -> bool {
+    BLOCH_CUDA(launch_gram(S.p, k, ld, AS.p, k, ld, Nl, dGA.p, s));
+    BLOCH_CUDA(launch_gram(S.p, k, ld, MS.p, k, ld, Nl, dGM.p, s));
+    count_launch(2);
+    BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    Mat GA((size_t)k * k), GM((size_t)k * k), C;
+    for (int i = 0; i < k; i++)
+      for (int j = 0; j < k; j++) {
+        // Hermitian part (the two triangles are computed independently on the device)
+        const D2 a = hGA[i * k + j], at = hGA[j * k + i], b = hGM[i * k + j], bt = hGM[j * k + i];
+        GA[i * k + j] = 0.5 * cplx(a.x + at.x, a.y - at.y);
+        GM[i * k + j] = 0.5 * cplx(b.x + bt.x, b.y - bt.y);
+      }
+    std::vector<double> l;
+    if (!dense::hegv_lowest(k, mb, GA, GM, l, C)) return false;
+    std::vector<D2> hC((size_t)k * mb);
+    for (size_t i = 0; i < hC.size(); i++) hC[i] = make_double2(C[i].real(), C[i].imag());
+    lam = l;
+    BLOCH_CUDA(cudaMemcpyAsync(dC.p, hC.data(), sizeof(D2) * hC.size(), cudaMemcpyHostToDevice, s));
+    BLOCH_CUDA(cudaMemcpyAsync(dlam.p, lam.data(), sizeof(double) * mb, cudaMemcpyHostToDevice, s));
+    const unsigned g = (unsigned)std::min<long>((Nl + 7) / 8, 148L * 8);
+    k_rr_update<<<g, 256, sizeof(D2) * k * mb, s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+    count_launch();
+    BLOCH_CUDA(cudaStreamSynchronize(s));   // hC / lam are stack-lifetime host buffers
+    return true;
+  };
+
+  // ---- initial block ----
+  if (n_init > 0) {
+    const int mi = std::min(n_init, mb);
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)2 * Nl * mi);
+    BLOCH_CUDA(cudaMemcpyAsync(tmp.p, init_vecs.data(), sizeof(double) * 2 * Nl * mi, cudaMemcpyHostToDevice, s));
+    BLOCH_CUDA(launch_fill_random(Wc.p, Nl * mb, 0xB10C4ULL, s));
+    BLOCH_CUDA(launch_pack(tmp.p, Dd.p, Nl, mi, s));
+    BLOCH_CUDA(cudaMemcpy2DAsync(Wc.p, sizeof(D2) * mb, Dd.p, sizeof(D2) * mi, sizeof(D2) * mi, Nl, cudaMemcpyDeviceToDevice, s));
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    count_launch(2);
+  } else if (warm && have_vectors == mb && d_X.n >= (size_t)Nl * mb) {
+    BLOCH_CUDA(cudaMemcpyAsync(Wc.p, d_X.p, sizeof(D2) * Nl * mb, cudaMemcpyDeviceToDevice, s));
+  } else {
+    BLOCH_CUDA(launch_fill_random(Wc.p, Nl * mb, 0xB10C4ULL, s));
+    count_launch();
+  }
+  {
+    int its = 0;
+    project_ld(this, Wc.p, mb, mb, std::min(proj_tol, 1e-10), 3000, &its);
+    BLOCH_CUDA(cudaMemcpy2DAsync(S.p, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
+    op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);
+    op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
+    if (!rayleigh_ritz(mb)) throw std::runtime_error("initial block is rank deficient");
+  }
+
+  bool have_P = false;
+  int it = 0, nconv = 0;
+  double maxres = 0;
+  for (it = 0; it < max_iter; it++) {
+    // residuals and their norms
+    BLOCH_CUDA(cudaMemsetAsync(drn.p, 0, sizeof(double) * mb, s));
+    k_resid_norm<<<grid_for(Nl * mb), TPB, sizeof(double) * mb, s>>>(AS.p, MS.p, ld, dlam.p, R.p, Nl, mb, drn.p);
+    count_launch();
+    BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * mb, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    nconv = 0;
+    maxres = 0;
+    for (int j = 0; j < nb; j++) {
+      const double r = std::sqrt(rn[j]);
+      maxres = std::max(maxres, r);
+      if (r <= tol) nconv++;
+    }
+    if (verbose) {
+      std::printf("[lobpcg] it %3d conv %2d maxres %.3e lam:", it, nconv, maxres);
+      for (int j = 0; j < std::min(nb, 6); j++) std::printf(" %.8f", lam[j]);
+      std::printf("\n");
+    }
+    if (nconv == nb) break;
+    // W = P_proj T R
+    precondition(R.p, Wc.p);
+    int its = 0;
+    project_ld(this, Wc.p, mb, mb, proj_tol, 3000, &its);
+    BLOCH_CUDA(cudaMemcpy2DAsync(S.p + mb, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
+    op(S.p + mb, ld, AS.p + mb, ld, mb, 1.0, 0.0);
+    op(S.p + mb, ld, MS.p + mb, ld, mb, 0.0, 1.0);
+    bool ok = rayleigh_ritz(have_P ? 3 * mb : 2 * mb);
+    if (!ok && have_P) ok = rayleigh_ritz(2 * mb);   // restart without P
+    if (!ok) throw std::runtime_error("Rayleigh-Ritz failed (basis numerically rank deficient)");
+    have_P = true;
+  }
+  stats.iterations = it;
+  stats.converged = nconv;
+  stats.max_residual = maxres;
+  eigenvalues.assign(lam.begin(), lam.begin() + nb);
+  d_X.alloc((size_t)Nl * mb);
+  BLOCH_CUDA(cudaMemcpy2DAsync(d_X.p, sizeof(D2) * mb, S.p, sizeof(D2) * ld, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
+  have_vectors = mb;
+  BLOCH_CUDA(cudaEventRecord(ev1, s));
+  BLOCH_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  stats.seconds = 1e-3 * ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+}

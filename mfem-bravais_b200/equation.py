@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference interface for this path, over the C ABI:
+
+  * BravaisLattice            <-> bravais::BravaisLattice           (lib/bravais.hpp:64-181)
+  * MaxwellBlochWaveEquation  <-> mfem::bloch::MaxwellBlochWaveEquation (maxwell/maxwell_bloch.hpp:140-234)
+
+Same method names and argument meaning as the reference; MFEM types are flattened to numpy
+arrays.  Vectors of length 2N are stored [re(N); im(N)] like the reference's block vectors.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import BlochError, check, dptr
+
+
+class BravaisLattice:
+    """BravaisLatticeFactory(type, a, b, c, alpha, beta, gamma) (lib/bravais.cpp:8598-8846)."""
+
+    def __init__(self, lattice_type, a=1.0, b=1.0, c=1.0, alpha=0.0, beta=0.0, gamma=0.0):
+        if isinstance(lattice_type, str):
+            lattice_type = capi.LATTICE_TYPES[lattice_type.upper()]
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        check(self._L.bloch_lattice_create(C.byref(self._h), int(lattice_type), a, b, c, alpha, beta, gamma),
+              "bloch_lattice_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.bloch_lattice_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _label(self, fn, *args):
+        buf = C.create_string_buffer(64)
+        check(fn(self._h, *args, buf, 64))
+        return buf.value.decode()
+
+    def GetLatticeTypeLabel(self):
+        return self._label(self._L.bloch_lattice_label)
+
+    def GetUnitCellVolume(self):
+        return self._L.bloch_lattice_volume(self._h)
+
+    def GetLatticeVectors(self):
+        a = np.zeros((3, 3))
+        check(self._L.bloch_lattice_vectors(self._h, dptr(a), None))
+        return a
+
+    def GetReciprocalLatticeVectors(self):
+        b = np.zeros((3, 3))
+        check(self._L.bloch_lattice_vectors(self._h, None, dptr(b)))
+        return b
+
+    def GetTranslationVectors(self):
+        n = self._L.bloch_lattice_num_translations(self._h)
+        t = np.zeros((n, 3))
+        check(self._L.bloch_lattice_translations(self._h, dptr(t), None))
+        return t
+
+    def GetFaceRadii(self):
+        n = self._L.bloch_lattice_num_translations(self._h)
+        r = np.zeros(n)
+        check(self._L.bloch_lattice_translations(self._h, None, dptr(r)))
+        return r
+
+    def GetNumberSymmetryPoints(self):
+        return self._L.bloch_lattice_num_symmetry_points(self._h)
+
+    def GetSymmetryPoint(self, i):
+        k = np.zeros(3)
+        check(self._L.bloch_lattice_symmetry_point(self._h, i, dptr(k), None, 0))
+        return k
+
+    def GetSymmetryPointLabel(self, i):
+        buf = C.create_string_buffer(64)
+        check(self._L.bloch_lattice_symmetry_point(self._h, i, None, buf, 64))
+        return buf.value.decode()
+
+    def GetSymmetryPointIndex(self, label):
+        return self._L.bloch_lattice_symmetry_point_index(self._h, label.encode())
+
+    def GetNumberPaths(self):
+        return self._L.bloch_lattice_num_paths(self._h)
+
+    def GetNumberPathSegments(self, p):
+        return check(self._L.bloch_lattice_num_path_segments(self._h, p))
+
+    def GetPathSegmentEndPointIndices(self, p, s):
+        e0, e1 = C.c_int(), C.c_int()
+        check(self._L.bloch_lattice_path_segment(self._h, p, s, C.byref(e0), C.byref(e1)))
+        return e0.value, e1.value
+
+    def GetIntermediatePoint(self, p, s):
+        k = np.zeros(3)
+        check(self._L.bloch_lattice_intermediate_point(self._h, p, s, dptr(k), None, 0))
+        return k
+
+    def GetIntermediatePointLabel(self, p, s):
+        buf = C.create_string_buffer(64)
+        check(self._L.bloch_lattice_intermediate_point(self._h, p, s, None, buf, 64))
+        return buf.value.decode()
+
+    def MapToPrimitiveCell(self, pt):
+        pt = np.ascontiguousarray(pt, float)
+        out = np.zeros(3)
+        mapped = self._L.bloch_lattice_map_to_primitive_cell(self._h, dptr(pt), dptr(out))
+        return bool(mapped), out
+
+
+class MaxwellBlochWaveEquation:
+    """MaxwellBlochWaveEquation(pmesh, order): here the periodic Wigner-Seitz hex mesh is
+    described by (lattice, n_sub) - n_sub = 2^r reproduces r uniform refinements."""
+
+    def __init__(self, lattice, n_sub, order, device=-1):
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        self.lattice = lattice
+        check(self._L.bloch_create(C.byref(self._h), lattice._h, int(n_sub), int(order), int(device)),
+              "bloch_create")
+        ne, nc = C.c_int64(), C.c_int()
+        check(self._L.bloch_num_elements(self._h, C.byref(ne), C.byref(nc)))
+        self.n_elem, self.n_class = ne.value, nc.value
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._L.bloch_num_dofs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        self.N, self.N_rt, self.N_h1 = a.value, b.value, c.value
+        self.order = int(order)
+        self.nev = 20
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.bloch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # ---- sizes / geometry ----
+    def GetHCurlTrueVSize(self):
+        return self.N
+
+    def mesh_counts(self):
+        v, e, f, vol = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        check(self._L.bloch_mesh_counts(self._h, C.byref(v), C.byref(e), C.byref(f), C.byref(vol)))
+        return v.value, e.value, f.value, vol.value
+
+    def element_centers(self):
+        c = np.zeros((self.n_elem, 3))
+        check(self._L.bloch_element_centers(self._h, dptr(c)))
+        return c
+
+    def element_geometry(self):
+        x0 = np.zeros((self.n_elem, 3))
+        cls = np.zeros(self.n_elem, dtype=np.int32)
+        J = np.zeros((self.n_class, 3, 3))
+        check(self._L.bloch_element_geometry(self._h, dptr(x0), cls.ctypes.data_as(C.POINTER(C.c_int)), dptr(J)))
+        return x0, cls, J
+
+    def dofmap(self, space):
+        """space: 'h1' | 'nd' | 'rt' -> (gid[n_elem, L], sign[n_elem, L])"""
+        sp = {"h1": 0, "nd": 1, "rt": 2}[space]
+        L = self._L.bloch_local_size(self._h, sp)
+        m = np.zeros((self.n_elem, L), dtype=np.int32)
+        check(self._L.bloch_get_dofmap(self._h, sp, m.ctypes.data_as(C.POINTER(C.c_int32))))
+        return np.abs(m).astype(np.int64) - 1, np.sign(m).astype(float)
+
+    # ---- reference interface ----
+    def SetMassCoef(self, eps_per_elem):
+        e = np.ascontiguousarray(eps_per_elem, float)
+        assert e.shape == (self.n_elem,)
+        check(self._L.bloch_set_eps(self._h, dptr(e)), "bloch_set_eps")
+
+    def SetStiffnessCoef(self, muinv_per_elem):
+        e = np.ascontiguousarray(muinv_per_elem, float)
+        assert e.shape == (self.n_elem,)
+        check(self._L.bloch_set_muinv(self._h, dptr(e)), "bloch_set_muinv")
+
+    def SetKappa(self, kappa):
+        k = np.ascontiguousarray(kappa, float)
+        check(self._L.bloch_set_kappa(self._h, dptr(k)), "bloch_set_kappa")
+
+    def SetNumEigs(self, nev):
+        """nev counts REAL modes like the reference (2 per complex band)."""
+        self.nev = int(nev)
+        check(self._L.bloch_set_num_bands(self._h, (self.nev + 1) // 2), "bloch_set_num_bands")
+
+    def SetAbsoluteTolerance(self, atol, max_iter=2000):
+        check(self._L.bloch_set_tol(self._h, float(atol), int(max_iter)), "bloch_set_tol")
+
+    def Setup(self):
+        check(self._L.bloch_setup(self._h), "bloch_setup")
+
+    def SetInitialVectors(self, vecs):
+        if vecs is None or len(vecs) == 0:
+            check(self._L.bloch_set_initial_vectors(self._h, 0, None))
+            return
+        v = np.ascontiguousarray(vecs, float)
+        assert v.ndim == 2 and v.shape[1] == 2 * self.N
+        check(self._L.bloch_set_initial_vectors(self._h, v.shape[0], dptr(v)), "bloch_set_initial_vectors")
+
+    def Solve(self):
+        check(self._L.bloch_solve(self._h), "bloch_solve")
+
+    def GetEigenvalues(self, nev=None, kappa=None, init_vecs=None):
+        """GetEigenvalues(eigenvalues) or the 4-argument convenience form
+        (SetNumEigs + SetKappa + Setup + SetInitialVectors + Solve + get, maxwell_bloch.cpp:1078-1097).
+        Returns nev values: each complex band twice, like the reference's real block form."""
+        if kappa is not None:
+            self.SetNumEigs(nev)
+            self.SetKappa(kappa)
+            self.Setup()
+            if init_vecs is not None:
+                self.SetInitialVectors(init_vecs)
+            self.Solve()
+        nb = (self.nev + 1) // 2
+        lam = np.zeros(nb)
+        check(self._L.bloch_get_eigenvalues(self._h, dptr(lam), nb), "bloch_get_eigenvalues")
+        return np.repeat(lam, 2)[: self.nev]
+
+    def band_eigenvalues(self):
+        nb = (self.nev + 1) // 2
+        lam = np.zeros(nb)
+        check(self._L.bloch_get_eigenvalues(self._h, dptr(lam), nb), "bloch_get_eigenvalues")
+        return lam
+
+    def GetEigenvectorE(self, i):
+        re, im = np.zeros(self.N), np.zeros(self.N)
+        check(self._L.bloch_get_eigenvector_E(self._h, i, dptr(re), dptr(im)), "bloch_get_eigenvector_E")
+        return re, im
+
+    def GetEigenvectorB(self, i):
+        re, im = np.zeros(self.N_rt), np.zeros(self.N_rt)
+        check(self._L.bloch_get_eigenvector_B(self._h, i, dptr(re), dptr(im)), "bloch_get_eigenvector_B")
+        return re, im
+
+    def GetSolverStats(self):
+        st = capi.bloch_stats()
+        check(self._L.bloch_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def _apply(self, fn, x, nout):
+        x = np.ascontiguousarray(x, float)
+        single = x.ndim == 1
+        x2 = x.reshape(1, -1) if single else x
+        y = np.zeros((x2.shape[0], 2 * nout))
+        check(fn(self._h, dptr(x2), dptr(y), x2.shape[0]))
+        return y[0] if single else y
+
+    def MultA(self, x):      # GetAOperator()->Mult
+        return self._apply(self._L.bloch_apply_A, x, self.N)
+
+    def MultM(self, x):      # GetMOperator()->Mult
+        return self._apply(self._L.bloch_apply_M, x, self.N)
+
+    def MultProjector(self, x):   # GetSubSpaceProjector()->Mult
+        return self._apply(self._L.bloch_apply_projector, x, self.N)
+
+    def MultC(self, x):      # C_ block operator (curl + kappa cross)
+        return self._apply(self._L.bloch_apply_C, x, self.N_rt)
+
+    def debug_h1op(self, mode, x):
+        x = np.ascontiguousarray(x, float)
+        x2 = x.reshape(1, -1) if x.ndim == 1 else x
+        nout = self.N if mode == 1 else self.N_h1
+        y = np.zeros((x2.shape[0], 2 * nout))
+        check(self._L.bloch_debug_apply_h1op(self._h, mode, dptr(x2), dptr(y), x2.shape[0]))
+        return y[0] if x.ndim == 1 else y
+
+    # device-pointer entry points (integers = CUDA device addresses, e.g. torch tensor.data_ptr())
+    def set_stream(self, stream_ptr):
+        check(self._L.bloch_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def apply_A_device(self, x_ptr, y_ptr, nvec):
+        check(self._L.bloch_apply_A_device(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), nvec))
+
+    def apply_M_device(self, x_ptr, y_ptr, nvec):
+        check(self._L.bloch_apply_M_device(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), nvec))
+
+    def pack_device(self, reim_ptr, blk_ptr, nvec):
+        check(self._L.bloch_pack_device(self._h, C.c_void_p(reim_ptr), C.c_void_p(blk_ptr), nvec))
+
+    def unpack_device(self, blk_ptr, reim_ptr, nvec):
+        check(self._L.bloch_unpack_device(self._h, C.c_void_p(blk_ptr), C.c_void_p(reim_ptr), nvec))

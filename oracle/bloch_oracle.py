@@ -409,8 +409,12 @@ class Spaces:
             self.h1_gid = dofmaps["h1_gid"]
             self.n_nd = int(self.nd_gid.max()) + 1
             self.n_h1 = int(self.h1_gid.max()) + 1
-            rt_dirs = [np.einsum("ji,lj->li", np.linalg.inv(J), eye[ref.rt_comp]) for J in mesh.J]
-            self.rt_gid, self.rt_sign, self.n_rt = _identify(mesh, ref.rt_nodes, rt_dirs)
+            if "rt_gid" in dofmaps:
+                self.rt_gid, self.rt_sign = dofmaps["rt_gid"], dofmaps["rt_sign"]
+                self.n_rt = int(self.rt_gid.max()) + 1
+            else:
+                rt_dirs = [np.einsum("ji,lj->li", np.linalg.inv(J), eye[ref.rt_comp]) for J in mesh.J]
+                self.rt_gid, self.rt_sign, self.n_rt = _identify(mesh, ref.rt_nodes, rt_dirs)
         self.h1_sign = np.ones_like(self.h1_gid, dtype=float)
 
 
