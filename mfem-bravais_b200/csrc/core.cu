@@ -98,8 +98,41 @@ static void class_params(const double *J, const double kappa[3], double out[kCla
 
 // element-local diagonals of A, M1 and S0 per class, obtained by running the production kernels
 // on a probe problem (one private copy of the element per local unit vector)
+// largest eigenvalue of diag(X)^-1/2 X diag(X)^-1/2 for a Hermitian PSD local matrix (power iteration)
+static double local_scaled_lmax(int L, const D2 *X /* column k at X[k*L + l] */) {
+  std::vector<double> d(L);
+  for (int k = 0; k < L; k++) d[k] = X[(size_t)k * L + k].x > 0 ? 1.0 / std::sqrt(X[(size_t)k * L + k].x) : 0.0;
+  std::vector<double> vr(L), vi(L, 0.0), wr(L), wi(L);
+  for (int k = 0; k < L; k++) vr[k] = 1.0 + 0.37 * std::sin(1.0 + 2.3 * k);
+  double lam = 0;
+  for (int it = 0; it < 200; it++) {
+    for (int l = 0; l < L; l++) { wr[l] = 0; wi[l] = 0; }
+    for (int k = 0; k < L; k++) {
+      const double xr = vr[k] * d[k], xi = vi[k] * d[k];
+      const D2 *col = X + (size_t)k * L;
+      for (int l = 0; l < L; l++) {
+        wr[l] += col[l].x * xr - col[l].y * xi;
+        wi[l] += col[l].x * xi + col[l].y * xr;
+      }
+    }
+    double nw = 0, nv = 0;
+    for (int l = 0; l < L; l++) {
+      wr[l] *= d[l]; wi[l] *= d[l];
+      nw += wr[l] * wr[l] + wi[l] * wi[l];
+      nv += vr[l] * vr[l] + vi[l] * vi[l];
+    }
+    const double nl = std::sqrt(nw / nv);
+    const bool conv = std::fabs(nl - lam) < 1e-4 * nl;
+    lam = nl;
+    const double sc = 1.0 / std::sqrt(nw);
+    for (int l = 0; l < L; l++) { vr[l] = wr[l] * sc; vi[l] = wi[l] * sc; }
+    if (conv && it > 20) break;
+  }
+  return lam;
+}
+
 static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vector<double> &dM,
-                            std::vector<double> &dS0) {
+                            std::vector<double> &dS0, double *lmax_bound) {
   const int nc = h->mesh.n_class, Ln = h->L_nd, Lh = h->L_h1;
   cudaStream_t s = h->stream;
   auto run = [&](int L, bool h1space, std::vector<double> *outA, std::vector<double> *outM) {
@@ -128,6 +161,8 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
       out->resize((size_t)nc * L);
       for (int c = 0; c < nc; c++)
         for (int k = 0; k < L; k++) (*out)[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
+      if (!h1space && lmax_bound)   // lambda_max(D^-1 (a A + b M)) <= max_class max(mu_A, mu_M)
+        for (int c = 0; c < nc; c++) *lmax_bound = std::max(*lmax_bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
     };
     if (h1space) {
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
@@ -174,7 +209,9 @@ void bloch_handle_s::setup() {
   if (dirty_kappa || dirty_coef) {
     // Jacobi diagonals of A, M and S0 = G^H M G (element-local diagonals from a probe launch)
     std::vector<double> dA, dM, dS0;
-    probe_diagonals(this, dA, dM, dS0);
+    double bound = 0.0;
+    probe_diagonals(this, dA, dM, dS0, (lmax_local <= 0.0) ? &bound : nullptr);
+    if (lmax_local <= 0.0) lmax_local = bound;
     DevBuf<double> dl;
     d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0);
     BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N, stream));

@@ -88,7 +88,8 @@ struct bloch_handle_s {
   double tol = 1e-6;
   double sigma = 0;                 // shift of the preconditioner A + sigma M
   int cheb_degree = 8;
-  double lmaxA = 0;                 // estimate of lambda_max(D^-1 (A + sigma M))
+  double lmaxA = 0;                 // bound of lambda_max(D^-1 (A + sigma M)) used by Chebyshev
+  double lmax_local = 0;            // max over classes of lambda_max(diag(X_e)^-1 X_e), X = A, M
   std::vector<double> eigenvalues;  // ascending
   bloch_b200::DevBuf<D2> d_X;       // eigenvectors, block layout [N][block]
   int have_vectors = 0;             // number of valid columns in d_X

@@ -1,0 +1,160 @@
+// Device-side building blocks shared by the element kernels (kernels.cu) and the persistent
+// projector CG kernel (proj_cg.cu).  See kernels.cu for the formulation.
+#pragma once
+#include "kernels.hpp"
+
+namespace bloch_b200 {
+namespace dev {
+
+__device__ __forceinline__ double2 ld2(const double2 *p) { return *p; }
+
+#define CFMA(acc, a, z)            \
+  {                                \
+    (acc).x = fma((a), (z).x, (acc).x); \
+    (acc).y = fma((a), (z).y, (acc).y); \
+  }
+
+template <int P>
+struct Dim {
+  static constexpr int Q = P + 1;
+  static constexpr int NB = P * Q * Q;   // ND dofs per component
+  static constexpr int RB = Q * P * P;   // RT dofs per component
+  static constexpr int LND = 3 * NB, LRT = 3 * RB, LH1 = Q * Q * Q;
+  __host__ __device__ static constexpr int nd(int c, int o, int j1, int j2) {
+    return c * NB + (o * Q + j1) * Q + j2;
+  }
+  __host__ __device__ static constexpr int rt(int c, int j, int o1, int o2) {
+    return c * RB + (j * P + o1) * P + o2;
+  }
+};
+
+// ---- in-register slab transforms: s[a][b] (Q x Q), apply matrix along both indices ----
+// FWD: out[r] = sum_j Mx[r][j] in[j] ; ADJ: out[j] = sum_r Mx[r][j] in[r]
+template <int P, bool ADJ>
+__device__ __forceinline__ void slab_transform(double2 (&s)[P + 1][P + 1], const double (&Mx)[kMaxP + 1][kMaxP + 1]) {
+  constexpr int Q = P + 1;
+  double2 u[Q][Q];
+#pragma unroll
+  for (int a = 0; a < Q; a++)
+#pragma unroll
+    for (int r = 0; r < Q; r++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double m = ADJ ? Mx[j][r] : Mx[r][j];
+        CFMA(acc, m, s[a][j]);
+      }
+      u[a][r] = acc;
+    }
+#pragma unroll
+  for (int r = 0; r < Q; r++)
+#pragma unroll
+    for (int b = 0; b < Q; b++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double m = ADJ ? Mx[j][r] : Mx[r][j];
+        CFMA(acc, m, u[j][b]);
+      }
+      s[r][b] = acc;
+    }
+}
+
+// ND buffer: transform every (c, o) slab along its two closed directions
+template <int P, int NW, int WHICH>   // WHICH: 0 = TI fwd, 1 = TI adjoint, 2 = TIinv fwd
+__device__ __forceinline__ void nd_transform_all(double2 *sND, const Tabs &T, int warp, int lane) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  for (int t = warp; t < 3 * P; t += NW) {
+    const int c = t / P, o = t - c * P;
+    double2 s[Q][Q];
+    const int base = D::nd(c, o, 0, 0);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) s[a][b] = sND[(base + a * Q + b) * 32 + lane];
+    if (WHICH == 0) slab_transform<P, false>(s, T.TI);
+    else if (WHICH == 1) slab_transform<P, true>(s, T.TI);
+    else slab_transform<P, false>(s, T.TIinv);
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) sND[(base + a * Q + b) * 32 + lane] = s[a][b];
+  }
+}
+
+// pointwise ND mass in mode space, in place:  F_c(i) <- coef * Omega(i) * sum_d H[c][d] F_d(i)
+template <int P, int NW>
+__device__ __forceinline__ void nd_mass_pointwise(double2 *sND, const Tabs &T, const double *cp,
+                                                  double coef, int warp, int lane) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1;
+  const double *H = cp + 12;
+  for (int g = warp; g < Q * Q * Q; g += NW) {
+    int i[3];
+    i[0] = g / (Q * Q);
+    i[1] = (g / Q) % Q;
+    i[2] = g % Q;
+    double w = coef;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double o = T.om[0];
+#pragma unroll
+      for (int r = 1; r < Q; r++) o = (i[d] == r) ? T.om[r] : o;
+      w *= o;
+    }
+    double2 f[3];
+    int loc[3];
+    bool ex[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      ex[c] = i[c] < P;
+      loc[c] = D::nd(c, i[c], i[(c + 1) % 3], i[(c + 2) % 3]);
+      f[c] = ex[c] ? sND[loc[c] * 32 + lane] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (ex[c]) {
+        double2 r;
+        r.x = w * (H[3 * c] * f[0].x + H[3 * c + 1] * f[1].x + H[3 * c + 2] * f[2].x);
+        r.y = w * (H[3 * c] * f[0].y + H[3 * c + 1] * f[1].y + H[3 * c + 2] * f[2].y);
+        sND[loc[c] * 32 + lane] = r;
+      }
+    }
+  }
+}
+
+template <int P>
+__device__ __forceinline__ int h1_idx(int i0, int i1, int i2) {
+  return (i0 * (P + 1) + i1) * (P + 1) + i2;
+}
+
+template <int P, int NW, bool ADJ>
+__device__ __forceinline__ void h1_transform_dir(double2 *sH, const Tabs &T, int dir, int warp, int lane) {
+  constexpr int Q = P + 1;
+  const int sd = dir == 0 ? Q * Q : (dir == 1 ? Q : 1);
+  const int s1 = dir == 0 ? Q : Q * Q, s2 = dir == 2 ? Q : 1;   // strides of the other two dirs
+  for (int t = warp; t < Q * Q; t += NW) {
+    const int a = t / Q, b = t - a * Q;
+    const int base = a * s1 + b * s2;
+    double2 in[Q], out[Q];
+#pragma unroll
+    for (int j = 0; j < Q; j++) in[j] = sH[(base + j * sd) * 32 + lane];
+#pragma unroll
+    for (int r = 0; r < Q; r++) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const double mm = ADJ ? T.TI[j][r] : T.TI[r][j];
+        CFMA(acc, mm, in[j]);
+      }
+      out[r] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) sH[(base + j * sd) * 32 + lane] = out[j];
+  }
+}
+
+
+}  // namespace dev
+}  // namespace bloch_b200

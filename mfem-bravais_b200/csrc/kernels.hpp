@@ -79,6 +79,11 @@ cudaError_t launch_scalar_div(const double *num, const double *den, double *out,
 // diagonal accumulation: d[gid] += coef_e * dloc[cls][l] over elements (real)
 cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const double *coef,
                                 const double *dloc, int n_elem, double *d, cudaStream_t s);
+// Whole block Jacobi-PCG solve of S0 phi = r0 in ONE cooperative launch (proj_cg.cu).  On entry
+// phi = 0, r = right-hand side, scal (8*m doubles) = 0; info[0] = iterations, info[1] = converged.
+cudaError_t launch_proj_cg(int p, const Tabs &T, const ElemData &E, const double *jac, double2 *phi,
+                           double2 *r, double2 *z, double2 *pp, double2 *q, double *scal, int m,
+                           long n0, int max_it, double rel_tol, int *info, cudaStream_t s);
 // fill with deterministic pseudo-random complex numbers in (-1,1)
 cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s);
 
