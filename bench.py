@@ -44,6 +44,8 @@ def parse():
                     help="concurrent k-point solves per GPU (independent handles on separate streams)")
     ap.add_argument("--apply-vectors", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--apply-study", action="store_true",
+                    help="operator-apply roofline study (configs[2]: BCC order 3, ~2.2M complex DOF, 1/4/10/30 RHS)")
     ap.add_argument("--cpu-sample-nsub", type=int, default=0, help="0 = same mesh as the workload")
     ap.add_argument("--cpu-sample-iters", type=int, default=1,
                     help="LOBPCG iterations timed per CPU sample (0 = full solves)")
@@ -289,9 +291,59 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def apply_study(args):
+    """Y = A X throughput (GDOF/s) and fractions of the HBM (32 B/DOF/vector) and fp64 rooflines."""
+    import torch
+    import mfem_bravais_b200 as m
+    hbm, how = peaks()
+    out = []
+    st = torch.cuda.Stream()
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+    fp64 = None
+    for name, p, n in [("CUB", 1, 48), ("FCC", 2, 16), ("BCC", 3, 12)]:
+        lat = m.BravaisLattice(name)
+        eq = m.MaxwellBlochWaveEquation(lat, n, p)
+        eq.SetMassCoef(m.sphere_eps(eq.element_centers()))
+        eq.set_stream(st.cuda_stream)
+        eq.SetKappa(0.5 * lat.GetSymmetryPoint(1)); eq.Setup()
+        if fp64 is None:
+            fp64 = eq.fp64_peak_tflops()
+        Q = p + 1
+        cfma = 12 * p * Q ** 3 + 12 * p * p * Q * Q + 9 * p * p * Q      # complex-by-real FMAs per element-vector
+        flops_per_dof = 4.0 * cfma * eq.n_elem / eq.N
+        for nv in (1, 4, 10, 30):
+            x = torch.rand(eq.N * nv * 2, device="cuda", dtype=torch.float64) * 2 - 1
+            y = torch.empty_like(x)
+            ts = []
+            with torch.cuda.stream(st):
+                for _ in range(5):
+                    eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
+                for _ in range(20):
+                    flush.fill_(1.0)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
+                    e1.record(st)
+                    e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e-3)
+            st.synchronize()
+            t = float(np.median(ts))
+            gd = eq.N * nv / t / 1e9
+            out.append({"lattice": name, "order": p, "n_sub": n, "N": eq.N, "vectors": nv, "median_us": t * 1e6,
+                        "best_us": float(np.min(ts)) * 1e6, "gdofs": gd,
+                        "hbm_frac": ALG_BYTES_PER_DOF * gd / hbm, "flops_per_dof": flops_per_dof,
+                        "tflops": gd * flops_per_dof / 1e3, "fp64_frac": gd * flops_per_dof / 1e3 / fp64})
+            del x, y
+        del eq
+    print(json.dumps({"apply_study": out, "hbm_peak_gbs": hbm, "hbm_peak_source": how, "fp64_peak_tflops": fp64,
+                      "note": "timing = cudaMemset of y + k_nd_apply, CUDA events, L2 flushed between launches"}))
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.apply_study:
+        apply_study(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -151,6 +151,9 @@ int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, i
  *   mode 0: y(2 N_h1) = S0 x(2 N_h1), S0 = G^T M G;  mode 1: y(2 N) = G x(2 N_h1);
  *   mode 2: y(2 N_h1) = G^T M x(2 N) */
 int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y, int nvec);
+/* Measurement hook: fp64 FMA throughput of the handle's device in TFLOP/s (roofline denominator
+ * of the flop-bound side of the element kernels; not part of the reference interface). */
+int bloch_debug_fp64_peak(bloch_handle h, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ SIGNATURES = {
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_debug_apply_h1op": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
+    "bloch_debug_fp64_peak": (C.c_int, [_vp, _dp]),
 }
 
 _lib = None

@@ -79,6 +79,10 @@ struct bloch_handle_s {
   bloch_b200::DevBuf<int> d_cls;
   bloch_b200::DevBuf<double> d_eps, d_muinv, d_cpar;
   bloch_b200::DevBuf<int32_t> d_map_nd, d_map_h1, d_map_rt;
+  bloch_b200::DevBuf<int> d_tp_ptr;          // transpose of map_nd: dof -> its local copies
+  bloch_b200::DevBuf<int32_t> d_tp_loc;      // signed 1-based positions e*L_nd + j
+  bloch_b200::DevBuf<D2> d_evec;             // E-vector of the atomic-free apply
+  int two_pass = 0;            // 1: atomic-free E-vector + owner reduction (deterministic, ~15% slower)
   bloch_b200::DevBuf<double> d_diagA, d_diagM, d_diagS0;   // Jacobi diagonals (real)
   bloch_b200::DevBuf<double> d_jac, d_jac0;                // 1/(diagA + sigma diagM), 1/diagS0
   bloch_b200::ElemData E{};
@@ -102,7 +106,8 @@ struct bloch_handle_s {
   bloch_b200::DevBuf<D2> d_blk_a, d_blk_b, d_blk_c;
 
   void setup();                                 // Setup()
-  void apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm);   // y = ca A x + cm M x (zeroes y)
+  void apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm);   // y = ca A x + cm M x
+  void apply_nd_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm);
   void apply_h1(int mode, const D2 *x, D2 *y, int nvec);               // zeroes y for modes 0, 2
   void apply_curl(const D2 *x, D2 *y, int nvec);
   void project(D2 *x, int nvec, double rel_tol, int *iters);           // in place x <- P x

@@ -197,30 +197,80 @@ inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V) {
   return true;
 }
 
-// Generalised Hermitian problem GA c = lambda GM c (GM positive definite), lowest m pairs.
-// C is n x m (row-major).  Returns false if GM is numerically not PD or QL fails.
-inline bool hegv_lowest(int n, int m, const Mat &GA, const Mat &GM, std::vector<double> &lam, Mat &C) {
-  Mat L = GM;
-  // scale-aware: normalise by the diagonal first (D^-1/2 GM D^-1/2) for a meaningful pivot test
+// Generalised Hermitian problem GA c = lambda GM c (GM positive semi-definite Gram matrix),
+// lowest m pairs, C is n x m (row-major).
+//   fast path : diagonal scaling + Cholesky, accepted only if every pivot is > chol_tol (well
+//               conditioned basis, error amplification <= 1/sqrt(chol_tol));
+//   fallback  : (only if drop_tol > 0) spectral whitening GM = U S U^H, directions with
+//               S_i <= drop_tol * S_max are discarded.  The eigensolver does NOT use it: dropping
+//               the whole P block and restarting proved more robust on tiny meshes whose
+//               constrained space is almost exhausted by [X W P].
+// Returns false only if fewer than m independent directions remain or QL fails.
+inline bool hegv_lowest(int n, int m, const Mat &GA, const Mat &GM, std::vector<double> &lam, Mat &C,
+                        double chol_tol = 1e-9, double drop_tol = 0.0) {
   std::vector<double> sc(n);
   for (int i = 0; i < n; i++) {
     double dii = GM[i * n + i].real();
     if (!(dii > 0)) return false;
     sc[i] = 1.0 / std::sqrt(dii);
   }
-  Mat B = GA;
+  Mat L = GM, B = GA;
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) { L[i * n + j] *= sc[i] * sc[j]; B[i * n + j] *= sc[i] * sc[j]; }
-  if (!cholesky(n, L, 1e-13)) return false;
-  reduce_to_standard(n, L, B);
+  const Mat GMs = L, GAs = B;
   std::vector<double> w;
   Mat V;
-  if (!heev(n, B, w, V)) return false;
-  lam.assign(w.begin(), w.begin() + m);
-  C.assign((size_t)n * m, cplx(0));
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < m; j++) C[i * m + j] = V[i * n + j];
-  back_transform(n, m, L, C);
+  if (cholesky(n, L, chol_tol)) {
+    reduce_to_standard(n, L, B);
+    if (!heev(n, B, w, V)) return false;
+    lam.assign(w.begin(), w.begin() + m);
+    C.assign((size_t)n * m, cplx(0));
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < m; j++) C[i * m + j] = V[i * n + j];
+    back_transform(n, m, L, C);
+  } else if (drop_tol <= 0.0) {
+    return false;   // caller shrinks the basis (drops the P block) and retries
+  } else {
+    std::vector<double> sig;
+    Mat U;
+    if (!heev(n, GMs, sig, U)) return false;
+    const double smax = sig[n - 1];
+    int first = 0;
+    while (first < n && !(sig[first] > drop_tol * smax)) first++;
+    const int r = n - first;
+    if (r < m) return false;
+    Mat W((size_t)n * r);                       // whitening basis: columns U_i / sqrt(sig_i)
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < r; k++) W[(size_t)i * r + k] = U[(size_t)i * n + first + k] / std::sqrt(sig[first + k]);
+    Mat T((size_t)n * r, cplx(0)), R((size_t)r * r, cplx(0));
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const cplx a = GAs[(size_t)i * n + j];
+        for (int k = 0; k < r; k++) T[(size_t)i * r + k] += a * W[(size_t)j * r + k];
+      }
+    for (int i = 0; i < n; i++)
+      for (int a = 0; a < r; a++) {
+        const cplx wc = std::conj(W[(size_t)i * r + a]);
+        for (int k = 0; k < r; k++) R[(size_t)a * r + k] += wc * T[(size_t)i * r + k];
+      }
+    for (int a = 0; a < r; a++) {
+      R[(size_t)a * r + a] = R[(size_t)a * r + a].real();
+      for (int k = a + 1; k < r; k++) {
+        const cplx x = 0.5 * (R[(size_t)a * r + k] + std::conj(R[(size_t)k * r + a]));
+        R[(size_t)a * r + k] = x;
+        R[(size_t)k * r + a] = std::conj(x);
+      }
+    }
+    if (!heev(r, R, w, V)) return false;
+    lam.assign(w.begin(), w.begin() + m);
+    C.assign((size_t)n * m, cplx(0));
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < m; j++) {
+        cplx sum = 0;
+        for (int k = 0; k < r; k++) sum += W[(size_t)i * r + k] * V[(size_t)k * r + j];
+        C[(size_t)i * m + j] = sum;
+      }
+  }
   for (int i = 0; i < n; i++)
     for (int j = 0; j < m; j++) C[i * m + j] *= sc[i];
   return true;

@@ -14,6 +14,7 @@
 #include "kernels.hpp"
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "elem_device.cuh"
 
@@ -26,37 +27,13 @@ using namespace dev;
 // ------------------------------------------------------------------------------------------
 // y = ca * A x + cm * M x on ND block vectors
 // ------------------------------------------------------------------------------------------
+// compute phases of y_e = ca A_e x_e + cm M_e x_e for one tile of 32 items: on entry sND holds the
+// gathered nodal values (after a block barrier), on exit the nodal result (after a block barrier)
 template <int P, int NW>
-__global__ void __launch_bounds__(NW * 32)
-k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
-           double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca, double cm) {
+__device__ __forceinline__ void nd_compute_tile(double2 *sND, double2 *sRT, const Tabs &T, const double *cp,
+                                                double eps, double mui, double ca, double cm, int warp, int lane) {
   using D = Dim<P>;
   constexpr int Q = P + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2 *sND = reinterpret_cast<double2 *>(smem_raw);
-  double2 *sRT = sND + D::LND * 32;
-  double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
-  const long item = (long)blockIdx.x * 32 + lane;
-  const bool active = item < n_items;
-  const int e = active ? (int)(item / m) : 0;
-  const int v = active ? (int)(item - (long)e * m) : 0;
-  const int32_t *mp = E.map_nd + (long)e * D::LND;
-  // ---- gather (signed, periodic identification is in the map) ----
-  for (int j = warp; j < D::LND; j += NW) {
-    double2 val = make_double2(0.0, 0.0);
-    if (active) {
-      const int s = __ldg(mp + j);
-      const long g = (s < 0 ? -s : s) - 1;
-      val = ld2(X + g * ldx + v);
-      if (s < 0) { val.x = -val.x; val.y = -val.y; }
-    }
-    sND[j * 32 + lane] = val;
-  }
-  __syncthreads();
-  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
-  const double eps = active ? E.eps[e] : 0.0, mui = active ? E.muinv[e] : 0.0;
   // ---- nodal -> mode in the closed directions ----
   nd_transform_all<P, NW, 0>(sND, T, warp, lane);
   __syncthreads();
@@ -172,19 +149,133 @@ k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__re
       for (int b = 0; b < Q; b++) sND[(base + a * Q + b) * 32 + lane] = f[a][b];
   }
   __syncthreads();
-  // ---- signed scatter-add ----
-  if (active) {
-    double *Yd = reinterpret_cast<double *>(Y);
-    for (int j = warp; j < D::LND; j += NW) {
-      const int s = __ldg(mp + j);
-      const long g = (s < 0 ? -s : s) - 1;
-      double2 val = sND[j * 32 + lane];
-      if (s < 0) { val.x = -val.x; val.y = -val.y; }
-      double *dst = Yd + 2 * (g * ldy + v);
-      atomicAdd(dst, val.x);
-      atomicAdd(dst + 1, val.y);
+}
+
+// Persistent, software-pipelined version: each CTA loops over tiles; the gather of tile t+1 is
+// issued with cp.async (LDGSTS, 16 B per request) into the second ND buffer while tile t is being
+// computed, so the two dependent global round trips (index, value) of the signed gather are off
+// the critical path.  Signs are applied in place by the thread that issued the copy.
+template <int P, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
+           double2 *__restrict__ Y, double2 *__restrict__ Z, int m, int ldx, int ldy, long n_items, double ca,
+           double cm) {
+  using D = Dim<P>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sBuf0 = reinterpret_cast<double2 *>(smem_raw);
+  double2 *sBuf1 = sBuf0 + D::LND * 32;
+  double2 *sRT = sBuf1 + D::LND * 32;
+  double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  constexpr int KG = (D::LND + NW - 1) / NW;
+  const long ntiles = (n_items + 31) / 32;
+  const double2 zero2 = make_double2(0.0, 0.0);
+
+  auto load_idx = [&](long tile, int (&sidx)[KG], int &cls_, double &eps_, double &mui_) {
+    const long item = tile * 32 + lane;
+    const bool act = tile < ntiles && item < n_items;
+    const int e = act ? (int)(item / m) : 0;
+    cls_ = act ? __ldg(E.cls + e) : 0;
+    eps_ = act ? __ldg(E.eps + e) : 0.0;
+    mui_ = act ? __ldg(E.muinv + e) : 0.0;
+    const int32_t *mp = E.map_nd + (long)e * D::LND;
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      const int j = warp + k * NW;
+      sidx[k] = (act && j < D::LND) ? __ldg(mp + j) : 0;
     }
+  };
+  auto issue_gather = [&](long tile, const int (&sidx)[KG], double2 *buf) {
+    const long item = tile * 32 + lane;
+    const int e = (int)(item / m);
+    const int v = (int)(item - (long)e * m);
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      const int j = warp + k * NW;
+      if (j < D::LND) {
+        double2 *dst = buf + j * 32 + lane;
+        const int s = sidx[k];
+        if (s != 0) {
+          const long g = (s < 0 ? -s : s) - 1;
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(X + g * ldx + v));
+        } else {
+          *dst = zero2;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  int idx_cur[KG], idx_nxt[KG];
+  int cls_cur, cls_nxt;
+  double eps_cur, eps_nxt, mui_cur, mui_nxt;
+  long tile = blockIdx.x;
+  load_idx(tile, idx_cur, cls_cur, eps_cur, mui_cur);
+  if (tile < ntiles) issue_gather(tile, idx_cur, sBuf0);
+  load_idx(tile + gridDim.x, idx_nxt, cls_nxt, eps_nxt, mui_nxt);
+  int parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    double2 *sND = parity ? sBuf1 : sBuf0;
+    double2 *sOther = parity ? sBuf0 : sBuf1;
+    const long item = tile * 32 + lane;
+    const bool active = item < n_items;
+    const int e = active ? (int)(item / m) : 0;
+    const int v = active ? (int)(item - (long)e * m) : 0;
+    // wait for this tile's gather, apply the orientation signs to the entries this thread copied
+    asm volatile("cp.async.wait_group 0;\n" ::);
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      if (idx_cur[k] < 0) {
+        const int j = warp + k * NW;
+        double2 val = sND[j * 32 + lane];
+        val.x = -val.x; val.y = -val.y;
+        sND[j * 32 + lane] = val;
+      }
+    }
+    __syncthreads();     // also orders the previous tile's scatter reads of sOther before the refill
+    const long next = tile + gridDim.x;
+    if (next < ntiles) issue_gather(next, idx_nxt, sOther);
+    int idx_nn[KG], cls_nn;
+    double eps_nn, mui_nn;
+    load_idx(next + gridDim.x, idx_nn, cls_nn, eps_nn, mui_nn);
+    const double *cp = sCP + kClassParDoubles * cls_cur;
+    nd_compute_tile<P, NW>(sND, sRT, T, cp, eps_cur, mui_cur, ca, cm, warp, lane);
+    if (Z != nullptr) {
+      // ---- element-local result to the E-vector (coalesced plain stores; summed by k_nd_reduce) ----
+      if (active) {
+        double2 *zp = Z + ((long)e * D::LND) * m + v;
+#pragma unroll
+        for (int k = 0; k < KG; k++) {
+          const int j = warp + k * NW;
+          if (j < D::LND) zp[(long)j * m] = sND[j * 32 + lane];
+        }
+      }
+    } else {
+      // ---- signed scatter-add (indices kept in registers since the gather) ----
+      double *Yd = reinterpret_cast<double *>(Y);
+#pragma unroll
+      for (int k = 0; k < KG; k++) {
+        const int s = idx_cur[k];
+        if (s != 0) {
+          const int j = warp + k * NW;
+          const long g = (s < 0 ? -s : s) - 1;
+          double2 val = sND[j * 32 + lane];
+          if (s < 0) { val.x = -val.x; val.y = -val.y; }
+          double *dst = Yd + 2 * (g * ldy + v);
+          atomicAdd(dst, val.x);
+          atomicAdd(dst + 1, val.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KG; k++) { idx_cur[k] = idx_nxt[k]; idx_nxt[k] = idx_nn[k]; }
+    cls_cur = cls_nxt; eps_cur = eps_nxt; mui_cur = mui_nxt;
+    cls_nxt = cls_nn; eps_nxt = eps_nn; mui_nxt = mui_nn;
+    parity ^= 1;
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -412,19 +503,26 @@ k_curl(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restri
 
 template <int P, int NW>
 cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
-                       int nvec, double ca, double cm, cudaStream_t s) {
+                       int nvec, double ca, double cm, double2 *z, cudaStream_t s) {
   using D = Dim<P>;
-  const size_t smem = (size_t)(D::LND + D::LRT) * 32 * sizeof(double2) +
+  const size_t smem = (size_t)(2 * D::LND + D::LRT) * 32 * sizeof(double2) +
                       (size_t)E.n_class * kClassParDoubles * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
     cudaError_t err = cudaFuncSetAttribute(k_nd_apply<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;
-    attr_set = true;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nd_apply<P, NW>, NW * 32, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    max_ctas = sms * per_sm;     // persistent: one wave of co-resident CTAs looping over the tiles
   }
   const long n_items = (long)E.n_elem * nvec;
-  const long grid = (n_items + 31) / 32;
-  k_nd_apply<P, NW><<<(unsigned)grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca, cm);
+  const long ntiles = (n_items + 31) / 32;
+  const unsigned grid = (unsigned)(ntiles < max_ctas ? ntiles : max_ctas);
+  k_nd_apply<P, NW><<<grid, NW * 32, smem, s>>>(T, E, x, y, z, nvec, ldx, ldy, n_items, ca, cm);
   return cudaGetLastError();
 }
 
@@ -473,11 +571,33 @@ cudaError_t curl_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, 
 }  // namespace
 
 cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
-                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s) {
+                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s,
+                            double2 *z) {
+  static int variant = -1;
+  if (variant < 0) { const char *e = std::getenv("BLOCH_ND_WARPS"); variant = e ? std::atoi(e) : 0; }
+  if (variant == 1) {
+    switch (p) {
+      case 1: return nd_apply_t<1, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 2: return nd_apply_t<2, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 3: return nd_apply_t<3, 4>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+    }
+  } else if (variant == 2) {
+    switch (p) {
+      case 1: return nd_apply_t<1, 2>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 2: return nd_apply_t<2, 2>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 3: return nd_apply_t<3, 6>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+    }
+  } else if (variant == 3) {
+    switch (p) {
+      case 1: return nd_apply_t<1, 3>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 2: return nd_apply_t<2, 3>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+      case 3: return nd_apply_t<3, 8>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+    }
+  }
   switch (p) {
-    case 1: return nd_apply_t<1, 6>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
-    case 2: return nd_apply_t<2, 9>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
-    case 3: return nd_apply_t<3, 12>(T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 1: return nd_apply_t<1, 6>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+    case 2: return nd_apply_t<2, 9>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
+    case 3: return nd_apply_t<3, 12>(T, E, x, ldx, y, ldy, nvec, ca, cm, z, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -778,6 +898,73 @@ cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const
 cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s) {
   k_fill_random<<<grid_for(total, 256), 256, 0, s>>>(X, total, seed);
   return cudaGetLastError();
+}
+
+// ---- second pass of the atomic-free apply: y[g][v] = sum over the local copies of dof g ----
+namespace {
+__global__ void k_nd_reduce(const int *__restrict__ ptr, const int32_t *__restrict__ loc,
+                            const double2 *__restrict__ Z, double2 *__restrict__ Y, long n, int m, int ldy) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long g = t / m;
+    const int v = (int)(t - g * m);
+    const int b = __ldg(ptr + g), e = __ldg(ptr + g + 1);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int k = b; k < e; k++) {
+      const int s = __ldg(loc + k);
+      const double2 z = Z[(long)((s < 0 ? -s : s) - 1) * m + v];
+      if (s < 0) { acc.x -= z.x; acc.y -= z.y; } else { acc.x += z.x; acc.y += z.y; }
+    }
+    Y[g * ldy + v] = acc;
+  }
+}
+}  // namespace
+
+cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *z, double2 *y, long n,
+                             int m, int ldy, cudaStream_t s) {
+  const long total = n * m;
+  long g = (total + 255) / 256;
+  if (g > 148L * 32) g = 148L * 32;
+  k_nd_reduce<<<(unsigned)(g < 1 ? 1 : g), 256, 0, s>>>(ptr, loc, z, y, n, m, ldy);
+  return cudaGetLastError();
+}
+
+// ---- fp64 FMA throughput probe (roofline denominator for the flop-bound side) ----
+namespace {
+__global__ void k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace
+
+cudaError_t measure_fp64_peak(double *tflops, cudaStream_t s) {
+  const int blocks = 148 * 8, threads = 256, iters = 20000;
+  double *d = nullptr;
+  cudaError_t err = cudaMalloc(&d, sizeof(double) * blocks * threads);
+  if (err != cudaSuccess) return err;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_fp64_peak<<<blocks, threads, 0, s>>>(d, 1000);
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    cudaEventRecord(e0, s);
+    k_fp64_peak<<<blocks, threads, 0, s>>>(d, iters);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  err = cudaGetLastError();
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return err;
 }
 
 }  // namespace bloch_b200

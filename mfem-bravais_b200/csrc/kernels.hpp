@@ -34,9 +34,16 @@ struct ElemData {            // device pointers, element order = mesh order
 };
 
 // y = ca * A x + cm * M x   (ND -> ND), A = (C - i Z_kappa)^H M2(muinv) (C - i Z_kappa), M = M1(eps)
-// y must be zero-initialised by the caller unless accumulate semantics are wanted.
+// z == nullptr: signed scatter-ADD into y with fp64 atomics (y must be zero-initialised).
+// z != nullptr: atomic-free first pass - the element-local results go to the E-vector
+//               z[(e*L_nd + j)*nvec + v] with plain coalesced stores and y is not touched;
+//               launch_nd_reduce then sums the copies of every dof (deterministic).
 cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
-                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s);
+                            double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s,
+                            double2 *z = nullptr);
+// y[g][v] = sum_{k in [ptr[g], ptr[g+1])} sign(loc[k]) * z[(|loc[k]|-1)*m + v]
+cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *z, double2 *y, long n,
+                             int m, int ldy, cudaStream_t s);
 // H1 <-> ND operators of the projector.  mode 0: y_h1 += S0 x_h1 (S0 = G^H M1 G);
 // mode 1: y_nd = G x_h1 (interpolation, plain stores); mode 2: y_h1 += G^H M1 x_nd
 cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
@@ -86,5 +93,8 @@ cudaError_t launch_proj_cg(int p, const Tabs &T, const ElemData &E, const double
                            long n0, int max_it, double rel_tol, int *info, cudaStream_t s);
 // fill with deterministic pseudo-random complex numbers in (-1,1)
 cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s);
+
+// measured fp64 FMA throughput of the current device (TFLOP/s, best of 5)
+cudaError_t measure_fp64_peak(double *tflops, cudaStream_t s);
 
 }  // namespace bloch_b200

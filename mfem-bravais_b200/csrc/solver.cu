@@ -137,114 +137,33 @@ __global__ void k_make_jacobi(const double *dA, const double *dM, double sigma, 
   }
 }
 
-// PCG on S0 (columns independent).  scal layout (device doubles, m each):
-//   [0] rz  [1] pq  [2] rz_new  [3] rr
-// step1: alpha = rz/pq ; phi += alpha p ; r -= alpha q ; z = jac .* r ; rz_new += <r,z> ; rr += <r,r>
-__global__ void k_cg_step1(const double *__restrict__ jac, const D2 *__restrict__ p, const D2 *__restrict__ q,
-                           D2 *__restrict__ phi, D2 *__restrict__ r, D2 *__restrict__ z,
-                           double *__restrict__ scal, long n, int m) {
-  extern __shared__ double sred[];   // [2][m]
+// column sums of a contiguous n x m block: sums[j] += sum_r X[r][j]  (complex)
+__global__ void k_col_sum(const D2 *__restrict__ X, long n, int m, double *__restrict__ sums) {
+  extern __shared__ double sred[];   // [2m]
   for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) sred[j] = 0.0;
   __syncthreads();
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long usable = (nthreads / m) * m;
   const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (start < usable) {
-    const int j = (int)(start % m);
-    const double pq = scal[m + j];
-    const double alpha = pq != 0.0 ? scal[j] / pq : 0.0;
-    double a_rz = 0.0, a_rr = 0.0;
-    for (long t = start; t < n * m; t += usable) {
-      const D2 pp = p[t], qq = q[t];
-      D2 f = phi[t], rr = r[t];
-      f.x = fma(alpha, pp.x, f.x); f.y = fma(alpha, pp.y, f.y);
-      rr.x = fma(-alpha, qq.x, rr.x); rr.y = fma(-alpha, qq.y, rr.y);
-      phi[t] = f;
-      r[t] = rr;
-      const double s = jac[t / m];
-      const D2 zz = make_double2(s * rr.x, s * rr.y);
-      z[t] = zz;
-      a_rz = fma(rr.x, zz.x, a_rz); a_rz = fma(rr.y, zz.y, a_rz);
-      a_rr = fma(rr.x, rr.x, a_rr); a_rr = fma(rr.y, rr.y, a_rr);
-    }
-    atomicAdd(&sred[j], a_rz);
-    atomicAdd(&sred[m + j], a_rr);
+    double ax = 0.0, ay = 0.0;
+    for (long t = start; t < n * m; t += usable) { const D2 v = X[t]; ax += v.x; ay += v.y; }
+    atomicAdd(&sred[2 * (start % m)], ax);
+    atomicAdd(&sred[2 * (start % m) + 1], ay);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    atomicAdd(scal + 2 * m + j, sred[j]);
-    atomicAdd(scal + 3 * m + j, sred[m + j]);
-  }
+  for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) atomicAdd(sums + j, sred[j]);
 }
-// step2: beta = rz_new / rz ; p = z + beta p
-__global__ void k_cg_step2(const D2 *__restrict__ z, D2 *__restrict__ p, const double *__restrict__ scal,
-                           long n, int m) {
+// X[r][j] -= sums[j] / n
+__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums) {
   const long total = n * m;
+  const double inv = 1.0 / (double)n;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const int j = (int)(t % m);
-    const double rz = scal[j];
-    const double beta = rz != 0.0 ? scal[2 * m + j] / rz : 0.0;
-    const D2 zz = z[t], pp = p[t];
-    p[t] = make_double2(fma(beta, pp.x, zz.x), fma(beta, pp.y, zz.y));
+    D2 v = X[t];
+    v.x -= sums[2 * j] * inv; v.y -= sums[2 * j + 1] * inv;
+    X[t] = v;
   }
-}
-// rz <- rz_new ; pq, rz_new, rr <- 0
-__global__ void k_cg_roll(double *scal, int m) {
-  const int j = threadIdx.x;
-  if (j < m) {
-    scal[j] = scal[2 * m + j];
-    scal[m + j] = 0.0; scal[2 * m + j] = 0.0; scal[3 * m + j] = 0.0;
-  }
-}
-// z = jac .* r ; p = z ; rz += <r,z> ; rr += <r,r>
-__global__ void k_cg_init(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ z,
-                          D2 *__restrict__ p, double *__restrict__ scal, long n, int m) {
-  extern __shared__ double sred[];
-  for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) sred[j] = 0.0;
-  __syncthreads();
-  const long nthreads = (long)gridDim.x * blockDim.x;
-  const long usable = (nthreads / m) * m;
-  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (start < usable) {
-    const int j = (int)(start % m);
-    double a_rz = 0.0, a_rr = 0.0;
-    for (long t = start; t < n * m; t += usable) {
-      const D2 rr = r[t];
-      const double s = jac[t / m];
-      const D2 zz = make_double2(s * rr.x, s * rr.y);
-      z[t] = zz;
-      p[t] = zz;
-      a_rz = fma(rr.x, zz.x, a_rz); a_rz = fma(rr.y, zz.y, a_rz);
-      a_rr = fma(rr.x, rr.x, a_rr); a_rr = fma(rr.y, rr.y, a_rr);
-    }
-    atomicAdd(&sred[j], a_rz);
-    atomicAdd(&sred[m + j], a_rr);
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    atomicAdd(scal + j, sred[j]);
-    atomicAdd(scal + 3 * m + j, sred[m + j]);
-  }
-}
-// pq[j] += Re <p_j, q_j>
-__global__ void k_cg_pq(const D2 *__restrict__ p, const D2 *__restrict__ q, double *__restrict__ scal,
-                        long n, int m) {
-  extern __shared__ double sred[];
-  for (int j = threadIdx.x; j < m; j += blockDim.x) sred[j] = 0.0;
-  __syncthreads();
-  const long nthreads = (long)gridDim.x * blockDim.x;
-  const long usable = (nthreads / m) * m;
-  const long start = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (start < usable) {
-    double acc = 0.0;
-    for (long t = start; t < n * m; t += usable) {
-      const D2 a = p[t], b = q[t];
-      acc = fma(a.x, b.x, acc); acc = fma(a.y, b.y, acc);
-    }
-    atomicAdd(&sred[start % m], acc);
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(scal + m + j, sred[j]);
 }
 // X[:, :m] (pitch ld) -= G (contiguous n x m)
 __global__ void k_sub_strided(D2 *__restrict__ X, int ld, const D2 *__restrict__ G, long n, int m) {
@@ -295,6 +214,15 @@ static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_t
   BLOCH_CUDA(launch_h1_op(h->p, 2, h->tabs, h->E, x, ldx, w.rhs.p, m, m, s));
   BLOCH_CUDA(cudaMemsetAsync(w.phi.p, 0, sizeof(D2) * N0 * m, s));
   BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * (8 * m + 2), s));
+  if (h->beta == 0.0) {
+    // Gamma point: S0 = G^T M G is singular (constants).  The exact right-hand side is orthogonal
+    // to the constants; rounding is not, and CG amplifies that component without bound - remove it.
+    const unsigned g1 = std::min<unsigned>(grid_for(N0 * m), 148);
+    k_col_sum<<<g1, TPB, sizeof(double) * 2 * m, s>>>(w.rhs.p, N0, m, w.scal.p);
+    k_col_shift<<<grid_for(N0 * m), TPB, 0, s>>>(w.rhs.p, N0, m, w.scal.p);
+    BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * (8 * m + 2), s));
+    h->count_launch(2);
+  }
   if (dbg) { int magic = 12345; BLOCH_CUDA(cudaMemcpyAsync(d_info + 2, &magic, sizeof(int), cudaMemcpyHostToDevice, s)); }
   // the whole block PCG in one cooperative launch
   BLOCH_CUDA(launch_proj_cg(h->p, h->tabs, h->E, h->d_jac0.p, w.phi.p, w.rhs.p, w.z.p, w.p.p, w.q.p,
@@ -350,6 +278,7 @@ void bloch_handle_s::solve() {
   const double cheb_ratio = env_double("BLOCH_CHEB_RATIO", 300.0);
   const double proj_tol = std::min(env_double("BLOCH_PROJ_TOL", 1e-9), 1e-3 * tol);
   const bool warm = env_double("BLOCH_WARM_START", 1.0) != 0.0;
+  const int refresh_every = (int)env_double("BLOCH_REFRESH_EVERY", 1.0);
   const double proj_adapt = env_double("BLOCH_PROJ_ADAPT", 0.0);
   const bool verbose = env_double("BLOCH_VERBOSE", 0.0) != 0.0;
   d_jac.alloc(Nl);
@@ -368,10 +297,7 @@ void bloch_handle_s::solve() {
   dlam.alloc(mb); drn.alloc(mb);
 
   auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
-    BLOCH_CUDA(cudaMemset2DAsync(y, sizeof(D2) * ldy, 0, sizeof(D2) * nvec, Nl, s));
-    BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, s));
-    count_launch();
-    if (ca != 0.0) stats.applies_A += nvec;
+    apply_nd_ld(x, ldx, y, ldy, nvec, ca, cm);
   };
 
   // lambda_max(D^-1 (A + sigma M)) <= max over element classes of the local scaled spectra
@@ -403,6 +329,8 @@ void bloch_handle_s::solve() {
   // Rayleigh-Ritz on the first k basis columns; returns false if the Gram matrix is not PD
   std::vector<D2> hGA((size_t)ld * ld), hGM((size_t)ld * ld);
   std::vector<double> lam(mb, 0.0), rn(mb, 0.0);
+  std::vector<char> active(mb, 1);
+  bool need_refresh = false;
   auto rayleigh_ritz = [&](int k) -> bool {
     BLOCH_CUDA(launch_gram(S.p, k, ld, AS.p, k, ld, Nl, dGA.p, s));
     BLOCH_CUDA(launch_gram(S.p, k, ld, MS.p, k, ld, Nl, dGM.p, s));
@@ -410,16 +338,49 @@ void bloch_handle_s::solve() {
     BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaStreamSynchronize(s));
-    Mat GA((size_t)k * k), GM((size_t)k * k), C;
-    for (int i = 0; i < k; i++)
-      for (int j = 0; j < k; j++) {
-        // Hermitian part (the two triangles are computed independently on the device)
-        const D2 a = hGA[i * k + j], at = hGA[j * k + i], b = hGM[i * k + j], bt = hGM[j * k + i];
-        GA[i * k + j] = 0.5 * cplx(a.x + at.x, a.y - at.y);
-        GM[i * k + j] = 0.5 * cplx(b.x + bt.x, b.y - bt.y);
-      }
+    // basis columns that take part: all of X; W_j / P_j only for unconverged j (soft locking) and
+    // only if they are not numerically zero (X is M-orthonormal, so diag(GM) of X is ~1)
+    std::vector<int> keep;
+    for (int i = 0; i < k; i++) {
+      const int j = i % mb;
+      const bool is_x = i < mb;
+      const double dii = hGM[i * k + i].x;
+      if (is_x || (active[j] && dii > 1e-26)) keep.push_back(i);
+    }
+    int kk = (int)keep.size();
+    bool dropped = false;
     std::vector<double> l;
-    if (!dense::hegv_lowest(k, mb, GA, GM, l, C)) return false;
+    Mat C;
+    bool ok = false;
+    while (!ok) {
+      Mat GA((size_t)kk * kk), GM((size_t)kk * kk), Cs;
+      for (int a = 0; a < kk; a++)
+        for (int b = 0; b < kk; b++) {
+          // Hermitian part (the two triangles are computed independently on the device)
+          const int i = keep[a], j = keep[b];
+          const D2 x = hGA[i * k + j], xt = hGA[j * k + i], y = hGM[i * k + j], yt = hGM[j * k + i];
+          GA[a * kk + b] = 0.5 * cplx(x.x + xt.x, x.y - xt.y);
+          GM[a * kk + b] = 0.5 * cplx(y.x + yt.x, y.y - yt.y);
+        }
+      ok = dense::hegv_lowest(kk, mb, GA, GM, l, Cs);
+      if (ok) {
+        C.assign((size_t)k * mb, cplx(0));
+        for (int a = 0; a < kk; a++)
+          for (int j = 0; j < mb; j++) C[(size_t)keep[a] * mb + j] = Cs[(size_t)a * mb + j];
+      } else {
+        // drop the P block first, then halve what is left of the W block, then give up
+        if (kk > mb && keep.back() >= 2 * mb) {
+          while (!keep.empty() && keep.back() >= 2 * mb) keep.pop_back();
+        } else if (kk > mb) {
+          const int nw = kk - mb;
+          for (int d = 0; d < (nw + 1) / 2; d++) keep.pop_back();
+        } else {
+          return false;
+        }
+        kk = (int)keep.size();
+        dropped = true;
+      }
+    }
     std::vector<D2> hC((size_t)k * mb);
     for (size_t i = 0; i < hC.size(); i++) hC[i] = make_double2(C[i].real(), C[i].imag());
     lam = l;
@@ -429,6 +390,7 @@ void bloch_handle_s::solve() {
     k_rr_update<<<g, 256, sizeof(D2) * k * mb, s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
     count_launch();
     BLOCH_CUDA(cudaStreamSynchronize(s));   // hC / lam are stack-lifetime host buffers
+    if (dropped) need_refresh = true;
     return true;
   };
 
@@ -479,6 +441,7 @@ void bloch_handle_s::solve() {
     BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * mb, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaStreamSynchronize(s));
     t_res += since(t0);
+    for (int j = 0; j < mb; j++) active[j] = std::sqrt(rn[j]) > 0.1 * tol;
     nconv = 0;
     maxres = 0;
     for (int j = 0; j < nb; j++) {
@@ -517,6 +480,14 @@ void bloch_handle_s::solve() {
     if (!ok && have_P) ok = rayleigh_ritz(2 * mb);   // restart without P
     if (!ok) throw std::runtime_error("Rayleigh-Ritz failed (basis numerically rank deficient)");
     have_P = true;
+    if (need_refresh || refresh_every <= 1 || (it % refresh_every) == refresh_every - 1) {
+      // recompute A X and M X from X instead of carrying them by recurrence; after a degenerate
+      // Rayleigh-Ritz the search direction block is discarded as well
+      op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);
+      op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
+      if (need_refresh) have_P = false;
+      need_refresh = false;
+    }
     t_rr += since(t0);
   }
   if (verbose)

@@ -44,3 +44,35 @@ def dispersion_sweep(eq, kappas, n_bands, tol=1e-6, max_iter=2000):
         out.append(eq.band_eigenvalues())
         stats.append(eq.GetSolverStats())
     return np.array(out), stats
+
+
+def shard_kpoints(n_points, world_size, rank):
+    """Contiguous chunk [lo, hi) of the k-point list owned by `rank`:
+    contiguity keeps consecutive k-points on one GPU so eigenvectors can warm-start the next
+    solve.  The first n_points % world_size ranks get one extra point."""
+    base, extra = divmod(n_points, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sharded_sweep(solve_fn, kappas, n_bands, dist=None):
+    """Solves every k-point exactly once across the ranks of `dist` (a torch.distributed-like
+    module, None = single process): rank r solves its contiguous chunk with `solve_fn(kappa) ->
+    array of n_bands eigenvalues`; the per-rank blocks are gathered (no collective on the solve
+    path, one all_gather of n_bands doubles per k-point at the end) and returned in path order on
+    every rank as an array [len(kappas), n_bands]."""
+    import numpy as _np
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    lo, hi = shard_kpoints(len(kappas), world, rank)
+    mine = _np.zeros((hi - lo, n_bands))
+    for i in range(lo, hi):
+        mine[i - lo] = _np.asarray(solve_fn(kappas[i]))[:n_bands]
+    if dist is None:
+        return mine
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, mine))
+    out = _np.zeros((len(kappas), n_bands))
+    for plo, block in parts:
+        out[plo:plo + len(block)] = block
+    return out

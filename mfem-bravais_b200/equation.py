@@ -262,6 +262,11 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_debug_apply_h1op(self._h, mode, dptr(x2), dptr(y), x2.shape[0]))
         return y[0] if x.ndim == 1 else y
 
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        check(self._L.bloch_debug_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     # device-pointer entry points (integers = CUDA device addresses, e.g. torch tensor.data_ptr())
     def set_stream(self, stream_ptr):
         check(self._L.bloch_set_stream(self._h, C.c_void_p(stream_ptr)))

@@ -99,3 +99,19 @@ def test_eigenvectors_satisfy_pencil(bloch):
         ce = eq.MultC(x)
         assert np.allclose(bi, ce[: eq.N_rt] / np.sqrt(lam[i]), atol=1e-10)
         assert np.allclose(br, -ce[eq.N_rt:] / np.sqrt(lam[i]), atol=1e-10)
+
+
+def test_golden_fixtures(bloch):
+    """committed oracle fixtures (tests/golden/make_golden.py): no oracle code runs here"""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bands_small.json")))
+    for c in cases:
+        L = bloch.BravaisLattice(c["lattice"])
+        eq = bloch.MaxwellBlochWaveEquation(L, c["n_sub"], c["order"])
+        assert eq.N == c["n_nd"]
+        eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()) if c["sphere"] else np.ones(eq.n_elem))
+        nb = len(c["eigenvalues"])
+        eq.SetAbsoluteTolerance(1e-9)
+        lam = eq.GetEigenvalues(2 * nb, np.array(c["kappa"]))[0::2]
+        assert np.allclose(lam, c["eigenvalues"], rtol=1e-7, atol=1e-8), (c["lattice"], c["order"], lam, c["eigenvalues"])

@@ -1,0 +1,137 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol of
+include/bloch_b200.h, the lattice / k-path API matches the reference tables, the element -> dof
+maps agree with the oracle's independent geometric identification, and compute entry points
+fail loudly without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.bloch_oracle import Lattice, Mesh, Spaces
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(bloch):
+    hdr = open(os.path.join(ROOT, "include", "bloch_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(bloch_[a-z0-9_A-Z]+)\s*\(", hdr))
+    assert len(names) > 40
+    lib = C.CDLL(bloch.lib_path)
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+    from mfem_bravais_b200 import capi
+    assert names == set(capi.SIGNATURES), names ^ set(capi.SIGNATURES)
+    assert bloch.lib().bloch_version() >= 100
+
+
+@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
+def test_lattice_api_matches_reference_tables(bloch, name):
+    L = bloch.BravaisLattice(name)
+    o = Lattice(name)
+    assert L.GetLatticeTypeLabel() == name
+    assert np.allclose(L.GetLatticeVectors(), o.lat) and np.allclose(L.GetReciprocalLatticeVectors(), o.rec)
+    assert abs(L.GetUnitCellVolume() - o.volume) < 1e-14
+    assert L.GetNumberSymmetryPoints() == len(o.sp)
+    for i in range(L.GetNumberSymmetryPoints()):
+        lab = L.GetSymmetryPointLabel(i)
+        assert np.allclose(L.GetSymmetryPoint(i), o.kappa(lab))   # 2 pi * sp (lib/bravais.cpp:201-206)
+        assert L.GetSymmetryPointIndex(lab) == i
+    assert L.GetSymmetryPointIndex("nope") == -1
+    assert L.GetNumberPaths() == len(o.paths)
+    for p, path in enumerate(o.paths):
+        assert L.GetNumberPathSegments(p) == len(path) - 1
+        for s in range(len(path) - 1):
+            e0, e1 = L.GetPathSegmentEndPointIndices(p, s)
+            assert L.GetSymmetryPointLabel(e0) == path[s] and L.GetSymmetryPointLabel(e1) == path[s + 1]
+            mid = 0.5 * (o.kappa(path[s]) + o.kappa(path[s + 1]))
+            assert np.allclose(L.GetIntermediatePoint(p, s), mid)  # lib/bravais.cpp:59-74
+    # translation vectors are lattice vectors: integer in reciprocal coordinates
+    t = L.GetTranslationVectors() @ o.rec.T
+    assert np.allclose(t, np.round(t)) and len(L.GetFaceRadii()) == len(t)
+
+
+def test_reference_labels_and_paths(bloch):
+    L = bloch.BravaisLattice("FCC")       # lib/bravais.cpp:2420-2460
+    assert [L.GetSymmetryPointLabel(i) for i in range(6)] == ["Gamma", "X", "W", "K", "L", "U"]
+    assert L.GetIntermediatePointLabel(0, 0) == "Delta" and L.GetIntermediatePointLabel(1, 0) == "T"
+    assert np.allclose(L.GetSymmetryPoint(1), 2 * np.pi * np.array([0.0, 1.0, 0.0]))
+    B = bloch.BravaisLattice("BCC")       # lib/bravais.cpp:2708-2736
+    assert [B.GetSymmetryPointLabel(i) for i in range(4)] == ["Gamma", "H", "N", "P"]
+    ks = bloch.k_path(L, ["Gamma", "X", "W", "L", "Gamma"], 8)
+    assert ks.shape == (32, 3) and np.allclose(ks[7], L.GetSymmetryPoint(1)) and np.allclose(ks[-1], 0)
+    mapped, ipt = L.MapToPrimitiveCell([0.45, 0.45, 0.05])
+    assert np.linalg.norm(ipt) <= np.linalg.norm([0.45, 0.45, 0.05]) + 1e-14
+
+
+def _equivalent(ga, sa, gb, sb):
+    n = int(ga.max()) + 1
+    if int(gb.max()) + 1 != n:
+        return False
+    f = np.full(n, -1)
+    sg = np.zeros(n)
+    for x, y, z in zip(ga.ravel(), gb.ravel(), (sa * sb).ravel()):
+        if f[x] < 0:
+            f[x], sg[x] = y, z
+        elif f[x] != y or sg[x] != z:
+            return False
+    return len(np.unique(f)) == n
+
+
+@pytest.mark.parametrize("name,n,p", [("CUB", 1, 1), ("CUB", 2, 2), ("CUB", 3, 3), ("FCC", 1, 2), ("FCC", 2, 3),
+                                      ("FCC", 3, 1), ("BCC", 1, 3), ("BCC", 2, 2), ("BCC", 3, 1)])
+def test_dofmaps_agree_with_geometric_identification(bloch, name, n, p):
+    """entity-based numbering (product) vs node-position hashing (oracle): same identification
+    up to renumbering and a per-dof orientation sign, including the degenerate n = 1 meshes"""
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, p, device=-2)        # topology-only handle
+    mesh = Mesh(Lattice(name), n)
+    sp = Spaces(mesh, p)
+    x0, cls, J = eq.element_geometry()
+    assert np.allclose(x0, mesh.x0) and np.allclose(J, mesh.J) and (cls == mesh.cls).all()
+    assert np.allclose(eq.element_centers(), mesh.centers)
+    v, e, f, vol = eq.mesh_counts()
+    assert v - e + f - eq.n_elem == 0 and abs(vol - mesh.volume) < 1e-13
+    assert (eq.N, eq.N_rt, eq.N_h1) == (sp.n_nd, sp.n_rt, sp.n_h1)
+    for space, og, osg in [("h1", sp.h1_gid, sp.h1_sign), ("nd", sp.nd_gid, sp.nd_sign), ("rt", sp.rt_gid, sp.rt_sign)]:
+        g, s = eq.dofmap(space)
+        assert _equivalent(g, np.abs(s) if space == "h1" else s, og, osg), space
+
+
+def test_no_cpu_fallback(bloch):
+    L = bloch.BravaisLattice("CUB")
+    eq = bloch.MaxwellBlochWaveEquation(L, 2, 1, device=-2)
+    x = np.zeros(2 * eq.N)
+    for fn in (eq.MultA, eq.MultM, eq.MultProjector):
+        with pytest.raises(bloch.BlochError):
+            fn(x)
+    with pytest.raises(bloch.BlochError):
+        eq.Solve()
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(bloch.BlochError):
+            bloch.MaxwellBlochWaveEquation(L, 2, 1)                 # real handle needs a GPU
+
+
+def test_argument_errors(bloch):
+    L = bloch.BravaisLattice("FCC")
+    with pytest.raises(bloch.BlochError):
+        bloch.MaxwellBlochWaveEquation(L, 2, 7, device=-2)         # unsupported order
+    with pytest.raises(bloch.BlochError):
+        bloch.MaxwellBlochWaveEquation(L, 0, 1, device=-2)
+    with pytest.raises(bloch.BlochError):
+        bloch.BravaisLattice(3)                                     # 2-D lattice not on this path
+    eq = bloch.MaxwellBlochWaveEquation(L, 1, 1, device=-2)
+    with pytest.raises(bloch.BlochError):
+        eq.SetMassCoef(np.zeros(eq.n_elem))                         # eps must be positive
+    with pytest.raises(bloch.BlochError):
+        eq.SetNumEigs(1000)
+
+
+def test_sphere_coefficient_and_omega_format(bloch):
+    from mfem_bravais_b200.dispersion import omega_of_lambda
+    c = np.array([[0.1, 0.1, 0.1], [0.2, 0.2, 0.0], [0.25, 0.0, 0.0], [0.3, 0.0, 0.0]])
+    assert bloch.sphere_eps(c).tolist() == [10.0, 1.0, 10.0, 1.0]   # maxwell_dispersion.cpp:1464-1467
+    assert omega_of_lambda([4.0, 0.0, -1e-9, -1.0]).tolist() == [2.0, 0.0, 0.0, -1.0]  # :1072-1083
