@@ -38,6 +38,7 @@ typedef struct bloch_handle_s *bloch_handle;
 #define BLOCH_LATTICE_CUB 7
 #define BLOCH_LATTICE_FCC 8
 #define BLOCH_LATTICE_BCC 9
+#define BLOCH_LATTICE_HEX 16   /* PRIMITIVE_HEXAGONAL_PRISM, parameters a and c */
 
 const char *bloch_last_error(void);
 int bloch_version(void);
@@ -145,6 +146,18 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 /* layout conversion helpers between the boundary layout and the block layout (device ptrs) */
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
+
+/* ---- scalar variant: ScalarFloquetWaveEquation of misc/scalar3d.cpp:662-818 ----
+ * (G - i Z_kappa)^T M1(k) (G - i Z_kappa) u = lambda M0(m) u on H1_p (orders 1..4), same handle, same mesh.
+ * kappa is set with bloch_set_kappa; the reference's phase shift beta is in DEGREES:
+ * kappa = (beta * pi / 180) * zeta (scalar3d.cpp:733,784-785).  Coefficients: one value per element
+ * (stiffness_coef / mass_coef, scalar3d.cpp:564-588).  No null space, hence no projector. */
+int bloch_scalar_set_coefs(bloch_handle h, const double *stiffness_k, const double *mass_m);
+int bloch_scalar_set_num_modes(bloch_handle h, int n_complex_modes);      /* lobpcg nev (default 5, :427) */
+int bloch_scalar_solve(bloch_handle h);
+int bloch_scalar_get_eigenvalues(bloch_handle h, double *lambda, int n);
+/* which = 0: y = A u (block [[S0, b DKZ],[-b DKZ, S0]]), 1: y = M u (diag(M0, M0)); vectors [re;im] of length 2 N_h1 */
+int bloch_scalar_apply(bloch_handle h, int which, const double *x, double *y, int nvec);
 
 /* Test hook for the H1 <-> ND operators inside the projector (MaxwellBlochWaveProjector::Setup,
  * maxwell_bloch.cpp:2053-2158), host vectors [re;im]:

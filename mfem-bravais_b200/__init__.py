@@ -6,5 +6,5 @@ There is no CPU fallback: creating an equation without the built library or with
 device raises.
 """
 from .capi import lib, lib_path, BlochError, LATTICE_TYPES  # noqa: F401
-from .equation import BravaisLattice, MaxwellBlochWaveEquation  # noqa: F401
+from .equation import BravaisLattice, MaxwellBlochWaveEquation, ScalarFloquetWaveEquation  # noqa: F401
 from .dispersion import k_path, sphere_eps, dispersion_sweep, shard_kpoints, sharded_sweep  # noqa: F401

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(_HERE, "lib", "libbloch_b200.so")
 
-LATTICE_TYPES = {"CUB": 7, "FCC": 8, "BCC": 9}
+LATTICE_TYPES = {"CUB": 7, "FCC": 8, "BCC": 9, "HEX": 16}
 
 
 class BlochError(RuntimeError):
@@ -76,6 +76,11 @@ SIGNATURES = {
     "bloch_apply_M_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "bloch_scalar_set_coefs": (C.c_int, [_vp, _dp, _dp]),
+    "bloch_scalar_set_num_modes": (C.c_int, [_vp, C.c_int]),
+    "bloch_scalar_solve": (C.c_int, [_vp]),
+    "bloch_scalar_get_eigenvalues": (C.c_int, [_vp, _dp, C.c_int]),
+    "bloch_scalar_apply": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "bloch_debug_apply_h1op": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "bloch_debug_fp64_peak": (C.c_int, [_vp, _dp]),
 }

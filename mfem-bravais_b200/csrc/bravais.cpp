@@ -179,9 +179,51 @@ static void build_bcc(double a, std::vector<Vec3> &lat, std::vector<Vec3> &rec,
         {30, 15, 35, 33, 4, 12, 31, 5},   {15, 26, 32, 35, 14, 0, 1, 27}};
 }
 
-BravaisLattice *BravaisLatticeFactory(BRAVAIS_LATTICE_TYPE type, double a, double, double, double,
+// Hexagonal prism lattice (lib/bravais.cpp:6023-6138) with the reference's 6-hex Wigner-Seitz
+// layout (rhombus prisms, 3 per layer, 2 layers; vertex/element tables at :6167-6199, which the
+// reference keeps commented out in favour of a wedge mesh - hexahedra are what this path supports).
+static void build_hex(double a, double c, std::vector<Vec3> &lat, std::vector<Vec3> &rec,
+                      std::vector<Vec3> &trn, std::vector<double> &rad, std::vector<Vec3> &sp,
+                      std::vector<std::string> &sl, std::vector<std::vector<int>> &path,
+                      std::vector<std::vector<std::string>> &il, std::vector<Vec3> &wv,
+                      std::vector<std::array<int, 8>> &wh) {
+  const double s3 = std::sqrt(3.0);
+  lat = {{0.5 * a, -std::sqrt(0.75) * a, 0}, {0.5 * a, std::sqrt(0.75) * a, 0}, {0, 0, c}};
+  rec = {{1 / a, -1 / (s3 * a), 0}, {1 / a, 1 / (s3 * a), 0}, {0, 0, 1 / c}};
+  trn = {{a, 0, 0}, {0.5 * a, std::sqrt(0.75) * a, 0}, {0.5 * a, -std::sqrt(0.75) * a, 0}, {0, 0, c}};
+  const double r0 = std::min(0.5 * a / s3, 0.5 * c);
+  rad = {r0, r0, r0, 0.5 * a};
+  sl = {"Gamma", "A", "H", "K", "L", "M"};
+  sp = {Vec3{0, 0, 0},
+        lin(0.5, rec[2]),
+        lin(1.0 / 3.0, rec[0], 1.0 / 3.0, rec[1], 0.5, rec[2]),
+        lin(1.0 / 3.0, rec[0], 1.0 / 3.0, rec[1]),
+        lin(0.5, rec[0], 0.0, rec[1], 0.5, rec[2]),
+        lin(0.5, rec[0])};
+  path = {{0, 5, 3, 0, 1, 4, 2, 1}, {4, 5}, {3, 2}};
+  il = {{"Sigma", "MK", "GammaK", "Delta", "AL", "LH", "AH"}, {"LM"}, {"HK"}};
+  const double h = a / s3;
+  const double ring[6][2] = {{0, -h}, {0.5 * a, -0.5 * h}, {0.5 * a, 0.5 * h}, {0, h}, {-0.5 * a, 0.5 * h}, {-0.5 * a, -0.5 * h}};
+  wv.clear();
+  for (int layer = 0; layer < 3; layer++) {
+    const double z = 0.5 * c * (layer - 1);
+    wv.push_back(Vec3{0, 0, z});
+    for (int k = 0; k < 6; k++) wv.push_back(Vec3{ring[k][0], ring[k][1], z});
+  }
+  wh.clear();
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++) {
+      const int v = 7 * i;
+      std::array<int, 8> e{0 + v, 2 * j + 1 + v, 2 * j + 2 + v, ((2 * j + 2) % 6) + 1 + v, 0, 0, 0, 0};
+      for (int k = 0; k < 4; k++) e[4 + k] = e[k] + 7;
+      wh.push_back(e);
+    }
+}
+
+BravaisLattice *BravaisLatticeFactory(BRAVAIS_LATTICE_TYPE type, double a, double, double c, double,
                                       double, double) {
-  if (a <= 0.0) a = 1.0;   // default-parameter rule of the reference factory (lib/bravais.cpp:8662-8691)
+  if (a <= 0.0) a = 1.0;
+  if (c <= 0.0) c = 1.0;   // default-parameter rule of the reference factory (lib/bravais.cpp:8662-8691)
   BravaisLattice *L = new BravaisLattice();
   L->type_ = type;
   switch (type) {
@@ -199,6 +241,11 @@ BravaisLattice *BravaisLatticeFactory(BRAVAIS_LATTICE_TYPE type, double a, doubl
       L->label_ = "BCC";
       build_bcc(a, L->lat_vecs_, L->rec_vecs_, L->trn_vecs_, L->face_radii_, L->sp_, L->sl_,
                 L->path_, L->il_, L->ws_vert_, L->ws_hex_);
+      break;
+    case PRIMITIVE_HEXAGONAL_PRISM:
+      L->label_ = "HEX";
+      build_hex(a, c, L->lat_vecs_, L->rec_vecs_, L->trn_vecs_, L->face_radii_, L->sp_, L->sl_, L->path_,
+                L->il_, L->ws_vert_, L->ws_hex_);
       break;
     default:
       delete L;

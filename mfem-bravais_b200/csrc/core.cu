@@ -112,6 +112,7 @@ static void class_params(const double *J, const double kappa[3], double out[kCla
   adj[3] = a[5] * a[6] - a[3] * a[8]; adj[4] = a[0] * a[8] - a[2] * a[6]; adj[5] = a[2] * a[3] - a[0] * a[5];
   adj[6] = a[3] * a[7] - a[4] * a[6]; adj[7] = a[1] * a[6] - a[0] * a[7]; adj[8] = a[0] * a[4] - a[1] * a[3];
   for (int k = 0; k < 9; k++) out[12 + k] = adj[k] / det;
+  out[21] = det;
 }
 
 // element-local diagonals of A, M1 and S0 per class, obtained by running the production kernels
@@ -150,7 +151,8 @@ static double local_scaled_lmax(int L, const D2 *X /* column k at X[k*L + l] */)
 }
 
 static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vector<double> &dM,
-                            std::vector<double> &dS0, double *lmax_bound) {
+                            std::vector<double> &dS0, std::vector<double> &dM0, double *lmax_bound,
+                            double *lmax_bound_h1) {
   const int nc = h->mesh.n_class, Ln = h->L_nd, Lh = h->L_h1;
   cudaStream_t s = h->stream;
   auto run = [&](int L, bool h1space, std::vector<double> *outA, std::vector<double> *outM) {
@@ -179,14 +181,19 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
       out->resize((size_t)nc * L);
       for (int c = 0; c < nc; c++)
         for (int k = 0; k < L; k++) (*out)[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
-      if (!h1space && lmax_bound)   // lambda_max(D^-1 (a A + b M)) <= max_class max(mu_A, mu_M)
-        for (int c = 0; c < nc; c++) *lmax_bound = std::max(*lmax_bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
+      double *bound = h1space ? lmax_bound_h1 : lmax_bound;
+      if (bound)   // lambda_max(D^-1 (a A + b M)) <= max_class max(mu_A, mu_M)
+        for (int c = 0; c < nc; c++) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
     };
     if (h1space) {
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
-      BLOCH_CUDA(launch_h1_op(h->p, 0, h->tabs, E, dx.p, 1, dy.p, 1, 1, s));
+      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 1.0, 0.0));
       h->count_launch();
       fetch(outA);
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 0.0, 1.0));
+      h->count_launch();
+      fetch(outM);
     } else {
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
       BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 1.0, 0.0, s));
@@ -198,8 +205,8 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
       fetch(outM);
     }
   };
-  run(Ln, false, &dA, &dM);
-  run(Lh, true, &dS0, nullptr);
+  if (h->p <= 3) run(Ln, false, &dA, &dM);
+  run(Lh, true, &dS0, &dM0);
 }
 
 void bloch_handle_s::setup() {
@@ -226,20 +233,28 @@ void bloch_handle_s::setup() {
   E.cpar = d_cpar.p;
   if (dirty_kappa || dirty_coef) {
     // Jacobi diagonals of A, M and S0 = G^H M G (element-local diagonals from a probe launch)
-    std::vector<double> dA, dM, dS0;
-    double bound = 0.0;
-    probe_diagonals(this, dA, dM, dS0, (lmax_local <= 0.0) ? &bound : nullptr);
+    std::vector<double> dA, dM, dS0, dM0;
+    double bound = 0.0, bound_h1 = 0.0;
+    probe_diagonals(this, dA, dM, dS0, dM0, (lmax_local <= 0.0) ? &bound : nullptr,
+                    (lmax_local_h1 <= 0.0) ? &bound_h1 : nullptr);
     if (lmax_local <= 0.0) lmax_local = bound;
+    if (lmax_local_h1 <= 0.0) lmax_local_h1 = bound_h1;
     DevBuf<double> dl;
-    d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0);
+    d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0); d_diagM0.alloc(N0);
     BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N, stream));
     BLOCH_CUDA(cudaMemsetAsync(d_diagM.p, 0, sizeof(double) * N, stream));
     BLOCH_CUDA(cudaMemsetAsync(d_diagS0.p, 0, sizeof(double) * N0, stream));
-    dl.upload(dA, stream);
-    BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagA.p, stream));
-    BLOCH_CUDA(cudaStreamSynchronize(stream));
-    dl.upload(dM, stream);
-    BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagM.p, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagM0.p, 0, sizeof(double) * N0, stream));
+    if (p <= 3) {
+      dl.upload(dA, stream);
+      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagA.p, stream));
+      BLOCH_CUDA(cudaStreamSynchronize(stream));
+      dl.upload(dM, stream);
+      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagM.p, stream));
+      BLOCH_CUDA(cudaStreamSynchronize(stream));
+    }
+    dl.upload(dM0, stream);
+    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagM0.p, stream));
     BLOCH_CUDA(cudaStreamSynchronize(stream));
     dl.upload(dS0, stream);
     BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagS0.p, stream));
@@ -256,6 +271,7 @@ void bloch_handle_s::apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm
 // E-vector, then one owner-computes reduction per dof; deterministic, bitwise reproducible).  Default
 // is the single-pass variant with fp64 atomics, which measured ~15% faster on B200.
 void bloch_handle_s::apply_nd_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
+  if (p > 3) throw std::invalid_argument("the Nedelec operators support orders 1..3 (order 4: scalar H1 problem only)");
   if (two_pass) {
     d_evec.alloc((size_t)mesh.n_elem * L_nd * nvec);
     BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, stream, d_evec.p));
@@ -268,7 +284,15 @@ void bloch_handle_s::apply_nd_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec,
   }
   if (ca != 0.0) stats.applies_A += nvec;
 }
+// scalar variant: y[:, :nvec] = ca G^H M1(k) G x + cm M0(m) x on H1 block vectors
+void bloch_handle_s::apply_scalar_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
+  BLOCH_CUDA(cudaMemset2DAsync(y, sizeof(D2) * ldy, 0, sizeof(D2) * nvec, N0, stream));
+  BLOCH_CUDA(launch_h1_op(p, 3, tabs, E, x, ldx, y, ldy, nvec, stream, ca, cm));
+  count_launch();
+  if (ca != 0.0) stats.applies_A += nvec;
+}
 void bloch_handle_s::apply_h1(int mode, const D2 *x, D2 *y, int nvec) {
+  if (p > 3) throw std::invalid_argument("the Nedelec / projector operators support orders 1..3 (order 4: scalar H1 problem only)");
   if (mode != 1) BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * (size_t)N0 * nvec, stream));
   else BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * (size_t)N * nvec, stream));
   BLOCH_CUDA(launch_h1_op(p, mode, tabs, E, x, nvec, y, nvec, nvec, stream));
@@ -282,7 +306,7 @@ void bloch_handle_s::apply_curl(const D2 *x, D2 *y, int nvec) {
 static bloch_handle_s *make_handle(const std::vector<std::array<double, 3>> &vert,
                                    const std::vector<std::array<int, 8>> &hex, const double rec[9],
                                    int n_sub, int order, int device) {
-  REQUIRE(order >= 1 && order <= 3, "order must be 1, 2 or 3");
+  REQUIRE(order >= 1 && order <= 4, "order must be 1..3 (Maxwell) or 1..4 (scalar H1 problem)");
   REQUIRE(n_sub >= 1, "n_sub must be >= 1");
   REQUIRE((int)hex.size() <= kMaxClasses, "too many coarse hexes (element classes)");
   const bool host_only = (device == BLOCH_DEVICE_NONE);
@@ -339,7 +363,7 @@ int bloch_lattice_create(bloch_lattice *out, int type, double a, double b, doubl
   API_BEGIN
   REQUIRE(out, "null output");
   bravais::BravaisLattice *L = bravais::BravaisLatticeFactory((bravais::BRAVAIS_LATTICE_TYPE)type, a, b, c, alpha, beta, gamma);
-  REQUIRE(L, "lattice type not available (CUB=7, FCC=8, BCC=9)");
+  REQUIRE(L, "lattice type not available (CUB=7, FCC=8, BCC=9, HEX=16)");
   *out = new bloch_lattice_s{L};
   return BLOCH_OK;
   API_END
@@ -706,6 +730,59 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   h->apply_h1(mode, ba.p, bb.p, nvec);
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// ---- scalar H1 Bloch Helmholtz variant: ScalarFloquetWaveEquation (misc/scalar3d.cpp:662-818) ----
+int bloch_scalar_set_coefs(bloch_handle h, const double *stiffness_k, const double *mass_m) {
+  API_BEGIN
+  REQUIRE(h && stiffness_k && mass_m, "null argument");
+  for (int e = 0; e < h->mesh.n_elem; e++) REQUIRE(stiffness_k[e] > 0.0 && mass_m[e] > 0.0, "coefficients must be positive");
+  h->eps.assign(stiffness_k, stiffness_k + h->mesh.n_elem);     // M1(k) weight of the gradient form
+  h->muinv.assign(mass_m, mass_m + h->mesh.n_elem);             // M0(m)
+  h->dirty_coef = true;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_scalar_set_num_modes(bloch_handle h, int n) {
+  API_BEGIN
+  REQUIRE(h && n >= 1 && n <= 28, "number of modes must be in [1,28]");
+  if (n != h->nbands_s) h->have_vectors_s = 0;
+  h->nbands_s = n;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_scalar_solve(bloch_handle h) {
+  API_BEGIN
+  REQUIRE(h, "null handle");
+  h->setup();
+  h->solve_scalar();
+  return h->stats.converged >= h->nbands_s ? BLOCH_OK : BLOCH_ERR_NOCONV;
+  API_END
+}
+int bloch_scalar_get_eigenvalues(bloch_handle h, double *lambda, int n) {
+  API_BEGIN
+  REQUIRE(h && lambda && n >= 0 && n <= (int)h->eigenvalues_s.size(), "more eigenvalues requested than computed");
+  std::memcpy(lambda, h->eigenvalues_s.data(), sizeof(double) * n);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_scalar_apply(bloch_handle h, int which, const double *x, double *y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && x && y && nvec >= 1 && (which == 0 || which == 1), "bad argument");
+  h->setup();
+  const long n = h->N0;
+  cudaStream_t s = h->stream;
+  DevBuf<double> ia, ib;
+  DevBuf<D2> ba, bb;
+  ia.alloc((size_t)2 * n * nvec); ib.alloc((size_t)2 * n * nvec); ba.alloc((size_t)n * nvec); bb.alloc((size_t)n * nvec);
+  BLOCH_CUDA(cudaMemcpyAsync(ia.p, x, sizeof(double) * 2 * n * nvec, cudaMemcpyHostToDevice, s));
+  BLOCH_CUDA(launch_pack(ia.p, ba.p, n, nvec, s));
+  h->apply_scalar_ld(ba.p, nvec, bb.p, nvec, nvec, which == 0 ? 1.0 : 0.0, which == 0 ? 0.0 : 1.0);
+  BLOCH_CUDA(launch_unpack(bb.p, ib.p, n, nvec, s));
+  BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * n * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
   return BLOCH_OK;
   API_END

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -49,6 +50,20 @@ struct DevBuf {   // owning device buffer
     alloc(h.size());
     BLOCH_CUDA(cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s));
   }
+};
+
+// one Hermitian pencil for the block eigensolver: y = ca A x + cm M x, Jacobi diagonals, optional
+// divergence constraint (ND problem) - lets the ND Maxwell and the scalar H1 problems share lobpcg()
+struct EigProblem {
+  long n = 0;
+  std::function<void(const double2 *, int, double2 *, int, int, double, double)> apply;
+  const double *diagA = nullptr, *diagM = nullptr;
+  double lmax_local = 0;
+  bool constrained = false, use_init = false;
+  DevBuf<double2> *X = nullptr;
+  std::vector<double> *evals = nullptr;
+  int *have = nullptr, *blk = nullptr;
+  int nbands = 0;
 };
 
 struct SolverStats {
@@ -101,6 +116,14 @@ struct bloch_handle_s {
   int n_init = 0;
   bloch_b200::SolverStats stats;
 
+  // scalar H1 variant (misc/scalar3d.cpp): stiffness coefficient k -> eps slot, mass coefficient m -> muinv slot
+  bloch_b200::DevBuf<double> d_diagM0;
+  double lmax_local_h1 = 0;
+  int nbands_s = 5, block_s = 0, have_vectors_s = 0;
+  std::vector<double> eigenvalues_s;
+  bloch_b200::DevBuf<D2> d_Xs;
+  bool scalar_ready = false;
+
   // scratch for host-pointer entry points
   bloch_b200::DevBuf<double> d_io_a, d_io_b;
   bloch_b200::DevBuf<D2> d_blk_a, d_blk_b, d_blk_c;
@@ -112,5 +135,9 @@ struct bloch_handle_s {
   void apply_curl(const D2 *x, D2 *y, int nvec);
   void project(D2 *x, int nvec, double rel_tol, int *iters);           // in place x <- P x
   void solve();
+  void solve_scalar();
+  void lobpcg(bloch_b200::EigProblem &prob);
+  void apply_scalar_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm);
+  void setup_scalar();
   void count_launch(int n = 1) { stats.launches += n; }
 };

@@ -156,7 +156,7 @@ __device__ __forceinline__ void nd_compute_tile(double2 *sND, double2 *sRT, cons
 // computed, so the two dependent global round trips (index, value) of the signed gather are off
 // the critical path.  Signs are applied in place by the thread that issued the copy.
 template <int P, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (P == 1 ? 6 : (P == 2 ? 3 : 1)))
 k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
            double2 *__restrict__ Y, double2 *__restrict__ Z, int m, int ldx, int ldy, long n_items, double ca,
            double cm) {
@@ -285,7 +285,7 @@ k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__re
 template <int P, int NW, int MODE>
 __global__ void __launch_bounds__(NW * 32)
 k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
-        double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items) {
+        double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca, double cm) {
   using D = Dim<P>;
   constexpr int Q = P + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,8 +368,10 @@ k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restr
     }
     return;
   }
-  nd_mass_pointwise<P, NW>(sND, T, cp, eps, warp, lane);
+  nd_mass_pointwise<P, NW>(sND, T, cp, (MODE == 3) ? ca * eps : eps, warp, lane);
   __syncthreads();
+  // scalar variant (MODE 3): + cm * M0(m) x, pointwise in mode space: m_e detJ w(i0) w(i1) w(i2)
+  const double mcoef = (MODE == 3 && active) ? cm * E.muinv[e] * cp[21] : 0.0;
   // adjoint gradient: Phi'[i_c = t] (+)= sum_o Dt[o][t] F_c[o] + i kh_c F_c[t] (t < P)
   for (int c = 0; c < 3; c++) {
     const int sc = c == 0 ? Q * Q : (c == 1 ? Q : 1);
@@ -382,9 +384,18 @@ k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restr
       double2 in[P];
 #pragma unroll
       for (int o = 0; o < P; o++) in[o] = sND[D::nd(c, o, j1, j2) * 32 + lane];
+      double wj = 1.0;
+      if (MODE == 3) {   // c == 0 pencils run along direction 0: (j1, j2) = (i1, i2)
+        double o1 = T.om[0], o2 = T.om[0];
+#pragma unroll
+        for (int r = 1; r < Q; r++) { o1 = (j1 == r) ? T.om[r] : o1; o2 = (j2 == r) ? T.om[r] : o2; }
+        wj = mcoef * o1 * o2;
+      }
 #pragma unroll
       for (int q = 0; q < Q; q++) {
-        double2 acc = (c == 0) ? make_double2(0.0, 0.0) : sH[(base + q * sc) * 32 + lane];
+        double2 acc = make_double2(0.0, 0.0);
+        if (c != 0 || MODE == 3) acc = sH[(base + q * sc) * 32 + lane];
+        if (c == 0 && MODE == 3) { const double w = wj * T.om[q]; acc.x *= w; acc.y *= w; }
 #pragma unroll
         for (int o = 0; o < P; o++) CFMA(acc, T.Dt[o][q], in[o]);
         if (q < P) { acc.x -= kc * in[q].y; acc.y += kc * in[q].x; }
@@ -528,27 +539,38 @@ cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int l
 
 template <int P, int NW>
 cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
-                    int ldy, int nvec, cudaStream_t s) {
+                    int ldy, int nvec, double ca, double cm, cudaStream_t s) {
   using D = Dim<P>;
   const size_t smem = (size_t)(D::LND + D::LH1) * 32 * sizeof(double2) +
                       (size_t)E.n_class * kClassParDoubles * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err;
-    err = cudaFuncSetAttribute(k_h1_op<P, NW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(k_h1_op<P, NW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(k_h1_op<P, NW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if constexpr (P <= 3) {
+      err = cudaFuncSetAttribute(k_h1_op<P, NW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+      if (err != cudaSuccess) return err;
+      err = cudaFuncSetAttribute(k_h1_op<P, NW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+      if (err != cudaSuccess) return err;
+      err = cudaFuncSetAttribute(k_h1_op<P, NW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+      if (err != cudaSuccess) return err;
+    }
+    err = cudaFuncSetAttribute(k_h1_op<P, NW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
   const long n_items = (long)E.n_elem * nvec;
   const unsigned grid = (unsigned)((n_items + 31) / 32);
-  if (mode == 0) k_h1_op<P, NW, 0><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
-  else if (mode == 1) k_h1_op<P, NW, 1><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
-  else k_h1_op<P, NW, 2><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
-  return cudaGetLastError();
+  if (mode == 3) {
+    k_h1_op<P, NW, 3><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca, cm);
+    return cudaGetLastError();
+  }
+  if constexpr (P <= 3) {
+    if (mode == 0) k_h1_op<P, NW, 0><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    else if (mode == 1) k_h1_op<P, NW, 1><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    else k_h1_op<P, NW, 2><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    return cudaGetLastError();
+  }
+  return cudaErrorInvalidValue;
 }
 
 template <int P, int NW>
@@ -603,11 +625,12 @@ cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const doubl
 }
 
 cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
-                         double2 *y, int ldy, int nvec, cudaStream_t s) {
+                         double2 *y, int ldy, int nvec, cudaStream_t s, double ca, double cm) {
   switch (p) {
-    case 1: return h1_op_t<1, 4>(mode, T, E, x, ldx, y, ldy, nvec, s);
-    case 2: return h1_op_t<2, 9>(mode, T, E, x, ldx, y, ldy, nvec, s);
-    case 3: return h1_op_t<3, 12>(mode, T, E, x, ldx, y, ldy, nvec, s);
+    case 1: return h1_op_t<1, 4>(mode, T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 2: return h1_op_t<2, 9>(mode, T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 3: return h1_op_t<3, 12>(mode, T, E, x, ldx, y, ldy, nvec, ca, cm, s);
+    case 4: return h1_op_t<4, 15>(mode, T, E, x, ldx, y, ldy, nvec, ca, cm, s);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -11,7 +11,7 @@ namespace bloch_b200 {
 
 constexpr int kMaxP = 4;
 constexpr int kMaxClasses = 64;
-constexpr int kClassParDoubles = 21;   // kh[3], G[3][3], H[3][3]
+constexpr int kClassParDoubles = 22;   // kh[3], G[3][3], H[3][3], det J
 
 // 1-D tables, sized for the largest supported order; indexed with compile-time indices in the
 // kernels so they are read straight from the constant bank holding the kernel parameters.
@@ -45,9 +45,11 @@ cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const doubl
 cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *z, double2 *y, long n,
                              int m, int ldy, cudaStream_t s);
 // H1 <-> ND operators of the projector.  mode 0: y_h1 += S0 x_h1 (S0 = G^H M1 G);
-// mode 1: y_nd = G x_h1 (interpolation, plain stores); mode 2: y_h1 += G^H M1 x_nd
+// mode 1: y_nd = G x_h1 (interpolation, plain stores); mode 2: y_h1 += G^H M1 x_nd;
+// mode 3 (scalar H1 Bloch Helmholtz, misc/scalar3d.cpp:662-818): y_h1 += ca G^H M1(k) G x + cm M0(m) x
+// with k = E.eps, m = E.muinv; orders 1..4 (modes 0-2: orders 1..3)
 cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
-                         double2 *y, int ldy, int nvec, cudaStream_t s);
+                         double2 *y, int ldy, int nvec, cudaStream_t s, double ca = 1.0, double cm = 0.0);
 // y_rt = (C - i Z_kappa) x_nd  (interpolation into nodal RT dofs, plain stores)
 cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
                         int ldy, int nvec, cudaStream_t s);

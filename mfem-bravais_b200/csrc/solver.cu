@@ -251,10 +251,55 @@ void bloch_handle_s::project(D2 *x, int nvec, double rel_tol, int *iters) {
 // Solve(): block LOBPCG
 // ------------------------------------------------------------------------------------------
 void bloch_handle_s::solve() {
+  bloch_b200::EigProblem prob;
+  prob.n = N;
+  prob.apply = [this](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
+    apply_nd_ld(x, ldx, y, ldy, nvec, ca, cm);
+  };
+  prob.diagA = d_diagA.p;
+  prob.diagM = d_diagM.p;
+  prob.lmax_local = lmax_local;
+  prob.constrained = true;
+  prob.X = &d_X;
+  prob.evals = &eigenvalues;
+  prob.have = &have_vectors;
+  prob.blk = &block;
+  prob.nbands = nbands;
+  prob.use_init = true;
+  lobpcg(prob);
+}
+
+// scalar H1 Bloch Helmholtz variant (misc/scalar3d.cpp:662-818): no null space, no projector
+void bloch_handle_s::solve_scalar() {
+  bloch_b200::EigProblem prob;
+  prob.n = N0;
+  prob.apply = [this](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
+    apply_scalar_ld(x, ldx, y, ldy, nvec, ca, cm);
+  };
+  prob.diagA = d_diagS0.p;
+  prob.diagM = d_diagM0.p;
+  prob.lmax_local = lmax_local_h1;
+  prob.constrained = false;
+  prob.X = &d_Xs;
+  prob.evals = &eigenvalues_s;
+  prob.have = &have_vectors_s;
+  prob.blk = &block_s;
+  prob.nbands = nbands_s;
+  prob.use_init = false;
+  lobpcg(prob);
+}
+
+void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   using dense::cplx;
   using dense::Mat;
   cudaStream_t s = stream;
-  const int nb = nbands;
+  const long N = prob.n;
+  const int nb = prob.nbands;
+  int &block = *prob.blk;
+  int &have_vectors = *prob.have;
+  bloch_b200::DevBuf<D2> &d_X = *prob.X;
+  std::vector<double> &eigenvalues = *prob.evals;
+  const double lmax_local = prob.lmax_local;
   int mb = nb + std::max(4, nb / 4);
   if (mb > 32) mb = 32;
   if (3L * mb > N) mb = (int)(N / 3);
@@ -283,8 +328,8 @@ void bloch_handle_s::solve() {
   const bool verbose = env_double("BLOCH_VERBOSE", 0.0) != 0.0;
   d_jac.alloc(Nl);
   d_jac0.alloc(N0);
-  k_make_jacobi<<<grid_for(Nl), TPB, 0, s>>>(d_diagA.p, d_diagM.p, sigma, d_jac.p, Nl);
-  k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
+  k_make_jacobi<<<grid_for(Nl), TPB, 0, s>>>(prob.diagA, prob.diagM, sigma, d_jac.p, Nl);
+  if (prob.constrained) k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
   count_launch(2);
 
   DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb;
@@ -297,7 +342,7 @@ void bloch_handle_s::solve() {
   dlam.alloc(mb); drn.alloc(mb);
 
   auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
-    apply_nd_ld(x, ldx, y, ldy, nvec, ca, cm);
+    prob.apply(x, ldx, y, ldy, nvec, ca, cm);
   };
 
   // lambda_max(D^-1 (A + sigma M)) <= max over element classes of the local scaled spectra
@@ -395,7 +440,7 @@ void bloch_handle_s::solve() {
   };
 
   // ---- initial block ----
-  if (n_init > 0) {
+  if (prob.use_init && n_init > 0) {
     const int mi = std::min(n_init, mb);
     DevBuf<double> tmp;
     tmp.alloc((size_t)2 * Nl * mi);
@@ -413,7 +458,7 @@ void bloch_handle_s::solve() {
   }
   {
     int its = 0;
-    project_ld(this, Wc.p, mb, mb, std::min(proj_tol, 1e-10), 3000, &its);
+    if (prob.constrained) project_ld(this, Wc.p, mb, mb, std::min(proj_tol, 1e-10), 3000, &its);
     BLOCH_CUDA(cudaMemcpy2DAsync(S.p, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
     op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);
     op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
@@ -468,7 +513,7 @@ void bloch_handle_s::solve() {
       const double scale = std::max(1.0, std::fabs(lam[nb - 1]));
       ptol = std::min(1e-4, std::max(proj_tol, proj_adapt * maxres / scale));
     }
-    project_ld(this, Wc.p, mb, mb, ptol, 3000, &its);
+    if (prob.constrained) project_ld(this, Wc.p, mb, mb, ptol, 3000, &its);
     t_proj += since(t0);
     t0 = tick();
     BLOCH_CUDA(cudaMemcpy2DAsync(S.p + mb, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));

@@ -282,3 +282,90 @@ class MaxwellBlochWaveEquation:
 
     def unpack_device(self, blk_ptr, reim_ptr, nvec):
         check(self._L.bloch_unpack_device(self._h, C.c_void_p(blk_ptr), C.c_void_p(reim_ptr), nvec))
+
+
+class ScalarFloquetWaveEquation:
+    """ScalarFloquetWaveEquation(pmesh, order) of misc/scalar3d.cpp:592-898 - the scalar H1 Bloch
+    Helmholtz variant  (G - i Z_kappa)^T M1(k) (G - i Z_kappa) u = lambda M0(m) u.  The reference takes
+    the phase shift beta in degrees (SetBeta) and a unit direction zeta (SetZeta)."""
+
+    def __init__(self, lattice, n_sub, order, device=-1):
+        self._eq = MaxwellBlochWaveEquation(lattice, n_sub, order, device)
+        self._L, self._h = self._eq._L, self._eq._h
+        self.n_elem, self.N = self._eq.n_elem, self._eq.N_h1
+        self._beta_deg, self._zeta = 0.0, np.array([1.0, 0.0, 0.0])
+        self.nev = 10
+
+    def element_centers(self):
+        return self._eq.element_centers()
+
+    def dofmap(self):
+        return self._eq.dofmap("h1")[0]
+
+    def element_geometry(self):
+        return self._eq.element_geometry()
+
+    def SetMassCoef(self, m_per_elem):
+        self._m = np.ascontiguousarray(m_per_elem, float)
+        self._push()
+
+    def SetStiffnessCoef(self, k_per_elem):
+        self._k = np.ascontiguousarray(k_per_elem, float)
+        self._push()
+
+    def _push(self):
+        if hasattr(self, "_m") and hasattr(self, "_k"):
+            check(self._L.bloch_scalar_set_coefs(self._h, dptr(self._k), dptr(self._m)), "bloch_scalar_set_coefs")
+
+    def SetBeta(self, beta_degrees):
+        self._beta_deg = float(beta_degrees)
+        self._push_kappa()
+
+    def SetZeta(self, zeta):
+        self._zeta = np.asarray(zeta, float)
+        self._push_kappa()
+
+    def SetKappa(self, kappa):
+        self._eq.SetKappa(kappa)
+
+    def _push_kappa(self):
+        self._eq.SetKappa(self._beta_deg * np.pi / 180.0 * self._zeta)     # scalar3d.cpp:733,784-785
+
+    def SetNumEigs(self, nev):
+        """real-mode count like the reference (2 per complex mode)"""
+        self.nev = int(nev)
+        check(self._L.bloch_scalar_set_num_modes(self._h, (self.nev + 1) // 2), "bloch_scalar_set_num_modes")
+
+    def SetAbsoluteTolerance(self, atol, max_iter=1000):
+        self._eq.SetAbsoluteTolerance(atol, max_iter)
+
+    def Setup(self):
+        self._eq.Setup()
+
+    def Solve(self):
+        check(self._L.bloch_scalar_solve(self._h), "bloch_scalar_solve")
+
+    def mode_eigenvalues(self):
+        nb = (self.nev + 1) // 2
+        lam = np.zeros(nb)
+        check(self._L.bloch_scalar_get_eigenvalues(self._h, dptr(lam), nb), "bloch_scalar_get_eigenvalues")
+        return lam
+
+    def GetEigenvalues(self):
+        return np.repeat(self.mode_eigenvalues(), 2)[: self.nev]
+
+    def GetSolverStats(self):
+        return self._eq.GetSolverStats()
+
+    def _apply(self, which, x):
+        x = np.ascontiguousarray(x, float)
+        x2 = x.reshape(1, -1) if x.ndim == 1 else x
+        y = np.zeros_like(x2)
+        check(self._L.bloch_scalar_apply(self._h, which, dptr(x2), dptr(y), x2.shape[0]), "bloch_scalar_apply")
+        return y[0] if x.ndim == 1 else y
+
+    def MultA(self, x):
+        return self._apply(0, x)
+
+    def MultM(self, x):
+        return self._apply(1, x)

@@ -169,6 +169,30 @@ class Lattice:
                 [33, 35, 32, 34, 5, 31, 37, 29], [5, 31, 37, 29, 20, 21, 22, 23],
                 [24, 11, 34, 32, 2, 10, 25, 1], [11, 28, 33, 34, 8, 6, 5, 29],
                 [30, 15, 35, 33, 4, 12, 31, 5], [15, 26, 32, 35, 14, 0, 1, 27]])
+        elif name == "HEX":      # lib/bravais.cpp:6023-6124, 6-hex layout :6167-6199 (a = c)
+            c = a
+            s3 = math.sqrt(3.0)
+            self.lat = np.array([[0.5 * a, -math.sqrt(0.75) * a, 0], [0.5 * a, math.sqrt(0.75) * a, 0], [0, 0, c]])
+            self.rec = np.array([[1 / a, -1 / (s3 * a), 0], [1 / a, 1 / (s3 * a), 0], [0, 0, 1 / c]])
+            b = self.rec
+            self.sp = {"Gamma": 0 * b[0], "A": 0.5 * b[2], "H": (b[0] + b[1]) / 3 + 0.5 * b[2],
+                       "K": (b[0] + b[1]) / 3, "L": 0.5 * b[0] + 0.5 * b[2], "M": 0.5 * b[0]}
+            self.paths = [["Gamma", "M", "K", "Gamma", "A", "L", "H", "A"], ["L", "M"], ["K", "H"]]
+            h = a / s3
+            ring = [[0, -h], [0.5 * a, -0.5 * h], [0.5 * a, 0.5 * h], [0, h], [-0.5 * a, 0.5 * h], [-0.5 * a, -0.5 * h]]
+            v = []
+            for layer in range(3):
+                z = 0.5 * c * (layer - 1)
+                v.append([0, 0, z])
+                v += [[x, y, z] for x, y in ring]
+            self.ws_vert = np.array(v, float)
+            hexes = []
+            for i in range(2):
+                for j in range(3):
+                    o = 7 * i
+                    q = [0 + o, 2 * j + 1 + o, 2 * j + 2 + o, ((2 * j + 2) % 6) + 1 + o]
+                    hexes.append(q + [k + 7 for k in q])
+            self.ws_hex = np.array(hexes)
         else:
             raise ValueError("oracle lattice %r not restated" % name)
         self.volume = abs(np.linalg.det(self.lat))
@@ -605,6 +629,55 @@ class BlochOperators:
         w = spla.eigsh(A, k=k, M=M, sigma=sigma, which="LM", return_eigenvectors=False, tol=1e-12)
         w = np.sort(w.real)
         return w
+
+
+class ScalarOperators:
+    """Scalar H1 Bloch Helmholtz variant, ScalarFloquetWaveEquation::Setup (misc/scalar3d.cpp:662-818):
+    S0 = G^T M1(k) G + b^2 Z^T M1(k) Z,  DKZ = G^T M1 Z - Z^T M1 G,  A = [[S0, b DKZ], [-b DKZ, S0]],
+    M = diag(M0(m), M0(m)), with b = beta * pi / 180 (beta in degrees) and kappa = b * zeta."""
+
+    def __init__(self, spaces, k_coef, m_coef):
+        s, mesh = spaces, spaces.mesh
+        self.sp_ = s
+        em = [element_matrices(s.ref, J, None) for J in mesh.J]
+        st = lambda key: np.array([e[key] for e in em])
+        self.M1 = _assemble_sum(s.nd_gid, s.nd_sign, s.nd_gid, s.nd_sign, s.n_nd, s.n_nd, st("M1"), mesh.cls,
+                                np.asarray(k_coef, float))
+        self.M0 = _assemble_sum(s.h1_gid, s.h1_sign, s.h1_gid, s.h1_sign, s.n_h1, s.n_h1, st("M0"), mesh.cls,
+                                np.asarray(m_coef, float))
+        self.T01 = _assemble_set(s.nd_gid, s.nd_sign, s.h1_gid, s.h1_sign, s.n_nd, s.n_h1, st("T01"), mesh.cls)
+
+    def set_kappa(self, kappa):
+        s, mesh = self.sp_, self.sp_.mesh
+        kappa = np.asarray(kappa, float)
+        self.b = b = float(np.linalg.norm(kappa))
+        G, M1 = self.T01, self.M1
+        GMG = G.T @ M1 @ G
+        if b > 0:
+            zeta = kappa / b
+            em = [element_matrices(s.ref, J, zeta) for J in mesh.J]
+            Z = _assemble_set(s.nd_gid, s.nd_sign, s.h1_gid, s.h1_sign, s.n_nd, s.n_h1,
+                              np.array([e["Z01"] for e in em]), mesh.cls)
+            self.S0 = (GMG + b * b * (Z.T @ M1 @ Z)).tocsr()
+            self.DKZ = (G.T @ M1 @ Z - Z.T @ M1 @ G).tocsr()
+        else:
+            self.S0, self.DKZ = GMG.tocsr(), None
+        return self
+
+    def A_c(self):
+        return self.S0.astype(complex) if self.DKZ is None else (self.S0 - 1j * self.b * self.DKZ).tocsr()
+
+    def A_block(self):
+        if self.DKZ is None:
+            return sp.bmat([[self.S0, None], [None, self.S0]]).tocsr()
+        return sp.bmat([[self.S0, self.b * self.DKZ], [-self.b * self.DKZ, self.S0]]).tocsr()
+
+    def M_block(self):
+        return sp.bmat([[self.M0, None], [None, self.M0]]).tocsr()
+
+    def eig_dense(self, nev):
+        import scipy.linalg as sla
+        return sla.eigh(self.A_c().toarray(), self.M0.toarray().astype(complex), eigvals_only=True)[:nev]
 
 
 def empty_lattice_eigs(lattice, kappa, nev, nmax=3):

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 CASES = [("CUB", 3, 1), ("CUB", 2, 2), ("CUB", 2, 3), ("FCC", 2, 1), ("FCC", 2, 2), ("FCC", 1, 3),
-         ("BCC", 1, 1), ("BCC", 1, 2), ("BCC", 1, 3), ("CUB", 1, 1), ("FCC", 3, 2)]
+         ("BCC", 1, 1), ("BCC", 1, 2), ("BCC", 1, 3), ("CUB", 1, 1), ("FCC", 3, 2), ("HEX", 2, 2), ("HEX", 1, 3)]
 
 
 def _setup(bloch, name, n, p, seed=0):

@@ -19,7 +19,7 @@ def _eq(bloch, name, n, p, eps_fn=None, device=-1):
 
 
 @pytest.mark.parametrize("name,n,p,nb", [("CUB", 3, 1, 6), ("CUB", 2, 2, 8), ("FCC", 2, 1, 4),
-                                          ("FCC", 2, 2, 10), ("BCC", 1, 2, 8), ("CUB", 2, 3, 10)])
+                                          ("FCC", 2, 2, 10), ("BCC", 1, 2, 8), ("CUB", 2, 3, 10), ("HEX", 2, 2, 8)])
 def test_bands_match_dense_constrained_pencil(bloch, name, n, p, nb):
     L, eq, eps = _eq(bloch, name, n, p)
     kappa = np.array([0.7, -0.4, 1.1])
@@ -112,6 +112,8 @@ def test_golden_fixtures(bloch):
         assert eq.N == c["n_nd"]
         eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()) if c["sphere"] else np.ones(eq.n_elem))
         nb = len(c["eigenvalues"])
-        eq.SetAbsoluteTolerance(1e-9)
+        # residual 1e-7 => eigenvalue error ~1e-14 relative (quadratic); the tiny Gamma-point case
+        # (12-fold cluster cut by the block) is not reliably driven below 1e-8, see DESIGN.md section 6
+        eq.SetAbsoluteTolerance(1e-7)
         lam = eq.GetEigenvalues(2 * nb, np.array(c["kappa"]))[0::2]
         assert np.allclose(lam, c["eigenvalues"], rtol=1e-7, atol=1e-8), (c["lattice"], c["order"], lam, c["eigenvalues"])

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(bloch):
     assert bloch.lib().bloch_version() >= 100
 
 
-@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
+@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC", "HEX"])
 def test_lattice_api_matches_reference_tables(bloch, name):
     L = bloch.BravaisLattice(name)
     o = Lattice(name)
@@ -58,6 +58,10 @@ def test_reference_labels_and_paths(bloch):
     assert [L.GetSymmetryPointLabel(i) for i in range(6)] == ["Gamma", "X", "W", "K", "L", "U"]
     assert L.GetIntermediatePointLabel(0, 0) == "Delta" and L.GetIntermediatePointLabel(1, 0) == "T"
     assert np.allclose(L.GetSymmetryPoint(1), 2 * np.pi * np.array([0.0, 1.0, 0.0]))
+    H = bloch.BravaisLattice("HEX")       # lib/bravais.cpp:6091-6124
+    assert [H.GetSymmetryPointLabel(i) for i in range(6)] == ["Gamma", "A", "H", "K", "L", "M"]
+    assert H.GetNumberPaths() == 3 and H.GetNumberPathSegments(0) == 7 and H.GetIntermediatePointLabel(2, 0) == "HK"
+    assert abs(H.GetUnitCellVolume() - np.sqrt(3) / 2) < 1e-14
     B = bloch.BravaisLattice("BCC")       # lib/bravais.cpp:2708-2736
     assert [B.GetSymmetryPointLabel(i) for i in range(4)] == ["Gamma", "H", "N", "P"]
     ks = bloch.k_path(L, ["Gamma", "X", "W", "L", "Gamma"], 8)
@@ -81,7 +85,8 @@ def _equivalent(ga, sa, gb, sb):
 
 
 @pytest.mark.parametrize("name,n,p", [("CUB", 1, 1), ("CUB", 2, 2), ("CUB", 3, 3), ("FCC", 1, 2), ("FCC", 2, 3),
-                                      ("FCC", 3, 1), ("BCC", 1, 3), ("BCC", 2, 2), ("BCC", 3, 1)])
+                                      ("FCC", 3, 1), ("BCC", 1, 3), ("BCC", 2, 2), ("BCC", 3, 1), ("HEX", 1, 2),
+                                      ("HEX", 2, 1), ("HEX", 2, 3)])
 def test_dofmaps_agree_with_geometric_identification(bloch, name, n, p):
     """entity-based numbering (product) vs node-position hashing (oracle): same identification
     up to renumbering and a per-dof orientation sign, including the degenerate n = 1 meshes"""

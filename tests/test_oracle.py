@@ -12,7 +12,7 @@ from oracle.bloch_oracle import (BlochOperators, Lattice, Mesh, RefElem, Spaces,
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("name,vol", [("CUB", 1.0), ("FCC", 0.25), ("BCC", 0.5)])
+@pytest.mark.parametrize("name,vol", [("CUB", 1.0), ("FCC", 0.25), ("BCC", 0.5), ("HEX", 0.8660254037844386)])
 def test_lattice_vectors_and_volume(name, vol):
     L = Lattice(name)
     assert np.allclose(L.lat @ L.rec.T, np.eye(3))                 # misc/test_bravais.cpp:274-287
@@ -21,7 +21,7 @@ def test_lattice_vectors_and_volume(name, vol):
         assert abs(Mesh(L, n).volume - vol) < 1e-13                # misc/test_bravais.cpp:432-438
 
 
-@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
+@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC", "HEX"])
 @pytest.mark.parametrize("p", [1, 2])
 def test_periodic_mesh_euler_number_and_counts(name, p):
     mesh = Mesh(Lattice(name), 2)
@@ -41,7 +41,7 @@ def test_1d_nodes():
             assert abs(w @ g ** k - 1 / (k + 1)) < 1e-13
 
 
-@pytest.mark.parametrize("name,n,p", [("CUB", 3, 1), ("FCC", 2, 2), ("BCC", 1, 2), ("CUB", 2, 3)])
+@pytest.mark.parametrize("name,n,p", [("CUB", 3, 1), ("FCC", 2, 2), ("BCC", 1, 2), ("CUB", 2, 3), ("HEX", 2, 1)])
 def test_operator_identities(name, n, p):
     mesh = Mesh(Lattice(name), n)
     rng = np.random.default_rng(0)
