@@ -227,9 +227,22 @@ def run_b200(args):
     t_apply = float(np.mean(times))
     hbm, how = peaks()
     achieved = ALG_BYTES_PER_DOF * N * nv / t_apply / 1e9
+    traffic, shares = None, {}
+    try:   # per-launch DRAM traffic of k_nd_apply from the committed ncu --set full capture (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        key = "%s_p%d_n%d" % (args.lattice.lower(), args.order, args.n_sub)
+        if key in tr and tr[key]["vectors"] == nv:
+            traffic = tr[key]["dram_bytes_per_launch"]
+        shares = json.load(open(os.path.join(ROOT, "profiles", "kernel_shares_r1.json")))
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": "k_nd_apply<%d> (y = A x, memset of y included)" % args.order,
             "achieved": achieved, "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "launch_us_mean": t_apply * 1e6, "launch_us_best": float(np.min(times)) * 1e6,
+            "traffic": traffic, "traffic_source": "profiles/ncu_nd_apply_r1.md" if traffic else None,
+            "share_of_step_ncu": next((v["share"] for k, v in shares.items() if k.startswith("k_nd_apply")), None),
+            "dominant_kernel_of_step": max(shares.items(), key=lambda kv: kv[1]["share"])[0] if shares else None,
+            "dominant_kernel_share": max((v["share"] for v in shares.values()), default=None),
+            "launch_us_mean": t_apply * 1e6, "launch_us_best": float(np.min(times)) * 1e6,
             "dofs": N, "vectors": nv, "alg_bytes_per_dof_vector": ALG_BYTES_PER_DOF}
 
     if rank != 0:

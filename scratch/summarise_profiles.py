@@ -25,6 +25,8 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("| `%s` | %d | %.1f | %.2f | %.1f %% |" % (k[:70], v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
 out.append("\ntotal %.1f us over %d launches\n" % (tot, sum(v[0] for v in agg.values())))
 open("profiles/launches_%s.md" % R, "w").write("\n".join(out))
+json.dump({k: {"launches": v[0], "total_us": v[1], "share": v[1] / tot} for k, v in agg.items()},
+          open("profiles/kernel_shares_%s.json" % R, "w"), indent=1)
 
 # ---- full captures ----
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
