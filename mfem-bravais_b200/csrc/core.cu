@@ -93,7 +93,8 @@ static void fill_tabs(const Basis1D &B, Tabs &T) {
   for (int r = 0; r < q; r++) T.om[r] = B.om[r];
 }
 
-static void class_params(const double *J, const double kappa[3], double out[kClassParDoubles]) {
+namespace bloch_b200 {
+void class_params(const double *J, const double kappa[3], double out[kClassParDoubles]) {
   double JtJ[9];
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
@@ -114,11 +115,13 @@ static void class_params(const double *J, const double kappa[3], double out[kCla
   for (int k = 0; k < 9; k++) out[12 + k] = adj[k] / det;
   out[21] = det;
 }
+}  // namespace bloch_b200
 
 // element-local diagonals of A, M1 and S0 per class, obtained by running the production kernels
 // on a probe problem (one private copy of the element per local unit vector)
 // largest eigenvalue of diag(X)^-1/2 X diag(X)^-1/2 for a Hermitian PSD local matrix (power iteration)
-static double local_scaled_lmax(int L, const D2 *X /* column k at X[k*L + l] */) {
+namespace bloch_b200 {
+double local_scaled_lmax(int L, const D2 *X /* column k at X[k*L + l] */) {
   std::vector<double> d(L);
   for (int k = 0; k < L; k++) d[k] = X[(size_t)k * L + k].x > 0 ? 1.0 / std::sqrt(X[(size_t)k * L + k].x) : 0.0;
   std::vector<double> vr(L), vi(L, 0.0), wr(L), wi(L);
@@ -149,6 +152,7 @@ static double local_scaled_lmax(int L, const D2 *X /* column k at X[k*L + l] */)
   }
   return lam;
 }
+}  // namespace bloch_b200
 
 static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vector<double> &dM,
                             std::vector<double> &dS0, std::vector<double> &dM0, double *lmax_bound,
@@ -261,6 +265,10 @@ void bloch_handle_s::setup() {
     BLOCH_CUDA(cudaStreamSynchronize(stream));
     count_launch(3);
   }
+  if ((dirty_kappa || dirty_coef) && use_mg) {
+    if (!mg) mg = mg_create(this);
+    if (mg) mg_setup(mg, this);
+  }
   dirty_coef = dirty_kappa = false;
 }
 
@@ -326,6 +334,8 @@ static bloch_handle_s *make_handle(const std::vector<std::array<double, 3>> &ver
       h->stream = h->own_stream;
     }
     h->p = order;
+    h->coarse_vert = vert;
+    h->coarse_hex = hex;
     build_mesh(vert, hex, rec, n_sub, h->mesh);
     build_dofmaps(h->mesh, order, h->maps);
     h->N = h->maps.n_nd; h->N0 = h->maps.n_h1; h->Nrt = h->maps.n_rt;
@@ -335,6 +345,7 @@ static bloch_handle_s *make_handle(const std::vector<std::array<double, 3>> &ver
     h->eps.assign(h->mesh.n_elem, 1.0);
     h->muinv.assign(h->mesh.n_elem, 1.0);
     if (const char *e = std::getenv("BLOCH_TWO_PASS")) h->two_pass = std::atoi(e);
+    if (const char *e = std::getenv("BLOCH_MG")) h->use_mg = std::atoi(e);
     if (!host_only) build_kernel_maps(h);
   } catch (...) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -506,6 +517,7 @@ int bloch_destroy(bloch_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaStream_t own = h->own_stream;
+  if (h->mg) mg_destroy(h->mg);
   delete h;
   if (own) cudaStreamDestroy(own);
   return BLOCH_OK;

@@ -14,6 +14,7 @@
 #include "bravais.hpp"
 #include "kernels.hpp"
 #include "mesh.hpp"
+#include "mg.hpp"
 
 struct bloch_lattice_s {
   bloch_b200::bravais::BravaisLattice *lat = nullptr;
@@ -66,6 +67,10 @@ struct EigProblem {
   int nbands = 0;
 };
 
+// shared host helpers (core.cu)
+void class_params(const double *J, const double kappa[3], double out[kClassParDoubles]);
+double local_scaled_lmax(int L, const double2 *X);
+
 struct SolverStats {
   int iterations = 0, converged = 0, inner_iterations = 0;
   double seconds = 0, max_residual = 0;
@@ -80,6 +85,10 @@ struct bloch_handle_s {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int p = 1;
   bloch_b200::HexMesh mesh;
+  std::vector<std::array<double, 3>> coarse_vert;   // coarse WS cell, kept for the multigrid levels
+  std::vector<std::array<int, 8>> coarse_hex;
+  bloch_b200::H1Multigrid *mg = nullptr;            // h-multigrid for the projector's S0 solves
+  int use_mg = 1;
   bloch_b200::DofMaps maps;
   bloch_b200::Basis1D basis;
   bloch_b200::Tabs tabs;
@@ -123,6 +132,11 @@ struct bloch_handle_s {
   std::vector<double> eigenvalues_s;
   bloch_b200::DevBuf<D2> d_Xs;
   bool scalar_ready = false;
+
+  struct LobpcgWork {
+    bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM;
+    bloch_b200::DevBuf<double> dlam, drn;
+  } lw;
 
   // scratch for host-pointer entry points
   bloch_b200::DevBuf<double> d_io_a, d_io_b;

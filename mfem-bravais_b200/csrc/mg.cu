@@ -1,0 +1,628 @@
+// Geometric h-multigrid for the projector's inner system  S0 phi = G^H M x,  S0 = G^H M1(eps) G
+// (H1_p Bloch Laplacian).  The reference solves it with MINRES to 1e-13 per vector per LOBPCG
+// iteration (maxwell/maxwell_bloch.cpp:2146-2152, 2280-2290) and that solve dominates its run
+// time; Jacobi-PCG needs O(n p) iterations.  The Wigner-Seitz meshes are n^3 subdivisions of a
+// few coarse hexes, so n -> n/2 -> ... gives nested H1_p spaces for free:
+//   * levels share the element classes (J_l = J_0 * n_0 / n_l); eps is averaged over children;
+//   * prolongation = element-wise tensor interpolation parent -> 8 children (1-D matrices
+//     c_j((a + l_i)/2)), restriction = its transpose with 1/multiplicity weights;
+//   * smoother = Chebyshev(degree 3) in D^-1 S0 on [lmax/4, lmax], symmetric V(1,1) cycle;
+//   * coarsest level: dense inverse computed on the host from one block apply of the level
+//     operator to the identity (a few dozen unknowns), or a long Chebyshev sweep if it is big;
+//   * outer iteration: block PCG (columns independent, scalars on the device) preconditioned by
+//     one V-cycle.  Every level operator is the same matrix-free kernel (k_h1_op mode 3).
+#include <algorithm>
+#include <deque>
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+
+#include "core.hpp"
+#include "dense.hpp"
+#include "mg.hpp"
+
+using namespace bloch_b200;
+using D2 = double2;
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned grid_for(long total) {
+  long g = (total + TPB - 1) / TPB;
+  const long cap = 148L * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+struct Transfer1D { double P[2][kMaxP + 1][kMaxP + 1]; };   // P[a][i][j] = c_j((a + l_i)/2)
+
+__device__ __forceinline__ void parent_of(int e, int n, int &parent, int &a0, int &a1, int &a2) {
+  const int n3 = n * n * n, nc = n / 2;
+  const int blk = e / n3, rem = e - blk * n3;
+  const int ix = rem % n, jy = (rem / n) % n, kz = rem / (n * n);
+  parent = blk * nc * nc * nc + ((kz / 2) * nc + jy / 2) * nc + ix / 2;
+  a0 = ix & 1; a1 = jy & 1; a2 = kz & 1;
+}
+
+// xf[fine dof][v] = interpolation of the parent's nodal polynomial (plain stores, conforming)
+template <int P>
+__global__ void k_h1_prolong(const __grid_constant__ Transfer1D T, const int32_t *__restrict__ map_f,
+                             const int32_t *__restrict__ map_c, int n_elem_f, int n_f,
+                             const D2 *__restrict__ xc, D2 *__restrict__ xf, int m) {
+  constexpr int Q = P + 1, L = Q * Q * Q;
+  const long total = (long)n_elem_f * L * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % m);
+    const long r = t / m;
+    const int i = (int)(r % L), e = (int)(r / L);
+    const int i0 = i / (Q * Q), i1 = (i / Q) % Q, i2 = i % Q;
+    int par, a0, a1, a2;
+    parent_of(e, n_f, par, a0, a1, a2);
+    const int32_t *mc = map_c + (long)par * L;
+    D2 acc = make_double2(0.0, 0.0);
+    for (int j0 = 0; j0 < Q; j0++) {
+      const double w0 = T.P[a0][i0][j0];
+      if (w0 == 0.0) continue;
+      for (int j1 = 0; j1 < Q; j1++) {
+        const double w1 = w0 * T.P[a1][i1][j1];
+        if (w1 == 0.0) continue;
+        for (int j2 = 0; j2 < Q; j2++) {
+          const double w = w1 * T.P[a2][i2][j2];
+          const D2 c = xc[(long)(__ldg(mc + (j0 * Q + j1) * Q + j2) - 1) * m + v];
+          acc.x = fma(w, c.x, acc.x); acc.y = fma(w, c.y, acc.y);
+        }
+      }
+    }
+    xf[(long)(__ldg(map_f + (long)e * L + i) - 1) * m + v] = acc;
+  }
+}
+
+// rc[coarse dof][v] += sum_i P[i][j] * rf[fine dof i][v] / multiplicity(fine dof i)
+template <int P>
+__global__ void k_h1_restrict(const __grid_constant__ Transfer1D T, const int32_t *__restrict__ map_f,
+                              const int32_t *__restrict__ map_c, int n_elem_f, int n_f,
+                              const double *__restrict__ invmult_f, const D2 *__restrict__ rf,
+                              D2 *__restrict__ rc, int m) {
+  constexpr int Q = P + 1, L = Q * Q * Q;
+  const long total = (long)n_elem_f * L * m;
+  double *rcd = reinterpret_cast<double *>(rc);
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % m);
+    const long r = t / m;
+    const int j = (int)(r % L), e = (int)(r / L);
+    const int j0 = j / (Q * Q), j1 = (j / Q) % Q, j2 = j % Q;
+    int par, a0, a1, a2;
+    parent_of(e, n_f, par, a0, a1, a2);
+    const int32_t *mf = map_f + (long)e * L;
+    D2 acc = make_double2(0.0, 0.0);
+    for (int i0 = 0; i0 < Q; i0++) {
+      const double w0 = T.P[a0][i0][j0];
+      if (w0 == 0.0) continue;
+      for (int i1 = 0; i1 < Q; i1++) {
+        const double w1 = w0 * T.P[a1][i1][j1];
+        if (w1 == 0.0) continue;
+        for (int i2 = 0; i2 < Q; i2++) {
+          const long g = __ldg(mf + (i0 * Q + i1) * Q + i2) - 1;
+          const double w = w1 * T.P[a2][i2][j2] * invmult_f[g];
+          const D2 c = rf[g * m + v];
+          acc.x = fma(w, c.x, acc.x); acc.y = fma(w, c.y, acc.y);
+        }
+      }
+    }
+    const long gc = __ldg(map_c + (long)par * L + j) - 1;
+    atomicAdd(rcd + 2 * (gc * m + v), acc.x);
+    atomicAdd(rcd + 2 * (gc * m + v) + 1, acc.y);
+  }
+}
+
+__global__ void k_count(const int32_t *__restrict__ map, long total, double *__restrict__ cnt) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x)
+    atomicAdd(cnt + (map[t] - 1), 1.0);
+}
+__global__ void k_invert(double *x, long n) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+    x[t] = x[t] > 0 ? 1.0 / x[t] : 0.0;
+}
+// x[r][v] = sum_c inv[r][c] b[c][v]   (small dense coarse solve)
+__global__ void k_dense_apply(const D2 *__restrict__ inv, const D2 *__restrict__ b, D2 *__restrict__ x, int n, int m) {
+  const int total = n * m;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int r = t / m, v = t - r * m;
+    D2 acc = make_double2(0.0, 0.0);
+    for (int c = 0; c < n; c++) {
+      const D2 a = inv[(long)r * n + c], y = b[(long)c * m + v];
+      acc.x = fma(a.x, y.x, acc.x); acc.x = fma(-a.y, y.y, acc.x);
+      acc.y = fma(a.x, y.y, acc.y); acc.y = fma(a.y, y.x, acc.y);
+    }
+    x[t] = acc;
+  }
+}
+// r = b - q
+__global__ void k_resid(const D2 *__restrict__ b, const D2 *__restrict__ q, D2 *__restrict__ r, long total) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x)
+    r[t] = make_double2(b[t].x - q[t].x, b[t].y - q[t].y);
+}
+// x += y
+__global__ void k_add(D2 *__restrict__ x, const D2 *__restrict__ y, long total) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    D2 a = x[t]; const D2 b = y[t];
+    a.x += b.x; a.y += b.y;
+    x[t] = a;
+  }
+}
+// Chebyshev: d = c0 jac r ; x (+)= d
+__global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ d,
+                             D2 *__restrict__ x, double c0, long n, int m, int accumulate) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[t / m];
+    const D2 v = r[t];
+    const D2 o = make_double2(s * v.x, s * v.y);
+    d[t] = o;
+    if (accumulate) { D2 a = x[t]; a.x += o.x; a.y += o.y; x[t] = a; } else x[t] = o;
+  }
+}
+// r -= q ; d = a d + b jac r ; x += d
+__global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict__ q, D2 *__restrict__ r,
+                            D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = b * jac[t / m];
+    const D2 qq = q[t];
+    D2 rr = r[t];
+    rr.x -= qq.x; rr.y -= qq.y;
+    r[t] = rr;
+    D2 dd = d[t];
+    dd.x = a * dd.x + s * rr.x; dd.y = a * dd.y + s * rr.y;
+    d[t] = dd;
+    D2 xx = x[t];
+    xx.x += dd.x; xx.y += dd.y;
+    x[t] = xx;
+  }
+}
+__global__ void k_jacobi(const double *d, double *jac, long n) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+    jac[t] = d[t] > 0 ? 1.0 / d[t] : 0.0;
+}
+// column means removed (Gamma point: S0 singular on constants)
+__global__ void k_col_sum(const D2 *__restrict__ X, long n, int m, double *__restrict__ sums) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const D2 v = X[t];
+    atomicAdd(sums + 2 * (t % m), v.x);
+    atomicAdd(sums + 2 * (t % m) + 1, v.y);
+  }
+}
+__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums) {
+  const long total = n * m;
+  const double inv = 1.0 / (double)n;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    D2 v = X[t];
+    v.x -= sums[2 * (t % m)] * inv; v.y -= sums[2 * (t % m) + 1] * inv;
+    X[t] = v;
+  }
+}
+
+template <int P>
+void prolong_t(const Transfer1D &T, const int32_t *mf, const int32_t *mc, int nef, int nf, const D2 *xc, D2 *xf, int m, cudaStream_t s) {
+  constexpr int L = (P + 1) * (P + 1) * (P + 1);
+  k_h1_prolong<P><<<grid_for((long)nef * L * m), TPB, 0, s>>>(T, mf, mc, nef, nf, xc, xf, m);
+}
+template <int P>
+void restrict_t(const Transfer1D &T, const int32_t *mf, const int32_t *mc, int nef, int nf, const double *w, const D2 *rf, D2 *rc, int m, cudaStream_t s) {
+  constexpr int L = (P + 1) * (P + 1) * (P + 1);
+  k_h1_restrict<P><<<grid_for((long)nef * L * m), TPB, 0, s>>>(T, mf, mc, nef, nf, w, rf, rc, m);
+}
+
+double env_double(const char *name, double dflt) {
+  const char *s = std::getenv(name);
+  return s ? std::atof(s) : dflt;
+}
+
+}  // namespace
+
+namespace bloch_b200 {
+
+struct H1Level {
+  int n = 0;
+  long N0 = 0;
+  HexMesh mesh;                       // levels >= 1 (level 0 lives in the handle)
+  DofMaps maps;
+  DevBuf<int32_t> map_h1;
+  DevBuf<int> cls;
+  DevBuf<double> eps, cpar, diag, jac, invmult;
+  std::vector<double> eps_h;
+  ElemData E{};
+  double lmax = 0;
+  DevBuf<D2> x, b, r, d, q;           // V-cycle work vectors, N0 x m
+  DevBuf<D2> inv;                     // dense inverse on the coarsest level
+  bool dense = false;
+};
+
+struct H1Multigrid {
+  std::deque<H1Level> lev;
+  Transfer1D T;
+  int m_alloc = 0;
+  DevBuf<D2> z, pvec, qvec;           // PCG vectors on the fine level
+  DevBuf<double> scal;                // rz | pq | rz_new | rr | alpha | beta  (m each) + 2m sums
+  // CUDA graphs of the two halves of one PCG iteration (re-captured after every mg_setup: the
+  // Chebyshev coefficients are kernel arguments captured by value)
+  cudaGraphExec_t gA = nullptr, gB = nullptr;
+  const void *g_rhs = nullptr, *g_phi = nullptr;
+  int g_m = 0;
+  void drop_graphs() {
+    if (gA) cudaGraphExecDestroy(gA);
+    if (gB) cudaGraphExecDestroy(gB);
+    gA = gB = nullptr;
+  }
+  ~H1Multigrid() { drop_graphs(); }
+};
+
+static void alloc_work(H1Multigrid *mg, int m) {
+  if (m <= mg->m_alloc) return;
+  for (auto &L : mg->lev) {
+    const size_t sz = (size_t)L.N0 * m;
+    L.x.alloc(sz); L.b.alloc(sz); L.r.alloc(sz); L.d.alloc(sz); L.q.alloc(sz);
+  }
+  const size_t sz0 = (size_t)mg->lev[0].N0 * m;
+  mg->z.alloc(sz0); mg->pvec.alloc(sz0); mg->qvec.alloc(sz0);
+  mg->scal.alloc(8 * (size_t)m);
+  mg->m_alloc = m;
+}
+
+H1Multigrid *mg_create(bloch_handle_s *h) {
+  const int p = h->p, Q = p + 1;
+  if (h->mesh.n_sub % 2 != 0 || h->mesh.n_sub < 2) return nullptr;   // no coarser nested mesh
+  H1Multigrid *mg = new H1Multigrid();
+  cudaStream_t s = h->stream;
+  // 1-D transfer tables
+  for (int a = 0; a < 2; a++)
+    for (int i = 0; i < Q; i++) {
+      std::vector<double> v, dv;
+      detail::lagrange(h->basis.l, 0.5 * (a + h->basis.l[i]), v, dv);
+      for (int j = 0; j < Q; j++) mg->T.P[a][i][j] = std::fabs(v[j]) < 1e-15 ? 0.0 : v[j];
+    }
+  // level 0 = the handle's own mesh
+  int n = h->mesh.n_sub;
+  mg->lev.emplace_back();
+  {
+    H1Level &L = mg->lev.back();
+    L.n = n; L.N0 = h->N0;
+  }
+  while (n % 2 == 0) {
+    n /= 2;
+    mg->lev.emplace_back();
+    H1Level &L = mg->lev.back();
+    L.n = n;
+    build_mesh(h->coarse_vert, h->coarse_hex, h->mesh.rec.data(), n, L.mesh);
+    build_dofmaps(L.mesh, p, L.maps);
+    L.N0 = L.maps.n_h1;
+    const int ne = L.mesh.n_elem, LH = L.maps.l_h1;
+    std::vector<int32_t> kh1((size_t)ne * LH);
+    for (int e = 0; e < ne; e++)
+      for (int i0 = 0; i0 < Q; i0++)
+        for (int i1 = 0; i1 < Q; i1++)
+          for (int i2 = 0; i2 < Q; i2++)
+            kh1[(size_t)e * LH + (i0 * Q + i1) * Q + i2] = L.maps.h1[(size_t)e * LH + i0 + Q * (i1 + Q * i2)];
+    L.map_h1.upload(kh1, s);
+    L.cls.upload(L.mesh.cls, s);
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    if (L.N0 <= 8) break;
+  }
+  // multiplicity weights of every level that restricts (all but the coarsest)
+  for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
+    H1Level &L = mg->lev[l];
+    const int32_t *map = l == 0 ? h->d_map_h1.p : L.map_h1.p;
+    const long ne = l == 0 ? h->mesh.n_elem : L.mesh.n_elem;
+    L.invmult.alloc(L.N0);
+    BLOCH_CUDA(cudaMemsetAsync(L.invmult.p, 0, sizeof(double) * L.N0, s));
+    k_count<<<grid_for(ne * h->L_h1), TPB, 0, s>>>(map, ne * h->L_h1, L.invmult.p);
+    k_invert<<<grid_for(L.N0), TPB, 0, s>>>(L.invmult.p, L.N0);
+  }
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return mg;
+}
+
+void mg_destroy(H1Multigrid *mg) { delete mg; }
+
+// element-local diagonal of S0 per class on one level (probe launch of the production kernel)
+static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound);
+
+void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
+  cudaStream_t s = h->stream;
+  mg->drop_graphs();
+  const int p = h->p;
+  const int nl = (int)mg->lev.size();
+  for (int l = 0; l < nl; l++) {
+    H1Level &L = mg->lev[l];
+    const HexMesh &mesh = l == 0 ? h->mesh : L.mesh;
+    // coefficient: level 0 = the user's eps, coarser = mean over the 8 children
+    if (l == 0) {
+      L.eps_h = h->eps;
+    } else {
+      const H1Level &F = mg->lev[l - 1];
+      const int nf = F.n, nc = L.n, n3 = nf * nf * nf;
+      L.eps_h.assign(mesh.n_elem, 0.0);
+      for (int e = 0; e < (int)F.eps_h.size(); e++) {
+        const int blk = e / n3, rem = e - blk * n3;
+        const int ix = rem % nf, jy = (rem / nf) % nf, kz = rem / (nf * nf);
+        L.eps_h[blk * nc * nc * nc + ((kz / 2) * nc + jy / 2) * nc + ix / 2] += 0.125 * F.eps_h[e];
+      }
+      L.eps.upload(L.eps_h, s);
+    }
+    // kappa-dependent class tables with this level's Jacobians
+    std::vector<double> cp((size_t)mesh.n_class * kClassParDoubles);
+    for (int c = 0; c < mesh.n_class; c++) class_params(&mesh.J[9 * c], h->kappa, &cp[(size_t)c * kClassParDoubles]);
+    L.cpar.upload(cp, s);
+    ElemData &E = L.E;
+    E = h->E;
+    E.n_elem = mesh.n_elem;
+    E.n_class = mesh.n_class;
+    E.cpar = L.cpar.p;
+    if (l > 0) {
+      E.cls = L.cls.p;
+      E.eps = L.eps.p;
+      E.muinv = L.eps.p;
+      E.map_h1 = L.map_h1.p;
+      E.map_nd = nullptr;
+      E.map_rt = nullptr;
+    }
+    // Jacobi diagonal and the rigorous local bound of lambda_max(D^-1 S0)
+    std::vector<double> dloc;
+    double bound = 0.0;
+    probe_level(h, E, dloc, &bound);
+    L.lmax = 1.05 * bound;
+    DevBuf<double> dl;
+    dl.upload(dloc, s);
+    L.diag.alloc(L.N0); L.jac.alloc(L.N0);
+    BLOCH_CUDA(cudaMemsetAsync(L.diag.p, 0, sizeof(double) * L.N0, s));
+    BLOCH_CUDA(launch_scatter_diag(E.map_h1, h->L_h1, E.cls, E.eps, dl.p, E.n_elem, L.diag.p, s));
+    k_jacobi<<<grid_for(L.N0), TPB, 0, s>>>(L.diag.p, L.jac.p, L.N0);
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+  }
+  // coarsest level: dense inverse from one block apply to the identity
+  H1Level &C = mg->lev[nl - 1];
+  C.dense = C.N0 <= 512;
+  if (C.dense) {
+    const int n = (int)C.N0;
+    std::vector<D2> I((size_t)n * n, make_double2(0.0, 0.0));
+    for (int i = 0; i < n; i++) I[(size_t)i * n + i].x = 1.0;
+    DevBuf<D2> dI, dA;
+    dI.upload(I, s);
+    dA.alloc((size_t)n * n);
+    BLOCH_CUDA(cudaMemsetAsync(dA.p, 0, sizeof(D2) * n * n, s));
+    BLOCH_CUDA(launch_h1_op(p, 3, h->tabs, C.E, dI.p, n, dA.p, n, n, s, 1.0, 0.0));
+    std::vector<D2> A((size_t)n * n);
+    BLOCH_CUDA(cudaMemcpyAsync(A.data(), dA.p, sizeof(D2) * n * n, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    dense::Mat Am((size_t)n * n);
+    double tr = 0;
+    for (int i = 0; i < n; i++) tr += A[(size_t)i * n + i].x;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const D2 a = A[(size_t)i * n + j], at = A[(size_t)j * n + i];
+        Am[(size_t)i * n + j] = 0.5 * dense::cplx(a.x + at.x, a.y - at.y);
+      }
+    if (h->beta == 0.0)   // singular on constants: lift that single mode
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += tr / ((double)n * n);
+    dense::Mat Lc = Am;
+    if (!dense::cholesky(n, Lc, 1e-14)) {
+      C.dense = false;
+    } else {
+      // inverse = L^-H L^-1: solve for the identity
+      dense::Mat X((size_t)n * n, dense::cplx(0));
+      for (int c = 0; c < n; c++) {
+        std::vector<dense::cplx> y(n, dense::cplx(0));
+        for (int i = 0; i < n; i++) {           // L y = e_c
+          dense::cplx sacc = (i == c) ? 1.0 : 0.0;
+          for (int k = 0; k < i; k++) sacc -= Lc[(size_t)i * n + k] * y[k];
+          y[i] = sacc / Lc[(size_t)i * n + i].real();
+        }
+        for (int i = n - 1; i >= 0; i--) {      // L^H x = y
+          dense::cplx sacc = y[i];
+          for (int k = i + 1; k < n; k++) sacc -= std::conj(Lc[(size_t)k * n + i]) * X[(size_t)k * n + c];
+          X[(size_t)i * n + c] = sacc / Lc[(size_t)i * n + i].real();
+        }
+      }
+      std::vector<D2> inv((size_t)n * n);
+      for (size_t i = 0; i < inv.size(); i++) inv[i] = make_double2(X[i].real(), X[i].imag());
+      C.inv.upload(inv, s);
+      BLOCH_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+}
+
+static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound) {
+  const int nc = Elev.n_class, L = h->L_h1;
+  cudaStream_t s = h->stream;
+  const int ne = nc * L;
+  std::vector<int32_t> map((size_t)ne * L);
+  std::vector<int> cls(ne);
+  std::vector<double> one(ne, 1.0);
+  std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
+  for (int c = 0; c < nc; c++)
+    for (int k = 0; k < L; k++) {
+      const int e = c * L + k;
+      cls[e] = c;
+      for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
+      x[(size_t)e * L + k].x = 1.0;
+    }
+  DevBuf<int32_t> dmap; DevBuf<int> dcls; DevBuf<double> done; DevBuf<D2> dx, dy;
+  dmap.upload(map, s); dcls.upload(cls, s); done.upload(one, s); dx.upload(x, s);
+  dy.alloc(x.size());
+  ElemData E = Elev;
+  E.n_elem = ne; E.cls = dcls.p; E.eps = done.p; E.muinv = done.p; E.map_h1 = dmap.p;
+  BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 1.0, 0.0));
+  std::vector<D2> y(x.size());
+  BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * y.size(), cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  dloc.resize((size_t)nc * L);
+  for (int c = 0; c < nc; c++) {
+    for (int k = 0; k < L; k++) dloc[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
+    if (bound) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
+  }
+}
+
+// ---- V-cycle pieces --------------------------------------------------------------------------
+static void level_apply(bloch_handle_s *h, H1Level &L, const D2 *x, D2 *y, int m) {
+  BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * L.N0 * m, h->stream));
+  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, L.E, x, m, y, m, m, h->stream, 1.0, 0.0));
+  h->count_launch();
+}
+// x (+)= Cheb_deg(D^-1 S0) applied to the residual held in L.r (destroyed)
+static void chebyshev(bloch_handle_s *h, H1Level &L, D2 *x, int m, int degree, double ratio, bool accumulate) {
+  cudaStream_t s = h->stream;
+  const double lmax = L.lmax, lmin = lmax / ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+  const unsigned g = grid_for(L.N0 * m);
+  k_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m, accumulate ? 1 : 0);
+  h->count_launch();
+  double rho = 1.0 / sigma1;
+  for (int k = 1; k < degree; k++) {
+    level_apply(h, L, L.d.p, L.q.p, m);
+    const double rho_n = 1.0 / (2.0 * sigma1 - rho);
+    k_cheb_step<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, rho_n * rho, 2.0 * rho_n / delta, L.N0, m);
+    h->count_launch();
+    rho = rho_n;
+  }
+}
+
+static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, double ratio) {
+  // input: lev[l].b ; output: lev[l].x
+  cudaStream_t s = h->stream;
+  H1Level &L = mg->lev[l];
+  const int nl = (int)mg->lev.size();
+  const long tot = L.N0 * m;
+  if (l == nl - 1) {
+    if (L.dense) {
+      k_dense_apply<<<grid_for(tot), TPB, 0, s>>>(L.inv.p, L.b.p, L.x.p, (int)L.N0, m);
+      h->count_launch();
+    } else {
+      BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+      chebyshev(h, L, L.x.p, m, 40, 2000.0, false);
+    }
+    return;
+  }
+  H1Level &C = mg->lev[l + 1];
+  const int32_t *map_f = L.E.map_h1, *map_c = C.E.map_h1;
+  const int nef = L.E.n_elem;
+  // pre-smoothing from a zero initial guess
+  BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+  chebyshev(h, L, L.x.p, m, deg, ratio, false);
+  // residual, restriction
+  level_apply(h, L, L.x.p, L.q.p, m);
+  k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
+  BLOCH_CUDA(cudaMemsetAsync(C.b.p, 0, sizeof(D2) * C.N0 * m, s));
+  switch (h->p) {
+    case 1: restrict_t<1>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    case 2: restrict_t<2>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    case 3: restrict_t<3>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    default: restrict_t<4>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+  }
+  h->count_launch(2);
+  vcycle(mg, h, l + 1, m, deg, ratio);
+  // prolongation + correction
+  switch (h->p) {
+    case 1: prolong_t<1>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+    case 2: prolong_t<2>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+    case 3: prolong_t<3>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+    default: prolong_t<4>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+  }
+  k_add<<<grid_for(tot), TPB, 0, s>>>(L.x.p, L.d.p, tot);
+  // post-smoothing
+  level_apply(h, L, L.x.p, L.q.p, m);
+  k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
+  h->count_launch(3);
+  chebyshev(h, L, L.x.p, m, deg, ratio, true);
+}
+
+// block PCG on the fine level, one V-cycle as preconditioner; rhs is overwritten by the residual
+int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+  cudaStream_t s = h->stream;
+  alloc_work(mg, m);
+  H1Level &F = mg->lev[0];
+  const long N0 = F.N0, tot = N0 * m;
+  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 3);
+  const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 4.0);
+  double *rz = mg->scal.p, *pq = rz + m, *rzn = pq + m, *rr = rzn + m, *alpha = rr + m, *beta = alpha + m;
+  double *sums = beta + m;
+  auto remove_mean = [&](D2 *v) {
+    if (h->beta != 0.0) return;
+    BLOCH_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * m, s));
+    k_col_sum<<<grid_for(tot), TPB, 0, s>>>(v, N0, m, sums);
+    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(v, N0, m, sums);
+    h->count_launch(2);
+  };
+  auto precond = [&](const D2 *r, D2 *z) {
+    BLOCH_CUDA(cudaMemcpyAsync(F.b.p, r, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+    vcycle(mg, h, 0, m, deg, ratio);
+    BLOCH_CUDA(cudaMemcpyAsync(z, F.x.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+  };
+  remove_mean(rhs);
+  BLOCH_CUDA(cudaMemsetAsync(phi, 0, sizeof(D2) * tot, s));
+  std::vector<double> rr0(m), rrh(m);
+  BLOCH_CUDA(launch_col_dot(rhs, rhs, N0, m, rr, s));
+  BLOCH_CUDA(cudaMemcpyAsync(rr0.data(), rr, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  double mx = 0;
+  for (double v : rr0) mx = std::max(mx, v);
+  if (mx == 0.0) return 0;
+  precond(rhs, mg->z.p);
+  BLOCH_CUDA(cudaMemcpyAsync(mg->pvec.p, mg->z.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+  BLOCH_CUDA(launch_col_dot(rhs, mg->z.p, N0, m, rz, s));
+  auto half_a = [&]() {      // q = S0 p ; alpha ; phi += alpha p ; r -= alpha q ; rr = <r,r>
+    level_apply(h, F, mg->pvec.p, mg->qvec.p, m);
+    BLOCH_CUDA(launch_col_dot(mg->pvec.p, mg->qvec.p, N0, m, pq, s));
+    BLOCH_CUDA(launch_scalar_div(rz, pq, alpha, m, s));
+    BLOCH_CUDA(launch_col_axpy(alpha, 1.0, mg->pvec.p, phi, N0, m, s));
+    BLOCH_CUDA(launch_col_axpy(alpha, -1.0, mg->qvec.p, rhs, N0, m, s));
+    BLOCH_CUDA(launch_col_dot(rhs, rhs, N0, m, rr, s));
+    h->count_launch(5);
+  };
+  auto half_b = [&]() {      // z = V(r) ; beta ; p = z + beta p
+    precond(rhs, mg->z.p);
+    BLOCH_CUDA(launch_col_dot(rhs, mg->z.p, N0, m, rzn, s));
+    BLOCH_CUDA(launch_scalar_div(rzn, rz, beta, m, s));
+    BLOCH_CUDA(launch_col_xpby(mg->z.p, beta, mg->pvec.p, N0, m, s));
+    BLOCH_CUDA(cudaMemcpyAsync(rz, rzn, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
+    h->count_launch(3);
+  };
+  static const bool use_graph = env_double("BLOCH_MG_GRAPH", 1.0) != 0.0;
+  auto capture = [&](cudaGraphExec_t *exec, const std::function<void()> &body) -> bool {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool ok = true;
+    try { body(); } catch (...) { ok = false; }
+    if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+    if (ok) ok = cudaGraphInstantiate(exec, graph, 0) == cudaSuccess;
+    cudaGraphDestroy(graph);
+    if (!ok) { cudaGetLastError(); *exec = nullptr; }
+    return ok;
+  };
+  int it = 0;
+  for (it = 1; it <= max_it; it++) {
+    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m;
+    if (use_graph && !graphs_ok && it == 2) {
+      // iteration 1 ran eagerly (kernel attributes set, buffers allocated): capture now
+      mg->drop_graphs();
+      if (capture(&mg->gA, half_a) && capture(&mg->gB, half_b)) {
+        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m;
+        graphs_ok = true;
+      } else {
+        mg->drop_graphs();
+      }
+    }
+    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); else half_a();
+    BLOCH_CUDA(cudaMemcpyAsync(rrh.data(), rr, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    bool done = true;
+    for (int j = 0; j < m; j++)
+      if (rrh[j] > rel_tol * rel_tol * rr0[j]) done = false;
+    if (done) break;
+    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); else half_b();
+  }
+  return it > max_it ? max_it : it;
+}
+
+}  // namespace bloch_b200

@@ -1,0 +1,16 @@
+// Geometric h-multigrid preconditioned block PCG for S0 phi = rhs (see mg.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+struct bloch_handle_s;
+
+namespace bloch_b200 {
+struct H1Multigrid;
+// builds the nested level hierarchy (topology, transfer tables); nullptr if n_sub is odd
+H1Multigrid *mg_create(bloch_handle_s *h);
+void mg_destroy(H1Multigrid *mg);
+// per (kappa, coefficients): class tables, restricted coefficients, Jacobi diagonals, coarse inverse
+void mg_setup(H1Multigrid *mg, bloch_handle_s *h);
+// rhs (N0 x m contiguous) is overwritten by the final residual; returns the PCG iteration count
+int mg_solve(H1Multigrid *mg, bloch_handle_s *h, double2 *rhs, double2 *phi, int m, double rel_tol, int max_it);
+}  // namespace bloch_b200

@@ -224,9 +224,15 @@ static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_t
     h->count_launch(2);
   }
   if (dbg) { int magic = 12345; BLOCH_CUDA(cudaMemcpyAsync(d_info + 2, &magic, sizeof(int), cudaMemcpyHostToDevice, s)); }
-  // the whole block PCG in one cooperative launch
-  BLOCH_CUDA(launch_proj_cg(h->p, h->tabs, h->E, h->d_jac0.p, w.phi.p, w.rhs.p, w.z.p, w.p.p, w.q.p,
-                            w.scal.p, m, N0, max_it, rel_tol, d_info, s));
+  int mg_its = -1;
+  if (h->mg && h->use_mg) {
+    // V-cycle preconditioned block PCG (mesh-independent iteration count)
+    mg_its = mg_solve(h->mg, h, w.rhs.p, w.phi.p, m, rel_tol, 200);
+  } else {
+    // Jacobi-PCG, the whole block solve in one cooperative launch
+    BLOCH_CUDA(launch_proj_cg(h->p, h->tabs, h->E, h->d_jac0.p, w.phi.p, w.rhs.p, w.z.p, w.p.p, w.q.p,
+                              w.scal.p, m, N0, max_it, rel_tol, d_info, s));
+  }
   // x -= G phi
   BLOCH_CUDA(launch_h1_op(h->p, 1, h->tabs, h->E, w.phi.p, m, w.g.p, m, m, s));
   k_sub_strided<<<grid_for(N * m), TPB, 0, s>>>(x, ldx, w.g.p, N, m);
@@ -234,6 +240,7 @@ static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_t
   int info[2] = {0, 0};
   BLOCH_CUDA(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
+  if (mg_its >= 0) info[0] = mg_its;
   h->stats.inner_iterations += info[0];
   if (iters) *iters = info[0];
 }
@@ -332,9 +339,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   if (prob.constrained) k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
   count_launch(2);
 
-  DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb;
-  DevBuf<D2> dC, dGA, dGM;
-  DevBuf<double> dlam, drn;
+  // workspace lives in the handle and only grows: cudaMalloc/cudaFree per solve cost random
+  // 0.5-1.5 s stalls on the shared boxes (measured)
+  DevBuf<D2> &S = lw.S, &AS = lw.AS, &MS = lw.MS, &R = lw.R, &Wc = lw.Wc, &Dd = lw.Dd, &Tq = lw.Tq, &Qb = lw.Qb;
+  DevBuf<D2> &dC = lw.dC, &dGA = lw.dGA, &dGM = lw.dGM;
+  DevBuf<double> &dlam = lw.dlam, &drn = lw.drn;
   S.alloc((size_t)Nl * ld); AS.alloc((size_t)Nl * ld); MS.alloc((size_t)Nl * ld);
   R.alloc((size_t)Nl * mb); Wc.alloc((size_t)Nl * mb); Dd.alloc((size_t)Nl * mb);
   Tq.alloc((size_t)Nl * mb); Qb.alloc((size_t)Nl * mb);
