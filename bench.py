@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--bands", type=int, default=10)
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--pts-per-segment", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "1")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "4")),
                     help="concurrent k-point solves per GPU (independent handles on separate streams)")
     ap.add_argument("--apply-vectors", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -163,7 +163,10 @@ def run_b200(args):
         if T == 1:
             solve_range(eqs[0], idxs, out, e2e)
         else:
-            th = [threading.Thread(target=solve_range, args=(eqs[t], idxs[t::T], out, e2e)) for t in range(T)]
+            # contiguous chunks per stream: neighbouring k-points warm-start each other
+            bounds = [m.shard_kpoints(len(idxs), T, t) for t in range(T)]
+            th = [threading.Thread(target=solve_range, args=(eqs[t], idxs[lo:hi], out, e2e))
+                  for t, (lo, hi) in enumerate(bounds)]
             [t.start() for t in th]
             [t.join() for t in th]
         return out

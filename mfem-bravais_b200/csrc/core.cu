@@ -598,7 +598,7 @@ int bloch_set_kappa(bloch_handle h, const double kappa[3]) {
 }
 int bloch_set_num_bands(bloch_handle h, int n) {
   API_BEGIN
-  REQUIRE(h && n >= 1 && n <= 64, "number of bands must be in [1,64]");
+  REQUIRE(h && n >= 1 && n <= 20, "number of bands must be in [1,20]");
   if (n != h->nbands) h->have_vectors = 0;
   h->nbands = n;
   return BLOCH_OK;
@@ -760,7 +760,7 @@ int bloch_scalar_set_coefs(bloch_handle h, const double *stiffness_k, const doub
 }
 int bloch_scalar_set_num_modes(bloch_handle h, int n) {
   API_BEGIN
-  REQUIRE(h && n >= 1 && n <= 28, "number of modes must be in [1,28]");
+  REQUIRE(h && n >= 1 && n <= 20, "number of modes must be in [1,20]");
   if (n != h->nbands_s) h->have_vectors_s = 0;
   h->nbands_s = n;
   return BLOCH_OK;

@@ -675,6 +675,7 @@ __global__ void k_unpack(const double2 *__restrict__ blk, double *__restrict__ r
 // Gram: each CTA reduces a row chunk into a register tile, then atomically adds into C.
 // thread (ti, tj) owns C entries (i, j) with i = ti + k*TI... simple generic version.
 constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_ACC = 16;     // outputs per thread: ma*mb <= 4096, i.e. up to 64 basis columns
 constexpr int GRAM_ROWS = 16;   // rows staged per iteration (16*(ma+mb)*16 B <= 48 KB for ma+mb <= 192)
 __global__ void k_gram(const double2 *__restrict__ A, int ma, int lda, const double2 *__restrict__ B, int mb,
                        int ldb, long n, double2 *__restrict__ C, long rows_per_cta) {
@@ -684,17 +685,17 @@ __global__ void k_gram(const double2 *__restrict__ A, int ma, int lda, const dou
   const long r0 = blockIdx.x * rows_per_cta;
   const long r1 = min(n, r0 + rows_per_cta);
   const int nout = ma * mb;
-  // each thread accumulates outputs t, t+256, ... (at most 8 -> ma*mb <= 2048)
-  double2 acc[8];
+  // each thread accumulates outputs t, t+256, ... (at most GRAM_ACC -> ma*mb <= 256*GRAM_ACC)
+  double2 acc[GRAM_ACC];
 #pragma unroll
-  for (int k = 0; k < 8; k++) acc[k] = make_double2(0.0, 0.0);
+  for (int k = 0; k < GRAM_ACC; k++) acc[k] = make_double2(0.0, 0.0);
   for (long r = r0; r < r1; r += GRAM_ROWS) {
     const int nr = (int)min((long)GRAM_ROWS, r1 - r);
     for (int t = threadIdx.x; t < nr * ma; t += GRAM_THREADS) sA[t] = A[(r + t / ma) * lda + t % ma];
     for (int t = threadIdx.x; t < nr * mb; t += GRAM_THREADS) sB[t] = B[(r + t / mb) * ldb + t % mb];
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < GRAM_ACC; k++) {
       const int o = threadIdx.x + k * GRAM_THREADS;
       if (o < nout) {
         const int i = o / mb, j = o - i * mb;
@@ -711,7 +712,7 @@ __global__ void k_gram(const double2 *__restrict__ A, int ma, int lda, const dou
   }
   double *Cd = reinterpret_cast<double *>(C);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
+  for (int k = 0; k < GRAM_ACC; k++) {
     const int o = threadIdx.x + k * GRAM_THREADS;
     if (o < nout) {
       atomicAdd(Cd + 2 * o, acc[k].x);
@@ -863,7 +864,7 @@ cudaError_t launch_unpack(const double2 *blk, double *reim, long n, int nvec, cu
 }
 cudaError_t launch_gram(const double2 *A, int ma, int lda, const double2 *B, int mb, int ldb, long n,
                         double2 *C, cudaStream_t s) {
-  if (ma * mb > 8 * GRAM_THREADS) return cudaErrorInvalidValue;
+  if (ma * mb > GRAM_ACC * GRAM_THREADS) return cudaErrorInvalidValue;
   cudaError_t err = cudaMemsetAsync(C, 0, sizeof(double2) * ma * mb, s);
   if (err != cudaSuccess) return err;
   long ctas = 148 * 2;

@@ -543,8 +543,8 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
   alloc_work(mg, m);
   H1Level &F = mg->lev[0];
   const long N0 = F.N0, tot = N0 * m;
-  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 3);
-  const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 4.0);
+  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
   double *rz = mg->scal.p, *pq = rz + m, *rzn = pq + m, *rr = rzn + m, *alpha = rr + m, *beta = alpha + m;
   double *sums = beta + m;
   auto remove_mean = [&](D2 *v) {

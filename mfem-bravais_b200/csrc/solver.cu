@@ -307,8 +307,8 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   bloch_b200::DevBuf<D2> &d_X = *prob.X;
   std::vector<double> &eigenvalues = *prob.evals;
   const double lmax_local = prob.lmax_local;
-  int mb = nb + std::max(4, nb / 4);
-  if (mb > 32) mb = 32;
+  int mb = nb + std::max((int)env_double("BLOCH_GUARD", 6.0), nb / 4);
+  if (mb > 21) mb = 21;      // 3 mb <= 64 basis columns (Gram kernel), lanes of k_rr_update
   if (3L * mb > N) mb = (int)(N / 3);
   if (nb > mb) throw std::invalid_argument("problem too small for the requested number of bands");
   if (block != mb) { have_vectors = 0; block = mb; }
@@ -325,10 +325,10 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
 
   // ---- preconditioner data: sigma, Jacobi, lambda_max estimate ----
   const double vol23 = std::cbrt(mesh.volume) * std::cbrt(mesh.volume);
-  sigma = env_double("BLOCH_SIGMA_SCALE", 1.0) / vol23 + beta * beta;
+  sigma = env_double("BLOCH_SIGMA_SCALE", 1.0) / vol23 + env_double("BLOCH_SIGMA_BETA", 0.0) * beta * beta;
   cheb_degree = (int)env_double("BLOCH_CHEB_DEGREE", 24);
   const double cheb_ratio = env_double("BLOCH_CHEB_RATIO", 300.0);
-  const double proj_tol = std::min(env_double("BLOCH_PROJ_TOL", 1e-9), 1e-3 * tol);
+  const double proj_tol = env_double("BLOCH_PROJ_TOL_FACTOR", 1e-2) * tol;
   const bool warm = env_double("BLOCH_WARM_START", 1.0) != 0.0;
   const int refresh_every = (int)env_double("BLOCH_REFRESH_EVERY", 1.0);
   const double proj_adapt = env_double("BLOCH_PROJ_ADAPT", 0.0);
