@@ -161,24 +161,32 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
   cudaStream_t s = h->stream;
   auto run = [&](int L, bool h1space, std::vector<double> *outA, std::vector<double> *outM) {
     const int ne = nc * L;
-    std::vector<int32_t> map((size_t)ne * L);
-    std::vector<int> cls(ne);
-    std::vector<double> one(ne, 1.0);
-    std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
-    for (int c = 0; c < nc; c++)
-      for (int k = 0; k < L; k++) {
-        const int e = c * L + k;
-        cls[e] = c;
-        for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
-        x[(size_t)e * L + k].x = 1.0;
-      }
-    DevBuf<int32_t> dmap; DevBuf<int> dcls; DevBuf<double> done; DevBuf<D2> dx, dy;
-    dmap.upload(map, s); dcls.upload(cls, s); done.upload(one, s); dx.upload(x, s);
-    dy.alloc(x.size());
+    bloch_handle_s::ProbeWork &pw = h1space ? h->probe_h1 : h->probe_nd;
+    if (!pw.built) {
+      std::vector<int32_t> map((size_t)ne * L);
+      std::vector<int> cls(ne);
+      std::vector<double> one(ne, 1.0);
+      std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
+      for (int c = 0; c < nc; c++)
+        for (int k = 0; k < L; k++) {
+          const int e = c * L + k;
+          cls[e] = c;
+          for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
+          x[(size_t)e * L + k].x = 1.0;
+        }
+      pw.map.upload(map, s); pw.cls.upload(cls, s); pw.one.upload(one, s); pw.x.upload(x, s);
+      pw.y.alloc(x.size());
+      pw.hy.resize(x.size());
+      BLOCH_CUDA(cudaStreamSynchronize(s));
+      pw.built = true;
+    }
+    DevBuf<int32_t> &dmap = pw.map; DevBuf<int> &dcls = pw.cls; DevBuf<double> &done = pw.one;
+    DevBuf<D2> &dx = pw.x, &dy = pw.y;
+    const size_t xsize = (size_t)ne * L;
     ElemData E = h->E;
     E.n_elem = ne; E.cls = dcls.p; E.eps = done.p; E.muinv = done.p;
     if (h1space) E.map_h1 = dmap.p; else E.map_nd = dmap.p;
-    std::vector<D2> y(x.size());
+    std::vector<D2> &y = pw.hy;
     auto fetch = [&](std::vector<double> *out) {
       BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * y.size(), cudaMemcpyDeviceToHost, s));
       BLOCH_CUDA(cudaStreamSynchronize(s));
@@ -190,20 +198,20 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
         for (int c = 0; c < nc; c++) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
     };
     if (h1space) {
-      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
       BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 1.0, 0.0));
       h->count_launch();
       fetch(outA);
-      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
       BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 0.0, 1.0));
       h->count_launch();
       fetch(outM);
     } else {
-      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
       BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 1.0, 0.0, s));
       h->count_launch();
       fetch(outA);
-      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
+      BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
       BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 0.0, 1.0, s));
       h->count_launch();
       fetch(outM);
@@ -243,7 +251,7 @@ void bloch_handle_s::setup() {
                     (lmax_local_h1 <= 0.0) ? &bound_h1 : nullptr);
     if (lmax_local <= 0.0) lmax_local = bound;
     if (lmax_local_h1 <= 0.0) lmax_local_h1 = bound_h1;
-    DevBuf<double> dl;
+    DevBuf<double> &dl = d_dloc;
     d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0); d_diagM0.alloc(N0);
     BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N, stream));
     BLOCH_CUDA(cudaMemsetAsync(d_diagM.p, 0, sizeof(double) * N, stream));

@@ -133,6 +133,18 @@ struct bloch_handle_s {
   bloch_b200::DevBuf<D2> d_Xs;
   bool scalar_ready = false;
 
+  // probe problems (one private element copy per local unit vector), built once per space;
+  // persistent so that Setup() never calls cudaMalloc/cudaFree (device-wide syncs)
+  struct ProbeWork {
+    bloch_b200::DevBuf<int32_t> map;
+    bloch_b200::DevBuf<int> cls;
+    bloch_b200::DevBuf<double> one;
+    bloch_b200::DevBuf<D2> x, y;
+    std::vector<D2> hy;
+    bool built = false;
+  } probe_nd, probe_h1;
+  bloch_b200::DevBuf<double> d_dloc;
+
   struct LobpcgWork {
     bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM;
     bloch_b200::DevBuf<double> dlam, drn;

@@ -234,7 +234,8 @@ struct H1Level {
   ElemData E{};
   double lmax = 0;
   DevBuf<D2> x, b, r, d, q;           // V-cycle work vectors, N0 x m
-  DevBuf<D2> inv;                     // dense inverse on the coarsest level
+  DevBuf<D2> inv, dI, dA;             // dense inverse on the coarsest level (+ identity / operator scratch)
+  DevBuf<double> dloc;                // element-local diagonals (scratch)
   bool dense = false;
 };
 
@@ -371,7 +372,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     double bound = 0.0;
     probe_level(h, E, dloc, &bound);
     L.lmax = 1.05 * bound;
-    DevBuf<double> dl;
+    DevBuf<double> &dl = L.dloc;
     dl.upload(dloc, s);
     L.diag.alloc(L.N0); L.jac.alloc(L.N0);
     BLOCH_CUDA(cudaMemsetAsync(L.diag.p, 0, sizeof(double) * L.N0, s));
@@ -386,8 +387,8 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     const int n = (int)C.N0;
     std::vector<D2> I((size_t)n * n, make_double2(0.0, 0.0));
     for (int i = 0; i < n; i++) I[(size_t)i * n + i].x = 1.0;
-    DevBuf<D2> dI, dA;
-    dI.upload(I, s);
+    DevBuf<D2> &dI = C.dI, &dA = C.dA;
+    if (dI.n < (size_t)n * n) dI.upload(I, s);
     dA.alloc((size_t)n * n);
     BLOCH_CUDA(cudaMemsetAsync(dA.p, 0, sizeof(D2) * n * n, s));
     BLOCH_CUDA(launch_h1_op(p, 3, h->tabs, C.E, dI.p, n, dA.p, n, n, s, 1.0, 0.0));
@@ -433,29 +434,20 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
 }
 
 static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound) {
+  // same probe problem as Setup() (core.cu): one private element per local unit vector; the probe
+  // buffers were built there and are reused (no allocation per k-point)
   const int nc = Elev.n_class, L = h->L_h1;
   cudaStream_t s = h->stream;
   const int ne = nc * L;
-  std::vector<int32_t> map((size_t)ne * L);
-  std::vector<int> cls(ne);
-  std::vector<double> one(ne, 1.0);
-  std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
-  for (int c = 0; c < nc; c++)
-    for (int k = 0; k < L; k++) {
-      const int e = c * L + k;
-      cls[e] = c;
-      for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
-      x[(size_t)e * L + k].x = 1.0;
-    }
-  DevBuf<int32_t> dmap; DevBuf<int> dcls; DevBuf<double> done; DevBuf<D2> dx, dy;
-  dmap.upload(map, s); dcls.upload(cls, s); done.upload(one, s); dx.upload(x, s);
-  dy.alloc(x.size());
+  bloch_handle_s::ProbeWork &pw = h->probe_h1;
+  if (!pw.built) throw std::runtime_error("multigrid setup before Setup()");
   ElemData E = Elev;
-  E.n_elem = ne; E.cls = dcls.p; E.eps = done.p; E.muinv = done.p; E.map_h1 = dmap.p;
-  BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * x.size(), s));
-  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 1.0, 0.0));
-  std::vector<D2> y(x.size());
-  BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * y.size(), cudaMemcpyDeviceToHost, s));
+  E.n_elem = ne; E.cls = pw.cls.p; E.eps = pw.one.p; E.muinv = pw.one.p; E.map_h1 = pw.map.p;
+  const size_t xs = (size_t)ne * L;
+  BLOCH_CUDA(cudaMemsetAsync(pw.y.p, 0, sizeof(D2) * xs, s));
+  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, pw.x.p, 1, pw.y.p, 1, 1, s, 1.0, 0.0));
+  std::vector<D2> &y = pw.hy;
+  BLOCH_CUDA(cudaMemcpyAsync(y.data(), pw.y.p, sizeof(D2) * xs, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
   dloc.resize((size_t)nc * L);
   for (int c = 0; c < nc; c++) {
