@@ -156,7 +156,7 @@ __device__ __forceinline__ void nd_compute_tile(double2 *sND, double2 *sRT, cons
 // computed, so the two dependent global round trips (index, value) of the signed gather are off
 // the critical path.  Signs are applied in place by the thread that issued the copy.
 template <int P, int NW>
-__global__ void __launch_bounds__(NW * 32, (P == 1 ? 6 : (P == 2 ? 3 : 1)))
+__global__ void __launch_bounds__(NW * 32, (P == 2 ? 3 : 1))
 k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
            double2 *__restrict__ Y, double2 *__restrict__ Z, int m, int ldx, int ldy, long n_items, double ca,
            double cm) {
