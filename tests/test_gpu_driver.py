@@ -1,0 +1,54 @@
+"""maxwell_dispersion-style sweeps: the Python sweep helpers and the C++ driver binary (built on
+include/maxwell_bloch_b200.hpp) must agree with direct solves; disp.dat follows the reference's
+format (maxwell/maxwell_dispersion.cpp:1062-1087)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dispersion_sweep_and_sharded_sweep_agree(bloch):
+    L = bloch.BravaisLattice("HEX")
+    eq = bloch.MaxwellBlochWaveEquation(L, 2, 2)
+    eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()))
+    ks = bloch.k_path(L, ["Gamma", "M", "K", "Gamma"], 2)
+    lam, stats = bloch.dispersion_sweep(eq, ks, 4, tol=1e-8)
+    assert lam.shape == (6, 4) and all(s["converged_bands"] == 4 for s in stats)
+    assert np.all(np.diff(lam, axis=1) >= -1e-9)                        # ascending per k-point
+    assert np.all(np.abs(lam[-1, :3]) < 1e-7)                           # back at Gamma: 3 zero modes
+
+    def solve(k):
+        eq.SetKappa(k)
+        eq.Setup()
+        eq.Solve()
+        return eq.band_eigenvalues()
+
+    eq.SetNumEigs(8)
+    again = bloch.sharded_sweep(solve, ks, 4, None)
+    assert np.allclose(again, lam, rtol=1e-6, atol=1e-7)
+
+
+def test_cpp_driver_writes_reference_style_disp_dat(bloch, tmp_path):
+    exe = os.path.join(ROOT, "mfem-bravais_b200", "lib", "maxwell_dispersion_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    r = subprocess.run([exe, "-bl", "1", "-o", "1", "-sr", "0", "-pr", "2", "-p", "2", "-np", "1", "-nb", "4",
+                        "-out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split("\t") for l in open(tmp_path / "disp.dat") if l.strip()]
+    # CUB paths: Gamma-X-M-Gamma-R-X (5 segments) and M-R (1): per segment np+1 points + the closing point
+    assert rows[0][1] == "Gamma" and rows[1][1] == "Delta" and rows[2][1] == "X"
+    assert all(len(row) == 2 + 8 for row in rows)                        # nev = 2 * nb real modes
+    w = np.array([[float(x) for x in row[2:]] for row in rows])
+    assert np.allclose(w[:, 0::2], w[:, 1::2])                           # every band twice
+    # same k-point solved through the Python mirror: X = pi * e_y
+    L = bloch.BravaisLattice("CUB")
+    eq = bloch.MaxwellBlochWaveEquation(L, 4, 1)
+    eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()))
+    lam = eq.GetEigenvalues(8, L.GetSymmetryPoint(1))
+    assert np.allclose(w[2], np.sqrt(np.maximum(lam, 0)), rtol=1e-5, atol=1e-6)
+    assert (tmp_path / "stats_0.out").read_text().startswith("Timings:")
