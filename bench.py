@@ -135,7 +135,10 @@ def run_b200(args):
     lat = m.BravaisLattice(args.lattice)
     ks = k_points(m, lat, args)
     nk = len(ks)
-    T = max(1, args.streams)
+    cores = os.cpu_count() or 1
+    T = max(1, min(args.streams, max(1, cores // max(1, world))))   # solver threads per rank <= cores per rank
+    if T * world * 2 > cores:
+        os.environ["BLOCH_BLOCKING_SYNC"] = "1"                    # sleep, do not spin, when threads are scarce
     eqs = [m.MaxwellBlochWaveEquation(lat, args.n_sub, args.order, device=local) for _ in range(T)]
     eps = m.sphere_eps(eqs[0].element_centers())
     for eq in eqs:

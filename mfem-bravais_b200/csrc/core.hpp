@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -31,6 +32,21 @@ struct CudaError : std::runtime_error {
     if (err__ != cudaSuccess)                                                                \
       throw ::bloch_b200::CudaError(std::string(#call) + ": " + cudaGetErrorString(err__)); \
   } while (0)
+
+// Host wait for the handle's stream.  BLOCH_BLOCKING_SYNC=1: wait on a blocking event so the thread
+// sleeps instead of spinning - for runs with more solver threads than host cores (several
+// concurrent k-point solves per GPU x several ranks per box).
+inline void h_sync(cudaStream_t s) {
+  static const bool blocking = [] { const char *e = std::getenv("BLOCH_BLOCKING_SYNC"); return e && std::atoi(e) != 0; }();
+  if (!blocking) {
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) BLOCH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+  BLOCH_CUDA(cudaEventRecord(ev, s));
+  BLOCH_CUDA(cudaEventSynchronize(ev));
+}
 
 template <class T>
 struct DevBuf {   // owning device buffer

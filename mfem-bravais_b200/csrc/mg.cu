@@ -306,7 +306,7 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
             kh1[(size_t)e * LH + (i0 * Q + i1) * Q + i2] = L.maps.h1[(size_t)e * LH + i0 + Q * (i1 + Q * i2)];
     L.map_h1.upload(kh1, s);
     L.cls.upload(L.mesh.cls, s);
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     if (L.N0 <= 8) break;
   }
   // multiplicity weights of every level that restricts (all but the coarsest)
@@ -319,7 +319,7 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
     k_count<<<grid_for(ne * h->L_h1), TPB, 0, s>>>(map, ne * h->L_h1, L.invmult.p);
     k_invert<<<grid_for(L.N0), TPB, 0, s>>>(L.invmult.p, L.N0);
   }
-  BLOCH_CUDA(cudaStreamSynchronize(s));
+  h_sync(s);
   return mg;
 }
 
@@ -378,7 +378,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     BLOCH_CUDA(cudaMemsetAsync(L.diag.p, 0, sizeof(double) * L.N0, s));
     BLOCH_CUDA(launch_scatter_diag(E.map_h1, h->L_h1, E.cls, E.eps, dl.p, E.n_elem, L.diag.p, s));
     k_jacobi<<<grid_for(L.N0), TPB, 0, s>>>(L.diag.p, L.jac.p, L.N0);
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
   }
   // coarsest level: dense inverse from one block apply to the identity
   H1Level &C = mg->lev[nl - 1];
@@ -394,7 +394,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     BLOCH_CUDA(launch_h1_op(p, 3, h->tabs, C.E, dI.p, n, dA.p, n, n, s, 1.0, 0.0));
     std::vector<D2> A((size_t)n * n);
     BLOCH_CUDA(cudaMemcpyAsync(A.data(), dA.p, sizeof(D2) * n * n, cudaMemcpyDeviceToHost, s));
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     dense::Mat Am((size_t)n * n);
     double tr = 0;
     for (int i = 0; i < n; i++) tr += A[(size_t)i * n + i].x;
@@ -428,7 +428,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
       std::vector<D2> inv((size_t)n * n);
       for (size_t i = 0; i < inv.size(); i++) inv[i] = make_double2(X[i].real(), X[i].imag());
       C.inv.upload(inv, s);
-      BLOCH_CUDA(cudaStreamSynchronize(s));
+      h_sync(s);
     }
   }
 }
@@ -448,7 +448,7 @@ static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<dou
   BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, pw.x.p, 1, pw.y.p, 1, 1, s, 1.0, 0.0));
   std::vector<D2> &y = pw.hy;
   BLOCH_CUDA(cudaMemcpyAsync(y.data(), pw.y.p, sizeof(D2) * xs, cudaMemcpyDeviceToHost, s));
-  BLOCH_CUDA(cudaStreamSynchronize(s));
+  h_sync(s);
   dloc.resize((size_t)nc * L);
   for (int c = 0; c < nc; c++) {
     for (int k = 0; k < L; k++) dloc[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
@@ -556,7 +556,7 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
   std::vector<double> rr0(m), rrh(m);
   BLOCH_CUDA(launch_col_dot(rhs, rhs, N0, m, rr, s));
   BLOCH_CUDA(cudaMemcpyAsync(rr0.data(), rr, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
-  BLOCH_CUDA(cudaStreamSynchronize(s));
+  h_sync(s);
   double mx = 0;
   for (double v : rr0) mx = std::max(mx, v);
   if (mx == 0.0) return 0;
@@ -607,7 +607,7 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
     }
     if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); else half_a();
     BLOCH_CUDA(cudaMemcpyAsync(rrh.data(), rr, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     bool done = true;
     for (int j = 0; j < m; j++)
       if (rrh[j] > rel_tol * rel_tol * rr0[j]) done = false;

@@ -239,7 +239,7 @@ static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_t
   h->count_launch(4);
   int info[2] = {0, 0};
   BLOCH_CUDA(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, s));
-  BLOCH_CUDA(cudaStreamSynchronize(s));
+  h_sync(s);
   if (mg_its >= 0) info[0] = mg_its;
   h->stats.inner_iterations += info[0];
   if (iters) *iters = info[0];
@@ -391,7 +391,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     count_launch(2);
     BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     // basis columns that take part: all of X; W_j / P_j only for unconverged j (soft locking) and
     // only if they are not numerically zero (X is M-orthonormal, so diag(GM) of X is ~1)
     std::vector<int> keep;
@@ -443,7 +443,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     const unsigned g = (unsigned)std::min<long>((Nl + 7) / 8, 148L * 8);
     k_rr_update<<<g, 256, sizeof(D2) * k * mb, s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
     count_launch();
-    BLOCH_CUDA(cudaStreamSynchronize(s));   // hC / lam are stack-lifetime host buffers
+    h_sync(s);   // hC / lam are stack-lifetime host buffers
     if (dropped) need_refresh = true;
     return true;
   };
@@ -457,7 +457,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     BLOCH_CUDA(launch_fill_random(Wc.p, Nl * mb, 0xB10C4ULL, s));
     BLOCH_CUDA(launch_pack(tmp.p, Dd.p, Nl, mi, s));
     BLOCH_CUDA(cudaMemcpy2DAsync(Wc.p, sizeof(D2) * mb, Dd.p, sizeof(D2) * mi, sizeof(D2) * mi, Nl, cudaMemcpyDeviceToDevice, s));
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     count_launch(2);
   } else if (warm && have_vectors == mb && d_X.n >= (size_t)Nl * mb) {
     BLOCH_CUDA(cudaMemcpyAsync(Wc.p, d_X.p, sizeof(D2) * Nl * mb, cudaMemcpyDeviceToDevice, s));
@@ -493,7 +493,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     k_resid_norm<<<grid_for(Nl * mb), TPB, sizeof(double) * mb, s>>>(AS.p, MS.p, ld, dlam.p, R.p, Nl, mb, drn.p);
     count_launch();
     BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * mb, cudaMemcpyDeviceToHost, s));
-    BLOCH_CUDA(cudaStreamSynchronize(s));
+    h_sync(s);
     t_res += since(t0);
     for (int j = 0; j < mb; j++) active[j] = std::sqrt(rn[j]) > 0.1 * tol;
     nconv = 0;
