@@ -1,0 +1,116 @@
+"""Less-travelled parts of the boundary: custom hex meshes, scaled lattices, variable mu^-1,
+user initial vectors, device-pointer entry points, error behaviour on a live handle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import oracle_on_product_maps, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_scaled_lattice_and_custom_hex_mesh(bloch):
+    """lambda scales like 1/a^2 (eps = mu = 1); bloch_create_from_hexes reproduces the lattice path"""
+    from mfem_bravais_b200 import capi
+    k = np.array([0.9, -0.3, 0.4])
+    L1, L2 = bloch.BravaisLattice("FCC", a=1.0), bloch.BravaisLattice("FCC", a=2.0)
+    e1, e2 = bloch.MaxwellBlochWaveEquation(L1, 2, 2), bloch.MaxwellBlochWaveEquation(L2, 2, 2)
+    for e in (e1, e2):
+        e.SetAbsoluteTolerance(1e-9)
+    a = e1.GetEigenvalues(8, k)[0::2]
+    b = e2.GetEigenvalues(8, k / 2.0)[0::2]
+    assert np.allclose(a, 4.0 * b, rtol=1e-7)
+    assert abs(L2.GetUnitCellVolume() - 8 * L1.GetUnitCellVolume()) < 1e-12
+    # the same cell given as an explicit list of hexes (unit cube split in 2 bricks along x)
+    xyz = np.array([[x, y, z] for z in (0, 1) for y in (0, 1) for x in (0, 0.5, 1.0)], float)
+    vid = lambda i, j, kk: i + 3 * (j + 2 * kk)
+    hexes = np.array([[vid(i, 0, 0), vid(i + 1, 0, 0), vid(i + 1, 1, 0), vid(i, 1, 0),
+                       vid(i, 0, 1), vid(i + 1, 0, 1), vid(i + 1, 1, 1), vid(i, 1, 1)] for i in (0, 1)], np.int32)
+    rec = np.eye(3)
+    h = C.c_void_p()
+    lib = capi.lib()
+    capi.check(lib.bloch_create_from_hexes(C.byref(h), len(xyz), capi.dptr(xyz), len(hexes),
+                                           hexes.ctypes.data_as(C.POINTER(C.c_int)), capi.dptr(rec), 2, 1, -1))
+    try:
+        n_nd = C.c_int64()
+        capi.check(lib.bloch_num_dofs(h, C.byref(n_nd), None, None))
+        assert n_nd.value == 3 * (2 * 8)                                  # 4 x 2 x 2 bricks, order 1
+        capi.check(lib.bloch_set_num_bands(h, 3))
+        capi.check(lib.bloch_set_tol(h, 1e-9, 500))
+        kk = np.array([0.5, 0.2, 0.1])
+        capi.check(lib.bloch_set_kappa(h, capi.dptr(kk)))
+        capi.check(lib.bloch_solve(h))
+        lam = np.zeros(3)
+        capi.check(lib.bloch_get_eigenvalues(h, capi.dptr(lam), 3))
+        assert abs(lam[0] - kk @ kk) < 1e-9 and abs(lam[1] - kk @ kk) < 1e-9   # exact lowest pair
+    finally:
+        lib.bloch_destroy(h)
+
+
+def test_variable_muinv_eigenvalues(bloch):
+    L = bloch.BravaisLattice("CUB")
+    eq = bloch.MaxwellBlochWaveEquation(L, 3, 1)
+    rng = np.random.default_rng(3)
+    eps, mui = rng.uniform(1, 5, eq.n_elem), rng.uniform(0.5, 2, eq.n_elem)
+    eq.SetMassCoef(eps)
+    eq.SetStiffnessCoef(mui)
+    k = np.array([0.4, 0.7, -0.2])
+    ops, _ = oracle_on_product_maps(eq, "CUB", 3, 1, eps, mui)
+    ref = ops.set_kappa(k).eig_dense(5)
+    eq.SetAbsoluteTolerance(1e-9)
+    assert np.allclose(eq.GetEigenvalues(10, k)[0::2], ref, rtol=1e-7)
+
+
+def test_initial_vectors_are_used(bloch):
+    L = bloch.BravaisLattice("FCC")
+    eq = bloch.MaxwellBlochWaveEquation(L, 2, 2)
+    eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()))
+    k = np.array([1.0, 0.3, -0.6])
+    eq.SetAbsoluteTolerance(1e-8)
+    lam = eq.GetEigenvalues(8, k)[0::2]
+    cold = eq.GetSolverStats()["iterations"]
+    vecs = np.array([np.concatenate(eq.GetEigenvectorE(i)) for i in range(4)])
+    eq2 = bloch.MaxwellBlochWaveEquation(L, 2, 2)
+    eq2.SetMassCoef(bloch.sphere_eps(eq2.element_centers()))
+    eq2.SetAbsoluteTolerance(1e-8)
+    lam2 = eq2.GetEigenvalues(8, k, init_vecs=vecs)[0::2]
+    assert np.allclose(lam, lam2, rtol=1e-8)
+    assert eq2.GetSolverStats()["iterations"] <= cold          # exact vectors for the wanted bands
+    eq2.SetInitialVectors(None)                                # back to the built-in guess
+
+
+def test_device_pointer_entry_points(bloch):
+    import torch
+    L = bloch.BravaisLattice("BCC")
+    eq = bloch.MaxwellBlochWaveEquation(L, 1, 2)
+    eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()))
+    eq.SetKappa([0.2, 0.5, 0.1])
+    eq.Setup()
+    nv, N = 3, eq.N
+    x = np.random.default_rng(0).uniform(-1, 1, (nv, 2 * N))
+    st = torch.cuda.Stream()
+    eq.set_stream(st.cuda_stream)
+    with torch.cuda.stream(st):
+        xr = torch.tensor(x, device="cuda")
+        blk = torch.empty(2 * N * nv, device="cuda", dtype=torch.float64)
+        yb = torch.empty_like(blk)
+        yr = torch.empty_like(xr)
+        eq.pack_device(xr.data_ptr(), blk.data_ptr(), nv)
+        eq.apply_A_device(blk.data_ptr(), yb.data_ptr(), nv)
+        eq.unpack_device(yb.data_ptr(), yr.data_ptr(), nv)
+    st.synchronize()
+    eq.set_stream(0)
+    assert rel_err(yr.cpu().numpy(), eq.MultA(x)) < 1e-13
+    # block layout: interleaved complex, dof-major
+    b = blk.cpu().numpy().reshape(N, nv, 2)
+    assert np.array_equal(b[:, 1, 0], x[1, :N]) and np.array_equal(b[:, 2, 1], x[2, N:])
+
+
+def test_errors_on_live_handle(bloch):
+    L = bloch.BravaisLattice("CUB")
+    eq = bloch.MaxwellBlochWaveEquation(L, 2, 1)
+    with pytest.raises(bloch.BlochError):
+        eq.GetEigenvectorE(0)                                   # before any Solve
+    with pytest.raises(bloch.BlochError):
+        eq.SetNumEigs(400000)
