@@ -147,6 +147,17 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
 
+/* ---- reduced-basis k-sweep: MaxwellDispersion::buildRawBasis / approxEigenfrequencies
+ * (meta-material/meta_material_solver.cpp:3132-3305).  Full solves are done only at symmetry (and mid)
+ * points and their eigenvectors appended to a raw basis kept on the device; bloch_rb_approx then, for any
+ * kappa, projects that basis with the kappa's divergence projector, forms the reduced Gram matrices
+ * <A p_i, p_j>, <M p_i, p_j> and solves the small dense pencil (the reference: LAPACK dsygv, :3285-3299).
+ * Returns APPROXIMATE eigenvalues (ascending), exact at the k-points whose eigenvectors are in the basis. */
+int bloch_rb_clear(bloch_handle h);
+int bloch_rb_append(bloch_handle h);        /* append the bands of the last bloch_solve */
+int bloch_rb_size(bloch_handle h);
+int bloch_rb_approx(bloch_handle h, const double kappa[3], double *lambda, int n);
+
 /* ---- scalar variant: ScalarFloquetWaveEquation of misc/scalar3d.cpp:662-818 ----
  * (G - i Z_kappa)^T M1(k) (G - i Z_kappa) u = lambda M0(m) u on H1_p (orders 1..4), same handle, same mesh.
  * kappa is set with bloch_set_kappa; the reference's phase shift beta is in DEGREES:

@@ -76,6 +76,10 @@ SIGNATURES = {
     "bloch_apply_M_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "bloch_rb_clear": (C.c_int, [_vp]),
+    "bloch_rb_append": (C.c_int, [_vp]),
+    "bloch_rb_size": (C.c_int, [_vp]),
+    "bloch_rb_approx": (C.c_int, [_vp, _dp, _dp, C.c_int]),
     "bloch_scalar_set_coefs": (C.c_int, [_vp, _dp, _dp]),
     "bloch_scalar_set_num_modes": (C.c_int, [_vp, C.c_int]),
     "bloch_scalar_solve": (C.c_int, [_vp]),

@@ -3,6 +3,7 @@
 // Setup :337-620, GetEigenvalues :1052-1076, GetEigenvectorE/B :1371-1458.
 #include "core.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -751,6 +752,35 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// ---- reduced-basis sweep: MaxwellDispersion (meta-material/meta_material_solver.cpp:3132-3410) ----
+int bloch_rb_clear(bloch_handle h) {
+  if (!h) return BLOCH_ERR_ARG;
+  h->rb_size = 0;
+  return BLOCH_OK;
+}
+int bloch_rb_append(bloch_handle h) {
+  API_BEGIN
+  REQUIRE(h && h->device >= 0, "bad handle");
+  BLOCH_CUDA(cudaSetDevice(h->device));
+  h->rb_append();
+  return BLOCH_OK;
+  API_END
+}
+int bloch_rb_size(bloch_handle h) { return h ? h->rb_size : BLOCH_ERR_ARG; }
+int bloch_rb_approx(bloch_handle h, const double kappa[3], double *lambda, int n) {
+  API_BEGIN
+  REQUIRE(h && kappa && lambda && n >= 1, "bad argument");
+  for (int i = 0; i < 3; i++) h->kappa[i] = kappa[i];
+  h->dirty_kappa = true;
+  auto t0 = std::chrono::steady_clock::now();
+  h->setup();
+  if (std::getenv("BLOCH_VERBOSE"))
+    std::printf("[rb] setup %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  h->rb_approx(lambda, n);
   return BLOCH_OK;
   API_END
 }

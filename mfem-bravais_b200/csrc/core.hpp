@@ -141,6 +141,12 @@ struct bloch_handle_s {
   int n_init = 0;
   bloch_b200::SolverStats stats;
 
+  // reduced-basis sweep (meta-material/meta_material_solver.cpp:3132-3305)
+  bloch_b200::DevBuf<D2> d_rb, d_rb_p, d_rb_ap, d_rb_mp, d_rb_tmp;   // raw basis [N][rb_cap] and projected work arrays
+  int rb_size = 0, rb_cap = 0;
+  void rb_append();
+  void rb_approx(double *lambda, int n);
+
   // scalar H1 variant (misc/scalar3d.cpp): stiffness coefficient k -> eps slot, mass coefficient m -> muinv slot
   bloch_b200::DevBuf<double> d_diagM0;
   double lmax_local_h1 = 0;

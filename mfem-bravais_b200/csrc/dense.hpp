@@ -70,7 +70,8 @@ inline void back_transform(int n, int m, const Mat &L, Mat &C) {
 }
 
 // Real symmetric tridiagonal QL with implicit shifts; d (diag, n), e (sub-diag, e[i] couples i and
-// i+1, e[n-1] unused); Z (n x n real, row-major) is post-multiplied by the rotations.
+// i+1, e[n-1] unused); Z (n x n real, row-major) is post-multiplied by the rotations (an empty Z
+// skips the eigenvector accumulation).
 inline bool tridiag_ql(int n, std::vector<double> &d, std::vector<double> &e, std::vector<double> &Z) {
   for (int l = 0; l < n; l++) {
     int iter = 0, m;
@@ -97,7 +98,7 @@ inline bool tridiag_ql(int n, std::vector<double> &d, std::vector<double> &e, st
           p = s * r;
           d[i + 1] = g + p;
           g = c * r - b;
-          for (int k = 0; k < n; k++) {
+          for (int k = 0; k < n && !Z.empty(); k++) {
             double f2 = Z[k * n + i + 1];
             Z[k * n + i + 1] = s * Z[k * n + i] + c * f2;
             Z[k * n + i] = c * Z[k * n + i] - s * f2;
@@ -115,9 +116,13 @@ inline bool tridiag_ql(int n, std::vector<double> &d, std::vector<double> &e, st
 
 // Hermitian eigen-decomposition A = V diag(w) V^H, w ascending, V (n x n) columns = eigenvectors.
 // Householder tridiagonalisation, phase normalisation to a real tridiagonal, QL.
-inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V) {
-  Mat Q(n * n, cplx(0));
-  for (int i = 0; i < n; i++) Q[i * n + i] = 1.0;
+// want_vectors = false skips the accumulation of Q and of the QL rotations (V is left empty).
+inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V, bool want_vectors = true) {
+  Mat Q;
+  if (want_vectors) {
+    Q.assign((size_t)n * n, cplx(0));
+    for (int i = 0; i < n; i++) Q[i * n + i] = 1.0;
+  }
   std::vector<cplx> v(n), pv(n), qv(n);
   for (int k = 0; k + 2 < n; k++) {
     double xn = 0;
@@ -161,7 +166,7 @@ inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V) {
       for (int j = k + 1; j < n; j++)
         A[i * n + j] -= 2.0 * (v[i] * std::conj(qv[j]) + qv[i] * std::conj(v[j]));
     // Q <- Q H
-    for (int r = 0; r < n; r++) {
+    for (int r = 0; r < n && want_vectors; r++) {
       cplx s = 0;
       for (int j = k + 1; j < n; j++) s += Q[r * n + j] * v[j];
       for (int j = k + 1; j < n; j++) Q[r * n + j] -= 2.0 * s * std::conj(v[j]);
@@ -177,9 +182,18 @@ inline bool heev(int n, Mat A, std::vector<double> &w, Mat &V) {
     e[i] = a;
     ph[i + 1] = a > 0 ? ph[i] * ek / a : ph[i];
   }
-  std::vector<double> Z(n * n, 0.0);
-  for (int i = 0; i < n; i++) Z[i * n + i] = 1.0;
+  std::vector<double> Z;
+  if (want_vectors) {
+    Z.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) Z[i * n + i] = 1.0;
+  }
   if (!tridiag_ql(n, d, e, Z)) return false;
+  if (!want_vectors) {
+    std::sort(d.begin(), d.end());
+    w = d;
+    V.clear();
+    return true;
+  }
   std::vector<int> ord(n);
   for (int i = 0; i < n; i++) ord[i] = i;
   std::sort(ord.begin(), ord.end(), [&](int a, int b) { return d[a] < d[b]; });
@@ -273,6 +287,65 @@ inline bool hegv_lowest(int n, int m, const Mat &GA, const Mat &GM, std::vector<
   }
   for (int i = 0; i < n; i++)
     for (int j = 0; j < m; j++) C[i * m + j] *= sc[i];
+  return true;
+}
+
+
+// Lowest m eigenvalues only of GA c = lambda GM c for a LARGE, possibly nearly dependent basis (the
+// reduced-basis sweep: a few hundred vectors collected at neighbouring k-points).  Diagonal scaling,
+// then Cholesky with diagonal pivoting picks a well-conditioned subset of the basis vectors and stops
+// when the largest remaining Schur-complement diagonal falls to drop_tol (a vector whose component
+// outside the span of the chosen ones is below sqrt(drop_tol) of its norm adds nothing but noise);
+// the pencil restricted to the subset is reduced to standard form and only tridiagonalised.
+inline bool hegv_lowest_values(int n, int m, const Mat &GA, const Mat &GM, std::vector<double> &lam,
+                               double drop_tol = 1e-10, int *rank_out = nullptr) {
+  std::vector<double> sc(n);
+  for (int i = 0; i < n; i++) {
+    const double dii = GM[(size_t)i * n + i].real();
+    if (!(dii > 0)) return false;
+    sc[i] = 1.0 / std::sqrt(dii);
+  }
+  Mat S((size_t)n * n);                        // scaled GM, overwritten column by column with L (pivoted order)
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) S[(size_t)i * n + j] = GM[(size_t)i * n + j] * (sc[i] * sc[j]);
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; i++) perm[i] = i;
+  std::vector<double> dg(n, 1.0);
+  Mat L((size_t)n * n, cplx(0));               // L[row in pivoted order][k]
+  int r = 0;
+  for (; r < n; r++) {
+    int piv = r;
+    for (int i = r + 1; i < n; i++)
+      if (dg[i] > dg[piv]) piv = i;
+    if (!(dg[piv] > drop_tol)) break;
+    if (piv != r) {
+      std::swap(perm[piv], perm[r]);
+      std::swap(dg[piv], dg[r]);
+      for (int k = 0; k < r; k++) std::swap(L[(size_t)piv * n + k], L[(size_t)r * n + k]);
+    }
+    const double lrr = std::sqrt(dg[r]);
+    L[(size_t)r * n + r] = lrr;
+    for (int i = r + 1; i < n; i++) {
+      cplx v = S[(size_t)perm[i] * n + perm[r]];
+      for (int k = 0; k < r; k++) v -= L[(size_t)i * n + k] * std::conj(L[(size_t)r * n + k]);
+      v /= lrr;
+      L[(size_t)i * n + r] = v;
+      dg[i] -= std::norm(v);
+    }
+  }
+  if (rank_out) *rank_out = r;
+  if (r < m) return false;
+  Mat Lr((size_t)r * r, cplx(0)), B((size_t)r * r);
+  for (int i = 0; i < r; i++) {
+    for (int k = 0; k <= i; k++) Lr[(size_t)i * r + k] = L[(size_t)i * n + k];
+    for (int j = 0; j < r; j++)
+      B[(size_t)i * r + j] = GA[(size_t)perm[i] * n + perm[j]] * (sc[perm[i]] * sc[perm[j]]);
+  }
+  reduce_to_standard(r, Lr, B);
+  std::vector<double> w;
+  Mat V;
+  if (!heev(r, B, w, V, false)) return false;
+  lam.assign(w.begin(), w.begin() + m);
   return true;
 }
 

@@ -562,3 +562,112 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
 }
+
+// ------------------------------------------------------------------------------------------
+// Reduced-basis k-sweep (MaxwellDispersion::buildRawBasis / approxEigenfrequencies,
+// meta-material/meta_material_solver.cpp:3132-3305): full solves only at symmetry (+ mid) points;
+// at any other kappa the raw eigenvectors are projected with that kappa's divergence projector
+// and the pencil (A, M) is solved in their span (the reference: dsygv on the real 2N form; here
+// the equivalent complex Hermitian reduced problem).
+// ------------------------------------------------------------------------------------------
+void bloch_handle_s::rb_append() {
+  if (have_vectors <= 0) throw std::invalid_argument("no eigenvectors to append (call bloch_solve first)");
+  const int nb = nbands;
+  if (rb_size + nb > rb_cap) {
+    const int ncap = std::max(2 * rb_cap, rb_size + nb + 64);
+    DevBuf<D2> grown;
+    grown.alloc((size_t)N * ncap);
+    BLOCH_CUDA(cudaMemsetAsync(grown.p, 0, sizeof(D2) * (size_t)N * ncap, stream));
+    if (rb_size > 0)
+      BLOCH_CUDA(cudaMemcpy2DAsync(grown.p, sizeof(D2) * ncap, d_rb.p, sizeof(D2) * rb_cap, sizeof(D2) * rb_size, N,
+                                   cudaMemcpyDeviceToDevice, stream));
+    h_sync(stream);
+    std::swap(d_rb.p, grown.p);
+    std::swap(d_rb.n, grown.n);
+    rb_cap = ncap;
+  }
+  BLOCH_CUDA(cudaMemcpy2DAsync(d_rb.p + rb_size, sizeof(D2) * rb_cap, d_X.p, sizeof(D2) * block, sizeof(D2) * nb, N,
+                               cudaMemcpyDeviceToDevice, stream));
+  h_sync(stream);
+  rb_size += nb;
+}
+
+void bloch_handle_s::rb_approx(double *lambda, int n) {
+  using dense::cplx;
+  using dense::Mat;
+  const int K = rb_size;
+  if (K < n || n < 1) throw std::invalid_argument("reduced basis smaller than the number of requested eigenvalues");
+  cudaStream_t s = stream;
+  static const bool verbose = std::getenv("BLOCH_VERBOSE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    h_sync(s);
+    auto t1 = std::chrono::steady_clock::now();
+    std::printf("[rb] %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
+  k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, (d_jac0.alloc(N0), d_jac0.p), N0);
+  d_rb_p.alloc((size_t)N * K); d_rb_ap.alloc((size_t)N * K); d_rb_mp.alloc((size_t)N * K);
+  static const int CH = std::getenv("BLOCH_RB_CHUNK") ? std::max(1, std::atoi(std::getenv("BLOCH_RB_CHUNK"))) : 64;
+  d_rb_tmp.alloc((size_t)N * CH);
+  for (int c0 = 0; c0 < K; c0 += CH) {
+    const int mc = std::min(CH, K - c0);
+    BLOCH_CUDA(cudaMemcpy2DAsync(d_rb_tmp.p, sizeof(D2) * mc, d_rb.p + c0, sizeof(D2) * rb_cap, sizeof(D2) * mc, N,
+                                 cudaMemcpyDeviceToDevice, s));
+    project_ld(this, d_rb_tmp.p, mc, mc, 1e-8, 3000, nullptr);           // projector of the CURRENT kappa
+    BLOCH_CUDA(cudaMemcpy2DAsync(d_rb_p.p + c0, sizeof(D2) * K, d_rb_tmp.p, sizeof(D2) * mc, sizeof(D2) * mc, N,
+                                 cudaMemcpyDeviceToDevice, s));
+    apply_nd_ld(d_rb_p.p + c0, K, d_rb_ap.p + c0, K, mc, 1.0, 0.0);
+    apply_nd_ld(d_rb_p.p + c0, K, d_rb_mp.p + c0, K, mc, 0.0, 1.0);
+  }
+  lap("project + A/M applies");
+  // Gram matrices block by block (the Gram kernel handles up to 64 x 64 outputs per launch); upper
+  // triangle of blocks only, all blocks of both matrices copied back behind one synchronisation
+  const int GB = 32, nblk = (K + GB - 1) / GB;
+  Mat GA((size_t)K * K), GM((size_t)K * K);
+  const size_t per = (size_t)GB * GB, nout = (size_t)2 * nblk * nblk * per;
+  DevBuf<D2> &dG = lw.dGA;
+  dG.alloc(nout);
+  std::vector<D2> hG(nout);
+  for (int which = 0; which < 2; which++) {
+    const D2 *Y = which == 0 ? d_rb_ap.p : d_rb_mp.p;
+    for (int bi = 0; bi < nblk; bi++)
+      for (int bj = bi; bj < nblk; bj++) {
+        const int i0 = bi * GB, j0 = bj * GB, mi = std::min(GB, K - i0), mj = std::min(GB, K - j0);
+        BLOCH_CUDA(launch_gram(d_rb_p.p + i0, mi, K, Y + j0, mj, K, N, dG.p + ((size_t)(which * nblk + bi) * nblk + bj) * per, s));
+        count_launch();
+      }
+  }
+  BLOCH_CUDA(cudaMemcpyAsync(hG.data(), dG.p, sizeof(D2) * nout, cudaMemcpyDeviceToHost, s));
+  h_sync(s);
+  for (int which = 0; which < 2; which++) {
+    Mat &G = which == 0 ? GA : GM;
+    for (int bi = 0; bi < nblk; bi++)
+      for (int bj = bi; bj < nblk; bj++) {
+        const int i0 = bi * GB, j0 = bj * GB, mi = std::min(GB, K - i0), mj = std::min(GB, K - j0);
+        const D2 *blk = hG.data() + ((size_t)(which * nblk + bi) * nblk + bj) * per;
+        for (int a = 0; a < mi; a++)
+          for (int b = 0; b < mj; b++) {
+            const cplx v(blk[a * mj + b].x, blk[a * mj + b].y);
+            G[(size_t)(i0 + a) * K + j0 + b] = v;
+            if (bi != bj) G[(size_t)(j0 + b) * K + i0 + a] = std::conj(v);
+          }
+      }
+    for (int a = 0; a < K; a++)
+      for (int b = a; b < K; b++) {
+        const cplx v = 0.5 * (G[(size_t)a * K + b] + std::conj(G[(size_t)b * K + a]));
+        G[(size_t)a * K + b] = v;
+        G[(size_t)b * K + a] = std::conj(v);
+      }
+  }
+  lap("gram");
+  std::vector<double> lam;
+  // vectors taken from neighbouring k-points are nearly dependent: pivoted-Cholesky subset (dense.hpp)
+  int rank = 0;
+  if (!dense::hegv_lowest_values(K, n, GA, GM, lam, 1e-10, &rank))
+    throw std::runtime_error("reduced-basis eigenproblem failed");
+  if (verbose) std::printf("[rb] basis %d -> rank %d\n", K, rank);
+  lap("dense hegv");
+  for (int i = 0; i < n; i++) lambda[i] = lam[i];
+}

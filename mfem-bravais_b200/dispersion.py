@@ -76,3 +76,72 @@ def sharded_sweep(solve_fn, kappas, n_bands, dist=None):
     for plo, block in parts:
         out[plo:plo + len(block)] = block
     return out
+
+
+class MaxwellDispersion:
+    """Reduced-basis band-structure sweep: the reference's MaxwellDispersion
+    (meta-material/meta_material_solver.cpp:3132-3410).
+
+    buildRawBasis(): full eigen-solves at every symmetry point of the lattice's paths (and at the
+    labelled intermediate points when mid_pts), eigenvectors kept on the device as the raw basis.
+    approxEigenfrequencies(kappa): Rayleigh-Ritz in the span of that basis projected with the
+    kappa's divergence projector; omega = sqrt|lambda|.
+    traverseBrillouinZone(): 2**samp_pow intervals per path segment; end (and mid) points take
+    the full-solve values, the rest the approximation.  Result: seg_eigs[p][s][i] = omega array."""
+
+    def __init__(self, eq, lattice, n_bands, samp_pow=2, mid_pts=True, tol=1e-6):
+        self.eq, self.lat, self.nb = eq, lattice, int(n_bands)
+        self.samp_pow, self.mid_pts = int(samp_pow), bool(mid_pts)
+        self.sp_eigs = {}
+        self.seg_eigs = []
+        eq.SetNumEigs(2 * self.nb)
+        eq.SetAbsoluteTolerance(tol)
+
+    def _full(self, label, kappa):
+        if label in self.sp_eigs:
+            return
+        self.eq.SetKappa(kappa)
+        self.eq.Setup()
+        self.eq.Solve()
+        self.sp_eigs[label] = np.sqrt(np.abs(self.eq.band_eigenvalues()))
+        self.eq.ReducedBasisAppend()
+
+    def buildRawBasis(self):
+        lat = self.lat
+        self.eq.ReducedBasisClear()
+        self.sp_eigs = {}
+        for p in range(lat.GetNumberPaths()):
+            for s in range(lat.GetNumberPathSegments(p)):
+                e0, e1 = lat.GetPathSegmentEndPointIndices(p, s)
+                self._full(lat.GetSymmetryPointLabel(e0), lat.GetSymmetryPoint(e0))
+                if self.mid_pts:
+                    self._full(lat.GetIntermediatePointLabel(p, s), lat.GetIntermediatePoint(p, s))
+                self._full(lat.GetSymmetryPointLabel(e1), lat.GetSymmetryPoint(e1))
+        return self.eq.ReducedBasisSize()
+
+    def approxEigenfrequencies(self, kappa):
+        return np.sqrt(np.abs(self.eq.ApproxEigenvalues(kappa, self.nb)))
+
+    def traverseBrillouinZone(self):
+        lat = self.lat
+        self.buildRawBasis()
+        ni = 2 ** self.samp_pow
+        self.seg_eigs = []
+        for p in range(lat.GetNumberPaths()):
+            segs = []
+            for s in range(lat.GetNumberPathSegments(p)):
+                e0, e1 = lat.GetPathSegmentEndPointIndices(p, s)
+                k0, k1 = lat.GetSymmetryPoint(e0), lat.GetSymmetryPoint(e1)
+                row = [None] * (ni + 1)
+                row[0] = self.sp_eigs[lat.GetSymmetryPointLabel(e0)]
+                row[ni] = self.sp_eigs[lat.GetSymmetryPointLabel(e1)]
+                for i in range(1, ni):
+                    if ni == 2 * i and self.mid_pts:
+                        row[i] = self.sp_eigs[lat.GetIntermediatePointLabel(p, s)]
+                    else:
+                        # (on segments touching Gamma the reference interpolates beta along a fixed
+                        # zeta, :3355-3374 - the same points as this linear interpolation)
+                        row[i] = self.approxEigenfrequencies(((ni - i) * k0 + i * k1) / ni)
+                segs.append(row)
+            self.seg_eigs.append(segs)
+        return self.seg_eigs

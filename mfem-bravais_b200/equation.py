@@ -219,6 +219,24 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_get_eigenvalues(self._h, dptr(lam), nb), "bloch_get_eigenvalues")
         return lam
 
+    # reduced-basis sweep pieces (MaxwellDispersion, meta_material_solver.cpp:3132-3305)
+    def ReducedBasisClear(self):
+        check(self._L.bloch_rb_clear(self._h), "bloch_rb_clear")
+
+    def ReducedBasisAppend(self):
+        """Appends the bands of the last Solve() to the device-resident raw basis."""
+        check(self._L.bloch_rb_append(self._h), "bloch_rb_append")
+
+    def ReducedBasisSize(self):
+        return int(self._L.bloch_rb_size(self._h))
+
+    def ApproxEigenvalues(self, kappa, n_bands):
+        """approxEigenfrequencies (meta_material_solver.cpp:3213-3305) at kappa, as eigenvalues."""
+        k = np.ascontiguousarray(kappa, float)
+        lam = np.zeros(int(n_bands))
+        check(self._L.bloch_rb_approx(self._h, dptr(k), dptr(lam), int(n_bands)), "bloch_rb_approx")
+        return lam
+
     def GetEigenvectorE(self, i):
         re, im = np.zeros(self.N), np.zeros(self.N)
         check(self._L.bloch_get_eigenvector_E(self._h, i, dptr(re), dptr(im)), "bloch_get_eigenvector_E")
