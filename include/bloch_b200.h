@@ -147,6 +147,12 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
 
+/* GetFieldAverages (maxwell/maxwell_bloch.cpp:1550-1632): cell integrals of the full Bloch fields
+ * e^{i kappa.x}(Er + i Ei) etc. of band i, out24 = Er[3], Ei[3], Br[3], Bi[3], Dr[3], Di[3], Hr[3], Hi[3]
+ * (D = eps E, H = mu^-1 B, B as returned by bloch_get_eigenvector_B; not divided by the cell volume, like
+ * the reference).  Quadrature: p + 1 Gauss points per direction (MFEM's default for these linear forms). */
+int bloch_get_field_averages(bloch_handle h, int i, double out24[24]);
+
 /* ---- reduced-basis k-sweep: MaxwellDispersion::buildRawBasis / approxEigenfrequencies
  * (meta-material/meta_material_solver.cpp:3132-3305).  Full solves are done only at symmetry (and mid)
  * points and their eigenvectors appended to a raw basis kept on the device; bloch_rb_approx then, for any

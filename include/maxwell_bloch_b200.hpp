@@ -111,6 +111,38 @@ public:
   void SetBravaisLattice(const BravaisLattice &) {}     // reference stores an unused pointer
   void Solve() { check(bloch_solve(h_), "Solve"); }
 
+  // GetFieldAverages (maxwell_bloch.cpp:1550-1632); i counts REAL modes: mode 2b is the complex band b,
+  // mode 2b+1 its partner i*E, i.e. (Er, Ei) -> (-Ei, Er), and likewise for B, D, H
+  void GetFieldAverages(unsigned int i, std::vector<double> &Er, std::vector<double> &Ei, std::vector<double> &Br,
+                        std::vector<double> &Bi, std::vector<double> &Dr, std::vector<double> &Di,
+                        std::vector<double> &Hr, std::vector<double> &Hi) {
+    double o[24];
+    check(bloch_get_field_averages(h_, (int)(i / 2), o), "GetFieldAverages");
+    std::vector<double> *re[4] = {&Er, &Br, &Dr, &Hr}, *im[4] = {&Ei, &Bi, &Di, &Hi};
+    for (int f = 0; f < 4; f++) {
+      re[f]->assign(3, 0.0);
+      im[f]->assign(3, 0.0);
+      for (int k = 0; k < 3; k++) {
+        const double a = o[6 * f + k], b = o[6 * f + 3 + k];
+        (*re[f])[k] = (i % 2) ? -b : a;
+        (*im[f])[k] = (i % 2) ? a : b;
+      }
+    }
+  }
+
+  // reduced-basis sweep pieces of MaxwellDispersion (meta-material/meta_material_solver.cpp:3132-3305)
+  void ReducedBasisClear() { check(bloch_rb_clear(h_), "ReducedBasisClear"); }
+  void ReducedBasisAppend() { check(bloch_rb_append(h_), "ReducedBasisAppend"); }   // bands of the last Solve()
+  int ReducedBasisSize() const { return bloch_rb_size(h_); }
+  // approxEigenfrequencies(omega): nev values omega = sqrt|lambda|, every complex band twice
+  void ApproxEigenfrequencies(const std::vector<double> &kappa, std::vector<double> &omega) {
+    const int nb = (nev_ + 1) / 2;
+    std::vector<double> lam(nb);
+    check(bloch_rb_approx(h_, kappa.data(), lam.data(), nb), "ApproxEigenfrequencies");
+    omega.resize(nev_);
+    for (int i = 0; i < nev_; i++) omega[i] = std::sqrt(std::fabs(lam[i / 2]));
+  }
+
   // nev values, every complex band twice like the reference's real 2N form (maxwell_bloch.cpp:1052-1076)
   void GetEigenvalues(std::vector<double> &eigenvalues) {
     const int nb = (nev_ + 1) / 2;

@@ -281,6 +281,56 @@ void bloch_handle_s::setup() {
   dirty_coef = dirty_kappa = false;
 }
 
+void bloch_handle_s::field_averages(int i, double out24[24]) {
+  cudaStream_t s = stream;
+  if (!avg_ready) {
+    const int q = p + 1;
+    Basis1D B = make_basis(p);
+    std::vector<double> xq, wq, v, dv;
+    detail::gauss_legendre01(q, xq, wq);
+    std::memset(&avg_tabs, 0, sizeof(avg_tabs));
+    for (int a = 0; a < q; a++) {
+      avg_tabs.xq[a] = xq[a];
+      avg_tabs.wq[a] = wq[a];
+      detail::lagrange(B.g, xq[a], v, dv);
+      for (int o = 0; o < p; o++) avg_tabs.bo[a][o] = v[o];
+      detail::lagrange(B.l, xq[a], v, dv);
+      for (int j = 0; j < q; j++) avg_tabs.bc[a][j] = v[j];
+    }
+    std::vector<double> geom((size_t)mesh.n_class * 18);
+    for (int c = 0; c < mesh.n_class; c++) {
+      const double *J = &mesh.J[9 * c];
+      std::vector<double> Jm(J, J + 9), Ji;
+      detail::invert(3, Jm, Ji);
+      for (int k = 0; k < 9; k++) { geom[18 * c + k] = J[k]; geom[18 * c + 9 + k] = Ji[k]; }
+    }
+    d_geom.upload(geom, s);
+    d_x0.upload(mesh.x0, s);
+    BLOCH_CUDA(cudaStreamSynchronize(s));
+    avg_ready = true;
+  }
+  if (dirty_coef || dirty_kappa) setup();
+  d_fa_e.alloc(N); d_fa_b.alloc(Nrt);
+  d_fa_part.alloc((size_t)mesh.n_elem * 12); d_fa_out.alloc(12);
+  BLOCH_CUDA(cudaMemcpy2DAsync(d_fa_e.p, sizeof(D2), d_X.p + i, sizeof(D2) * block, sizeof(D2), N, cudaMemcpyDeviceToDevice, s));
+  apply_curl(d_fa_e.p, d_fa_b.p, 1);
+  BLOCH_CUDA(launch_field_avg(p, avg_tabs, E, d_x0.p, d_geom.p, kappa, d_fa_e.p, 1, d_fa_b.p, 1, 1, d_fa_part.p, d_fa_out.p, s));
+  count_launch(2);
+  D2 o[12];
+  BLOCH_CUDA(cudaMemcpyAsync(o, d_fa_out.p, sizeof(o), cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  // B = i C E / sqrt|lambda| (Bi = Re(C E), Br = -Im(C E), maxwell_bloch.cpp:1432-1457); output order of
+  // the reference's argument list: Er, Ei, Br, Bi, Dr, Di, Hr, Hi
+  const double lam = std::fabs(eigenvalues[i]);
+  const double sc = lam > 0 ? 1.0 / std::sqrt(lam) : 1.0;
+  for (int k = 0; k < 3; k++) {
+    out24[k] = o[k].x;            out24[3 + k] = o[k].y;
+    out24[6 + k] = -sc * o[3 + k].y;  out24[9 + k] = sc * o[3 + k].x;
+    out24[12 + k] = o[6 + k].x;   out24[15 + k] = o[6 + k].y;
+    out24[18 + k] = -sc * o[9 + k].y; out24[21 + k] = sc * o[9 + k].x;
+  }
+}
+
 void bloch_handle_s::apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm) {
   apply_nd_ld(x, nvec, y, nvec, nvec, ca, cm);
 }
@@ -752,6 +802,19 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// ---- field averages: GetFieldAverages (maxwell/maxwell_bloch.cpp:1550-1632) ----
+int bloch_get_field_averages(bloch_handle h, int i, double out24[24]) {
+  API_BEGIN
+  REQUIRE(h && out24, "null argument");
+  REQUIRE(h->device >= 0, "topology-only handle");
+  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  REQUIRE(h->p <= 3, "order not supported");
+  BLOCH_CUDA(cudaSetDevice(h->device));
+  h->field_averages(i, out24);
   return BLOCH_OK;
   API_END
 }

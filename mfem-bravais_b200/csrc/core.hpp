@@ -141,6 +141,13 @@ struct bloch_handle_s {
   int n_init = 0;
   bloch_b200::SolverStats stats;
 
+  // field averages (maxwell_bloch.cpp:1550-1632)
+  bloch_b200::DevBuf<double> d_x0, d_geom;
+  bloch_b200::DevBuf<D2> d_fa_part, d_fa_out, d_fa_e, d_fa_b;
+  bloch_b200::AvgTabs avg_tabs;
+  bool avg_ready = false;
+  void field_averages(int i, double out24[24]);
+
   // reduced-basis sweep (meta-material/meta_material_solver.cpp:3132-3305)
   bloch_b200::DevBuf<D2> d_rb, d_rb_p, d_rb_ap, d_rb_mp, d_rb_tmp;   // raw basis [N][rb_cap] and projected work arrays
   int rb_size = 0, rb_cap = 0;

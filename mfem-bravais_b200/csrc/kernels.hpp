@@ -22,6 +22,13 @@ struct Tabs {
   double om[kMaxP + 1];                 // diagonal 1-D mass weights in mode space
 };
 
+// 1-D tables of the field-average quadrature (field_avg.cu): q = p + 1 Gauss points
+struct AvgTabs {
+  double bo[kMaxP + 1][kMaxP];          // open (Gauss-Lagrange) basis at the quadrature points
+  double bc[kMaxP + 1][kMaxP + 1];      // closed (GLL-Lagrange) basis at the quadrature points
+  double xq[kMaxP + 1], wq[kMaxP + 1];
+};
+
 struct ElemData {            // device pointers, element order = mesh order
   int n_elem, n_class;
   const int *cls;            // [n_elem]
@@ -51,6 +58,12 @@ cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *
 cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
                          double2 *y, int ldy, int nvec, cudaStream_t s, double ca = 1.0, double cm = 0.0);
 // y_rt = (C - i Z_kappa) x_nd  (interpolation into nodal RT dofs, plain stores)
+// Per-vector cell integrals of e^{i kappa.x} {E, C E, eps E, mu^-1 C E} (12 complex numbers per vector,
+// out[nvec][12]); X = ND dofs, Y = RT dofs of (C - i Z_kappa) X; part = scratch [n_elem*nvec][12].
+cudaError_t launch_field_avg(int p, const AvgTabs &A, const ElemData &E, const double *x0, const double *geom,
+                             const double kappa[3], const double2 *X, int ldx, const double2 *Y, int ldy, int nvec,
+                             double2 *part, double2 *out, cudaStream_t s);
+
 cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
                         int ldy, int nvec, cudaStream_t s);
 

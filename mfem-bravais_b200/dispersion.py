@@ -78,6 +78,25 @@ def sharded_sweep(solve_fn, kappas, n_bands, dist=None):
     return out
 
 
+def homogenization_sweep(eq, kappa0, num_beta, n_bands, a=1.0, num_a_per_lambda=10.0, tol=1e-6):
+    """Small-kappa sweep of maxwell_homogenization.cpp:562-593: for i = 1 .. num_beta-1,
+    kappa = kappa0 * 2 pi (i / (num_beta-1)) / (a * num_a_per_lambda); solve, then the field averages
+    of every band (GetFieldAverages).  Returns a list of dicts {kappa, lambda, averages[band]} - the
+    inputs of the reference's effective-medium fit (CalcCoefs, not part of this path)."""
+    eq.SetNumEigs(2 * n_bands)
+    eq.SetAbsoluteTolerance(tol)
+    out = []
+    for i in range(1, num_beta):
+        frac = i / (num_beta - 1) if num_beta > 1 else 1.0
+        kappa = np.asarray(kappa0, float) * (2.0 * np.pi * frac / (a * num_a_per_lambda))
+        eq.SetKappa(kappa)
+        eq.Setup()
+        eq.Solve()
+        out.append({"kappa": kappa, "lambda": eq.band_eigenvalues(),
+                    "averages": [eq.GetFieldAverages(b) for b in range(n_bands)]})
+    return out
+
+
 class MaxwellDispersion:
     """Reduced-basis band-structure sweep: the reference's MaxwellDispersion
     (meta-material/meta_material_solver.cpp:3132-3410).

@@ -247,6 +247,13 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_get_eigenvector_B(self._h, i, dptr(re), dptr(im)), "bloch_get_eigenvector_B")
         return re, im
 
+    def GetFieldAverages(self, i):
+        """GetFieldAverages (maxwell_bloch.cpp:1550-1632) of band i: dict of complex 3-vectors E, B, D, H."""
+        o = np.zeros(24)
+        check(self._L.bloch_get_field_averages(self._h, int(i), dptr(o)), "bloch_get_field_averages")
+        return {"E": o[0:3] + 1j * o[3:6], "B": o[6:9] + 1j * o[9:12],
+                "D": o[12:15] + 1j * o[15:18], "H": o[18:21] + 1j * o[21:24]}
+
     def GetSolverStats(self):
         st = capi.bloch_stats()
         check(self._L.bloch_get_stats(self._h, C.byref(st)))

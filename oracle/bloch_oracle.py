@@ -602,6 +602,47 @@ class BlochOperators:
         rhs = G.conj().T @ (M @ xc.T)
         return (xc.T - G @ lu.solve(np.ascontiguousarray(rhs))).T
 
+    # ---- field averages ----
+    def field_average_forms(self):
+        """The 24 linear forms of SetKappa (maxwell/maxwell_bloch.cpp:211-279), assembled literally:
+        L[w] = int coef(x) {cos, sin}(kappa.x) e_i . w(x) dx with coef in {1, eps} on ND and
+        {1, mu^-1} on RT; quadrature = MFEM's default for VectorFEDomainLFIntegrator
+        (2 * element order -> p + 1 Gauss points per direction).  Returned as complex vectors
+        cos + i sin: dict name -> [3, n]."""
+        s, mesh = self.sp_, self.sp_.mesh
+        ref = s.ref
+        X, W = ref.quadrature(ref.p + 1)
+        nd, _ = ref.nd_shapes(X)
+        rt = ref.rt_shapes(X)
+        out = {k: np.zeros((3, n), complex) for k, n in
+               (("E", s.n_nd), ("D", s.n_nd), ("B", s.n_rt), ("H", s.n_rt))}
+        for e in range(mesh.ne):
+            J = mesh.J[mesh.cls[e]]
+            det = np.linalg.det(J)
+            xq = mesh.x0[e] + X @ J.T
+            ph = np.exp(1j * (xq @ self.kappa)) * W * det                      # [Q]
+            nd_phys = np.einsum("ji,qaj->qai", np.linalg.inv(J), nd)          # J^-T w
+            rt_phys = np.einsum("ij,qaj->qai", J, rt) / det                   # J w / det
+            le = np.einsum("q,qai->ia", ph, nd_phys) * s.nd_sign[e][None, :]
+            lb = np.einsum("q,qai->ia", ph, rt_phys) * s.rt_sign[e][None, :]
+            for i in range(3):
+                np.add.at(out["E"][i], s.nd_gid[e], le[i])
+                np.add.at(out["D"][i], s.nd_gid[e], self.eps[e] * le[i])
+                np.add.at(out["B"][i], s.rt_gid[e], lb[i])
+                np.add.at(out["H"][i], s.rt_gid[e], self.muinv[e] * lb[i])
+        return out
+
+    def field_averages(self, Ec, lam):
+        """GetFieldAverages (maxwell/maxwell_bloch.cpp:1550-1632) of the mode Ec = Er + i Ei with
+        eigenvalue lam.  (Br, Bi) follow GetEigenvectorB (:1432-1457): Bi = Re(C E)/sqrt|lam|,
+        Br = -Im(C E)/sqrt|lam|.  Er_avg = cos.Er - sin.Ei, Ei_avg = sin.Er + cos.Ei etc., i.e. the
+        plain (non-conjugated) product of (cos + i sin) with (Fr + i Fi)."""
+        L = self.field_average_forms()
+        CE = self.C_c() @ Ec
+        sc = 1.0 / np.sqrt(abs(lam)) if abs(lam) > 0 else 1.0
+        Bc = sc * (-CE.imag + 1j * CE.real)
+        return {"E": L["E"] @ Ec, "D": L["D"] @ Ec, "B": L["B"] @ Bc, "H": L["H"] @ Bc}
+
     # ---- eigen-solves ----
     def eig_dense(self, nev):
         """Lowest nev eigenvalues of the pencil (A_c, M_c) restricted to {x : G_c^H M x = 0}
