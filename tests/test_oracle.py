@@ -116,3 +116,26 @@ def test_golden_fixtures_pin_the_oracle():
         assert ops.sp_.n_nd == c["n_nd"]
         w = ops.eig_dense(len(c["eigenvalues"]))
         assert np.allclose(w, c["eigenvalues"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["CUB", "FCC"])
+def test_field_average_forms_on_constant_fields(name):
+    """SetKappa linear forms (maxwell_bloch.cpp:211-279) at kappa = 0: applied to the ND / RT
+    interpolants of a constant vector c they return V c (and eps-/mu^-1-weighted volumes for D, H)."""
+    lat = Lattice(name)
+    mesh = Mesh(lat, 2)
+    s = Spaces(mesh, 2)
+    rng = np.random.default_rng(5)
+    eps, mui = rng.uniform(1, 4, mesh.ne), rng.uniform(0.5, 2, mesh.ne)
+    ops = BlochOperators(s, eps, mui).set_kappa(np.zeros(3))
+    L = ops.field_average_forms()
+    c = np.array([0.3, -1.1, 0.7])
+    eye = np.eye(3)
+    e_nd, b_rt = np.zeros(s.n_nd), np.zeros(s.n_rt)
+    vol_e = np.array([np.linalg.det(mesh.J[k]) for k in mesh.cls])
+    for e in range(mesh.ne):
+        J = mesh.J[mesh.cls[e]]
+        e_nd[s.nd_gid[e]] = s.nd_sign[e] * (eye[s.ref.nd_comp] @ (J.T @ c))                    # t . J^T c
+        b_rt[s.rt_gid[e]] = s.rt_sign[e] * (eye[s.ref.rt_comp] @ (np.linalg.det(J) * np.linalg.inv(J) @ c))  # n . adj(J) c
+    assert np.allclose(L["E"] @ e_nd, mesh.volume * c) and np.allclose(L["B"] @ b_rt, mesh.volume * c)
+    assert np.allclose(L["D"] @ e_nd, (eps * vol_e).sum() * c) and np.allclose(L["H"] @ b_rt, (mui * vol_e).sum() * c)
