@@ -147,6 +147,13 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
 
+/* Multilevel warm start (MaxwellBlochWaveSolver::GetEigenfrequencies, meta-material/meta_material_solver.cpp:
+ * 2731-2881): `fine` must be the uniform refinement of `coarse` (n_sub doubled, same cell, same order, same
+ * device).  Interpolates the coarse handle's eigenvectors onto the fine mesh (the reference's
+ * GetUpdateOperator()->Mult, :2829-2849) and installs them as the fine handle's starting block, so the next
+ * bloch_solve(fine) starts from them (the reference's SetInitialVectors, :2853). */
+int bloch_prolong_eigenvectors(bloch_handle coarse, bloch_handle fine);
+
 /* GetFieldAverages (maxwell/maxwell_bloch.cpp:1550-1632): cell integrals of the full Bloch fields
  * e^{i kappa.x}(Er + i Ei) etc. of band i, out24 = Er[3], Ei[3], Br[3], Bi[3], Dr[3], Di[3], Hr[3], Hi[3]
  * (D = eps E, H = mu^-1 B, B as returned by bloch_get_eigenvector_B; not divided by the cell volume, like

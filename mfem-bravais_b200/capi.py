@@ -76,6 +76,7 @@ SIGNATURES = {
     "bloch_apply_M_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "bloch_prolong_eigenvectors": (C.c_int, [_vp, _vp]),
     "bloch_get_field_averages": (C.c_int, [_vp, C.c_int, _dp]),
     "bloch_rb_clear": (C.c_int, [_vp]),
     "bloch_rb_append": (C.c_int, [_vp]),

@@ -806,6 +806,46 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   API_END
 }
 
+// ---- multilevel warm start: refinement of eigenvectors (meta_material_solver.cpp:2829-2853) ----
+int bloch_prolong_eigenvectors(bloch_handle coarse, bloch_handle fine) {
+  API_BEGIN
+  REQUIRE(coarse && fine && coarse != fine, "bad handles");
+  REQUIRE(coarse->device >= 0 && coarse->device == fine->device, "handles must live on the same device");
+  REQUIRE(coarse->p == fine->p && coarse->p <= 3, "orders differ / not supported");
+  REQUIRE(fine->mesh.n_sub == 2 * coarse->mesh.n_sub && fine->mesh.n_elem == 8 * coarse->mesh.n_elem &&
+              coarse->coarse_hex == fine->coarse_hex && coarse->coarse_vert == fine->coarse_vert,
+          "fine mesh must be the uniform refinement of the coarse one");
+  REQUIRE(coarse->have_vectors > 0, "no coarse eigenvectors (call bloch_solve on the coarse handle first)");
+  BLOCH_CUDA(cudaSetDevice(fine->device));
+  const int p = fine->p, q = p + 1, mb = coarse->block;
+  NdTransfer1D T;
+  std::memset(&T, 0, sizeof(T));
+  std::vector<double> v, dv;
+  for (int a = 0; a < 2; a++) {
+    for (int i = 0; i < q; i++) {
+      detail::lagrange(fine->basis.l, 0.5 * (a + fine->basis.l[i]), v, dv);
+      for (int j = 0; j < q; j++) T.Pc[a][i][j] = std::fabs(v[j]) < 1e-15 ? 0.0 : v[j];
+    }
+    for (int o = 0; o < p; o++) {
+      detail::lagrange(fine->basis.g, 0.5 * (a + fine->basis.g[o]), v, dv);
+      for (int k = 0; k < p; k++) T.Po[a][o][k] = 0.5 * v[k];
+    }
+  }
+  // coarse stream finished -> prolong on the fine stream -> the fine solve warm-starts from d_X
+  BLOCH_CUDA(cudaStreamSynchronize(coarse->stream));
+  fine->d_X.alloc((size_t)fine->N * mb);
+  BLOCH_CUDA(launch_nd_prolong(p, T, fine->d_map_nd.p, coarse->d_map_nd.p, fine->mesh.n_elem, fine->mesh.n_sub,
+                               coarse->d_X.p, mb, fine->d_X.p, mb, mb, fine->stream));
+  fine->count_launch();
+  BLOCH_CUDA(cudaStreamSynchronize(fine->stream));
+  fine->block = mb;
+  fine->have_vectors = coarse->have_vectors;
+  fine->eigenvalues = coarse->eigenvalues;
+  fine->n_init = 0;
+  return BLOCH_OK;
+  API_END
+}
+
 // ---- field averages: GetFieldAverages (maxwell/maxwell_bloch.cpp:1550-1632) ----
 int bloch_get_field_averages(bloch_handle h, int i, double out24[24]) {
   API_BEGIN

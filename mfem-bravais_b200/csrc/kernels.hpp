@@ -29,6 +29,12 @@ struct AvgTabs {
   double xq[kMaxP + 1], wq[kMaxP + 1];
 };
 
+// 1-D tables of the nested ND prolongation (nd_transfer.cu)
+struct NdTransfer1D {
+  double Pc[2][kMaxP + 1][kMaxP + 1];   // closed: c_j((a + l_i)/2)
+  double Po[2][kMaxP][kMaxP];           // open:   o_k((a + g_o)/2) / 2
+};
+
 struct ElemData {            // device pointers, element order = mesh order
   int n_elem, n_class;
   const int *cls;            // [n_elem]
@@ -63,6 +69,10 @@ cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, cons
 cudaError_t launch_field_avg(int p, const AvgTabs &A, const ElemData &E, const double *x0, const double *geom,
                              const double kappa[3], const double2 *X, int ldx, const double2 *Y, int ldy, int nvec,
                              double2 *part, double2 *out, cudaStream_t s);
+
+// xf = nodal interpolation of the coarse ND block xc on the once-refined mesh (n_f = 2 n_c subdivisions)
+cudaError_t launch_nd_prolong(int p, const NdTransfer1D &T, const int32_t *map_f, const int32_t *map_c, int n_elem_f,
+                              int n_f, const double2 *xc, int ldc, double2 *xf, int ldf, int m, cudaStream_t s);
 
 cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
                         int ldy, int nvec, cudaStream_t s);

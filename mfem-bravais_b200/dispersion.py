@@ -97,6 +97,67 @@ def homogenization_sweep(eq, kappa0, num_beta, n_bands, a=1.0, num_a_per_lambda=
     return out
 
 
+class MaxwellBlochWaveSolver:
+    """Multilevel warm start: MaxwellBlochWaveSolver::GetEigenfrequencies
+    (meta-material/meta_material_solver.cpp:2731-2881).  Level l is the cell with n0 * 2**l
+    subdivisions; the coarse level is solved first, its eigenvectors are interpolated to the next
+    level and used as initial vectors there, until sum_i |lambda_i(fine) - lambda_i(coarse)| <= tol
+    or max_lvl levels were used.  `eps_fn(centers) -> eps per element` re-samples the coefficient on
+    every level, like the reference's Coefficient objects."""
+
+    def __init__(self, lattice, n0, order, n_bands, eps_fn=None, muinv_fn=None, max_lvl=3, tol=1e-3,
+                 solver_tol=1e-6, equation_cls=None):
+        from .equation import MaxwellBlochWaveEquation
+        self._cls = equation_cls or MaxwellBlochWaveEquation
+        self.lat, self.n0, self.order, self.nb = lattice, int(n0), int(order), int(n_bands)
+        self.eps_fn, self.muinv_fn = eps_fn, muinv_fn
+        self.max_lvl, self.tol, self.solver_tol = int(max_lvl), float(tol), float(solver_tol)
+        self.kappa = np.zeros(3)
+        self.levels = []
+        self.level_eigs, self.level_iters = [], []
+
+    def _level(self, lvl):
+        while len(self.levels) <= lvl:
+            eq = self._cls(self.lat, self.n0 * 2 ** len(self.levels), self.order)
+            if self.eps_fn is not None:
+                eq.SetMassCoef(self.eps_fn(eq.element_centers()))
+            if self.muinv_fn is not None:
+                eq.SetStiffnessCoef(self.muinv_fn(eq.element_centers()))
+            eq.SetNumEigs(2 * self.nb)
+            eq.SetAbsoluteTolerance(self.solver_tol)
+            self.levels.append(eq)
+        return self.levels[lvl]
+
+    def SetKappa(self, kappa):
+        self.kappa = np.asarray(kappa, float)
+
+    def GetEigenfrequencies(self):
+        eq = self._level(0)
+        eq.SetKappa(self.kappa)
+        eq.Setup()
+        eq.Solve()
+        fine = eq.band_eigenvalues()
+        self.level_eigs, self.level_iters = [fine], [eq.GetSolverStats()["iterations"]]
+        lvl, err = 1, 2.0 * self.tol
+        while lvl < self.max_lvl and err > self.tol:
+            coarse = fine
+            nxt = self._level(lvl)
+            nxt.SetKappa(self.kappa)
+            nxt.Setup()
+            self.levels[lvl - 1].ProlongEigenvectorsTo(nxt)
+            nxt.Solve()
+            fine = nxt.band_eigenvalues()
+            self.level_eigs.append(fine)
+            self.level_iters.append(nxt.GetSolverStats()["iterations"])
+            err = float(np.abs(fine - coarse).sum())
+            lvl += 1
+        self.fine_level = lvl - 1
+        return np.sqrt(np.abs(fine))
+
+    def ReturnFineEigenvector(self, i):
+        return self.levels[self.fine_level].GetEigenvectorE(i)
+
+
 class MaxwellDispersion:
     """Reduced-basis band-structure sweep: the reference's MaxwellDispersion
     (meta-material/meta_material_solver.cpp:3132-3410).

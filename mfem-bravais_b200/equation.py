@@ -219,6 +219,11 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_get_eigenvalues(self._h, dptr(lam), nb), "bloch_get_eigenvalues")
         return lam
 
+    def ProlongEigenvectorsTo(self, fine):
+        """Interpolates this (coarse) equation's eigenvectors onto `fine` (its uniform refinement) and
+        installs them as the starting block of fine.Solve() (meta_material_solver.cpp:2829-2853)."""
+        check(self._L.bloch_prolong_eigenvectors(self._h, fine._h), "bloch_prolong_eigenvectors")
+
     # reduced-basis sweep pieces (MaxwellDispersion, meta_material_solver.cpp:3132-3305)
     def ReducedBasisClear(self):
         check(self._L.bloch_rb_clear(self._h), "bloch_rb_clear")
