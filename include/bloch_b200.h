@@ -147,6 +147,13 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
 
+/* Assembled operators for interchange (the reference's -wm dump of Ar / Ai / M, maxwell_dispersion.cpp:553-590).
+ * which = 0: A = S1 - i beta DKZ (complex Hermitian; Re = the reference's Ar block, Im = its (1,0) block with the
+ * coefficient folded in), which = 1: M = M1(eps) (real).  CSR over the ND dofs of bloch_get_dofmap numbering.
+ * Two calls: assemble (returns nnz), then copy out (im may be NULL).  Host-side merge - a debug path. */
+int bloch_assemble_matrix(bloch_handle h, int which, int64_t *nnz);
+int bloch_get_matrix(bloch_handle h, int64_t *rowptr, int32_t *col, double *re, double *im);
+
 /* Multilevel warm start (MaxwellBlochWaveSolver::GetEigenfrequencies, meta-material/meta_material_solver.cpp:
  * 2731-2881): `fine` must be the uniform refinement of `coarse` (n_sub doubled, same cell, same order, same
  * device).  Interpolates the coarse handle's eigenvectors onto the fine mesh (the reference's

@@ -6,6 +6,7 @@
 // Header-only; link with -lbloch_b200.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <set>
 #include <stdexcept>
@@ -110,6 +111,28 @@ public:
   }
   void SetBravaisLattice(const BravaisLattice &) {}     // reference stores an unused pointer
   void Solve() { check(bloch_solve(h_), "Solve"); }
+
+  // One block of the assembled operators in hypre's IJ text format, as HypreParMatrix::Print writes it
+  // (file <path>.00000: "ilower iupper jlower jupper", then "i j value" lines) - the -wm dump of
+  // maxwell_dispersion.cpp:553-590.  which = 0: A (imag = false: Ar, true: Ai incl. its block coefficient), 1: M.
+  void WriteMatrix(int which, bool imag, const std::string &path) {
+    int64_t nnz = 0;
+    check(bloch_assemble_matrix(h_, which, &nnz), "bloch_assemble_matrix");
+    int64_t n_nd = 0;
+    check(bloch_num_dofs(h_, &n_nd, nullptr, nullptr), "bloch_num_dofs");
+    std::vector<int64_t> ptr(n_nd + 1);
+    std::vector<int32_t> col(nnz);
+    std::vector<double> re(nnz), im(nnz);
+    check(bloch_get_matrix(h_, ptr.data(), col.data(), re.data(), im.data()), "bloch_get_matrix");
+    FILE *f = std::fopen((path + ".00000").c_str(), "w");
+    if (!f) throw Error(("cannot open " + path).c_str());
+    std::fprintf(f, "%lld %lld %lld %lld\n", 0LL, (long long)n_nd - 1, 0LL, (long long)n_nd - 1);
+    const std::vector<double> &v = imag ? im : re;
+    for (int64_t i = 0; i < n_nd; i++)
+      for (int64_t q = ptr[i]; q < ptr[i + 1]; q++)
+        if (!imag || v[q] != 0.0) std::fprintf(f, "%lld %d %.14e\n", (long long)i, col[q], v[q]);
+    std::fclose(f);
+  }
 
   // GetFieldAverages (maxwell_bloch.cpp:1550-1632); i counts REAL modes: mode 2b is the complex band b,
   // mode 2b+1 its partner i*E, i.e. (Er, Ei) -> (-Ei, Er), and likewise for B, D, H

@@ -76,6 +76,8 @@ SIGNATURES = {
     "bloch_apply_M_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "bloch_assemble_matrix": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "bloch_get_matrix": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, _dp]),
     "bloch_prolong_eigenvectors": (C.c_int, [_vp, _vp]),
     "bloch_get_field_averages": (C.c_int, [_vp, C.c_int, _dp]),
     "bloch_rb_clear": (C.c_int, [_vp]),

@@ -3,6 +3,7 @@
 // Setup :337-620, GetEigenvalues :1052-1076, GetEigenvectorE/B :1371-1458.
 #include "core.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -77,6 +78,7 @@ static void build_kernel_maps(bloch_handle_s *h) {
     h->d_tp_loc.upload(loc, h->stream);
     BLOCH_CUDA(cudaStreamSynchronize(h->stream));
   }
+  h->knd_host = knd;
   h->d_map_nd.upload(knd, h->stream);
   h->d_map_rt.upload(krt, h->stream);
   h->d_map_h1.upload(kh1, h->stream);
@@ -279,6 +281,64 @@ void bloch_handle_s::setup() {
     if (mg) mg_setup(mg, this);
   }
   dirty_coef = dirty_kappa = false;
+}
+
+// Assembled A = S1 - i beta DKZ (which = 0) or M = M1(eps) (which = 1) in CSR, for the matrix dump of
+// maxwell_dispersion.cpp:553-590.  The element matrices of every affine class come from the same probe
+// launch Setup() uses for the Jacobi diagonals (the kernels applied to element-local unit vectors); the
+// global rows are then merged on the host.  Debug / interchange path, not used by the solver.
+void bloch_handle_s::assemble(int which) {
+  if (p > 3) throw std::invalid_argument("order not supported");
+  if (dirty_coef || dirty_kappa) setup();
+  cudaStream_t s = stream;
+  const int L = L_nd, nc = mesh.n_class;
+  ProbeWork &pw = probe_nd;                      // built by setup()
+  ElemData Ep = E;
+  Ep.n_elem = nc * L; Ep.cls = pw.cls.p; Ep.eps = pw.one.p; Ep.muinv = pw.one.p; Ep.map_nd = pw.map.p;
+  const size_t xsize = (size_t)nc * L * L;
+  BLOCH_CUDA(cudaMemsetAsync(pw.y.p, 0, sizeof(D2) * xsize, s));
+  BLOCH_CUDA(launch_nd_apply(p, tabs, Ep, pw.x.p, 1, pw.y.p, 1, 1, which == 0 ? 1.0 : 0.0, which == 0 ? 0.0 : 1.0, s));
+  count_launch();
+  std::vector<D2> loc(xsize);                    // loc[(c*L + k)*L + l] = (X_c)[l][k]
+  BLOCH_CUDA(cudaMemcpyAsync(loc.data(), pw.y.p, sizeof(D2) * xsize, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  const std::vector<double> &coef = which == 0 ? muinv : eps;
+  // dof -> its local copies (counting sort)
+  const size_t nloc = (size_t)mesh.n_elem * L;
+  std::vector<int64_t> ptr(N + 1, 0);
+  for (size_t t = 0; t < nloc; t++) ptr[std::abs(knd_host[t])]++;
+  for (long g = 0; g < N; g++) ptr[g + 1] += ptr[g];
+  std::vector<int64_t> where(nloc), fill(ptr.begin(), ptr.end() - 1);
+  for (size_t t = 0; t < nloc; t++) where[fill[std::abs(knd_host[t]) - 1]++] = (int64_t)t;
+  csr_ptr.assign(N + 1, 0);
+  csr_col.clear(); csr_re.clear(); csr_im.clear();
+  struct Ent { int32_t col; double re, im; };
+  std::vector<Ent> row;
+  for (long g = 0; g < N; g++) {
+    row.clear();
+    for (int64_t q = ptr[g]; q < ptr[g + 1]; q++) {
+      const int64_t t = where[q];
+      const int e = (int)(t / L), l = (int)(t - (int64_t)e * L);
+      const int c = mesh.cls[e];
+      const double sl = knd_host[t] < 0 ? -coef[e] : coef[e];
+      for (int k = 0; k < L; k++) {
+        const int32_t sk = knd_host[(size_t)e * L + k];
+        const D2 v = loc[((size_t)c * L + k) * L + l];
+        if (v.x == 0.0 && v.y == 0.0) continue;
+        const double sg = sk < 0 ? -sl : sl;
+        row.push_back({std::abs(sk) - 1, sg * v.x, sg * v.y});
+      }
+    }
+    std::sort(row.begin(), row.end(), [](const Ent &a, const Ent &b) { return a.col < b.col; });
+    for (size_t i = 0; i < row.size();) {
+      size_t j = i;
+      double re = 0, im = 0;
+      while (j < row.size() && row[j].col == row[i].col) { re += row[j].re; im += row[j].im; j++; }
+      csr_col.push_back(row[i].col); csr_re.push_back(re); csr_im.push_back(im);
+      i = j;
+    }
+    csr_ptr[g + 1] = (int64_t)csr_col.size();
+  }
 }
 
 void bloch_handle_s::field_averages(int i, double out24[24]) {
@@ -802,6 +862,30 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// ---- assembled operators (the -wm dump of maxwell_dispersion.cpp:553-590) ----
+int bloch_assemble_matrix(bloch_handle h, int which, int64_t *nnz) {
+  API_BEGIN
+  REQUIRE(h && nnz, "null argument");
+  REQUIRE(h->device >= 0, "topology-only handle");
+  REQUIRE(which == 0 || which == 1, "which must be 0 (A) or 1 (M)");
+  BLOCH_CUDA(cudaSetDevice(h->device));
+  h->assemble(which);
+  *nnz = (int64_t)h->csr_col.size();
+  return BLOCH_OK;
+  API_END
+}
+int bloch_get_matrix(bloch_handle h, int64_t *rowptr, int32_t *col, double *re, double *im) {
+  API_BEGIN
+  REQUIRE(h && rowptr && col && re, "null argument");
+  REQUIRE((long)h->csr_ptr.size() == h->N + 1, "no assembled matrix (call bloch_assemble_matrix first)");
+  std::copy(h->csr_ptr.begin(), h->csr_ptr.end(), rowptr);
+  std::copy(h->csr_col.begin(), h->csr_col.end(), col);
+  std::copy(h->csr_re.begin(), h->csr_re.end(), re);
+  if (im) std::copy(h->csr_im.begin(), h->csr_im.end(), im);
   return BLOCH_OK;
   API_END
 }

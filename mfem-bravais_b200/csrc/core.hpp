@@ -141,6 +141,13 @@ struct bloch_handle_s {
   int n_init = 0;
   bloch_b200::SolverStats stats;
 
+  // assembled operators for the -wm dump (maxwell_dispersion.cpp:553-590)
+  std::vector<int32_t> knd_host;                 // kernel-order ND map (host copy)
+  std::vector<int64_t> csr_ptr;
+  std::vector<int32_t> csr_col;
+  std::vector<double> csr_re, csr_im;
+  void assemble(int which);
+
   // field averages (maxwell_bloch.cpp:1550-1632)
   bloch_b200::DevBuf<double> d_x0, d_geom;
   bloch_b200::DevBuf<D2> d_fa_part, d_fa_out, d_fa_e, d_fa_b;

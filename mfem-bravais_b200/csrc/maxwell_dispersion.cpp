@@ -56,6 +56,7 @@ static void WriteDispersionData(std::ostream &os, int c, const std::string &labe
 
 int main(int argc, char **argv) {
   int bl_type = 1, order = 1, sr = 0, pr = 2, np = 0, nb = 10, dev = -1;
+  bool write_mats = false;
   double a = -1.0;
   std::string out = ".";
   for (int i = 1; i < argc; i++) {
@@ -74,6 +75,7 @@ int main(int argc, char **argv) {
     else if (f == "-nb") nb = std::atoi(next("-nb"));
     else if (f == "-dev") dev = std::atoi(next("-dev"));
     else if (f == "-out") out = next("-out");
+    else if (f == "-wm" || f == "--write-mats") write_mats = true;
     else if (f == "-no-vis" || f == "-no-visit" || f == "-no-wm" || f == "-mp" || f == "-no-mp") {}
     else { std::cerr << "unknown option " << f << std::endl; return 1; }
   }
@@ -114,6 +116,11 @@ int main(int argc, char **argv) {
           } else {
             eq.GetEigenvalues(2 * nb, kappa, nullptr, eigenvalues);
             if (i == 0) sp_eigs[label] = eigenvalues;
+            if (write_mats && label != "-") {            // Ar / Ai / M dump (:553-590), hypre IJ text format
+              eq.WriteMatrix(0, false, out + "/Ar" + label + ".mat");
+              eq.WriteMatrix(0, true, out + "/Ai" + label + ".mat");
+              eq.WriteMatrix(1, false, out + "/M" + label + ".mat");
+            }
           }
           WriteDispersionData(ofs_disp, c++, label, eigenvalues);
         }

@@ -78,6 +78,40 @@ def sharded_sweep(solve_fn, kappas, n_bands, dist=None):
     return out
 
 
+def write_hypre_ij(path, mat, rank=0):
+    """Writes a real scipy sparse matrix the way HypreParMatrix::Print does (hypre_ParCSRMatrixPrintIJ:
+    file `<path>.<rank as %05d>`, header `ilower iupper jlower jupper`, then `i j value` per entry, %.14e)."""
+    m = mat.tocsr()
+    m.sort_indices()
+    fn = "%s.%05d" % (path, rank)
+    with open(fn, "w") as f:
+        f.write("%d %d %d %d\n" % (0, m.shape[0] - 1, 0, m.shape[1] - 1))
+        for i in range(m.shape[0]):
+            for q in range(m.indptr[i], m.indptr[i + 1]):
+                f.write("%d %d %.14e\n" % (i, m.indices[q], m.data[q]))
+    return fn
+
+
+def read_hypre_ij(fn):
+    import scipy.sparse as sp
+    with open(fn) as f:
+        i0, i1, j0, j1 = (int(t) for t in f.readline().split())
+        rows, cols, vals = [], [], []
+        for line in f:
+            a, b, c = line.split()
+            rows.append(int(a)); cols.append(int(b)); vals.append(float(c))
+    return sp.csr_matrix((vals, (rows, cols)), shape=(i1 - i0 + 1, j1 - j0 + 1))
+
+
+def write_matrices(eq, prefix, label=""):
+    """The -wm dump of maxwell_dispersion.cpp:553-590: Ar<label>.mat, Ai<label>.mat, M<label>.mat in
+    hypre IJ text format (Ai = Im(A), i.e. the reference's (1,0) block times its block coefficient)."""
+    A, M = eq.AssembleMatrix("A"), eq.AssembleMatrix("M")
+    return [write_hypre_ij("%s/Ar%s.mat" % (prefix, label), A.real),
+            write_hypre_ij("%s/Ai%s.mat" % (prefix, label), A.imag),
+            write_hypre_ij("%s/M%s.mat" % (prefix, label), M)]
+
+
 def homogenization_sweep(eq, kappa0, num_beta, n_bands, a=1.0, num_a_per_lambda=10.0, tol=1e-6):
     """Small-kappa sweep of maxwell_homogenization.cpp:562-593: for i = 1 .. num_beta-1,
     kappa = kappa0 * 2 pi (i / (num_beta-1)) / (a * num_a_per_lambda); solve, then the field averages

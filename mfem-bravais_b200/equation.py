@@ -219,6 +219,21 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_get_eigenvalues(self._h, dptr(lam), nb), "bloch_get_eigenvalues")
         return lam
 
+    def AssembleMatrix(self, which):
+        """'A' (complex Hermitian S1 - i beta DKZ) or 'M' (real M1(eps)) as scipy CSR - the operators the
+        reference dumps with -wm (maxwell_dispersion.cpp:553-590)."""
+        import scipy.sparse as sp
+        w = {"A": 0, "M": 1}[which]
+        nnz = C.c_int64()
+        check(self._L.bloch_assemble_matrix(self._h, w, C.byref(nnz)), "bloch_assemble_matrix")
+        ptr = np.zeros(self.N + 1, np.int64)
+        col = np.zeros(nnz.value, np.int32)
+        re, im = np.zeros(nnz.value), np.zeros(nnz.value)
+        check(self._L.bloch_get_matrix(self._h, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                       col.ctypes.data_as(C.POINTER(C.c_int32)), dptr(re), dptr(im)), "bloch_get_matrix")
+        data = re + 1j * im if w == 0 else re
+        return sp.csr_matrix((data, col, ptr), shape=(self.N, self.N))
+
     def ProlongEigenvectorsTo(self, fine):
         """Interpolates this (coarse) equation's eigenvectors onto `fine` (its uniform refinement) and
         installs them as the starting block of fine.Solve() (meta_material_solver.cpp:2829-2853)."""

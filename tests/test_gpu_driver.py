@@ -52,3 +52,24 @@ def test_cpp_driver_writes_reference_style_disp_dat(bloch, tmp_path):
     lam = eq.GetEigenvalues(8, L.GetSymmetryPoint(1))
     assert np.allclose(w[2], np.sqrt(np.maximum(lam, 0)), rtol=1e-5, atol=1e-6)
     assert (tmp_path / "stats_0.out").read_text().startswith("Timings:")
+
+
+def test_cpp_driver_matrix_dump(bloch, tmp_path):
+    """-wm: Ar / Ai / M at the labelled k-points in hypre IJ format (maxwell_dispersion.cpp:553-590)"""
+    exe = os.path.join(ROOT, "mfem-bravais_b200", "lib", "maxwell_dispersion_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    r = subprocess.run([exe, "-bl", "1", "-o", "1", "-sr", "0", "-pr", "1", "-p", "2", "-np", "0", "-nb", "2",
+                        "-wm", "-out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    L = bloch.BravaisLattice("CUB")
+    eq = bloch.MaxwellBlochWaveEquation(L, 2, 1)
+    eq.SetMassCoef(bloch.sphere_eps(eq.element_centers()))
+    eq.SetKappa(L.GetSymmetryPoint(L.GetSymmetryPointIndex("X")))
+    eq.Setup()
+    A, M = eq.AssembleMatrix("A"), eq.AssembleMatrix("M")
+    Ar = bloch.read_hypre_ij(str(tmp_path / "ArX.mat.00000"))
+    Ai = bloch.read_hypre_ij(str(tmp_path / "AiX.mat.00000"))
+    Mr = bloch.read_hypre_ij(str(tmp_path / "MX.mat.00000"))
+    assert abs(Ar - A.real).max() < 1e-12 and abs(Ai - A.imag).max() < 1e-12 and abs(Mr - M).max() < 1e-12
+    assert abs(Ai + Ai.T).max() < 1e-12 and abs(Ai).max() > 0          # the beta DKZ block is antisymmetric
