@@ -156,5 +156,115 @@ __device__ __forceinline__ void h1_transform_dir(double2 *sH, const Tabs &T, int
 }
 
 
+// ---- register-resident S0 element operator for one (element, vector) item, P <= 2 ----
+// sin: thread-private shared-memory column (element k at sin[k * STRIDE]) holding the gathered
+// nodal values on entry (overwritten by their mode-space transform); out: S0_e applied, nodal.
+// Returns Re(phi^H S0_e phi) (evaluated in mode space).
+template <int P, int STRIDE>
+__device__ __forceinline__ double s0_item(const Tabs &T, const double *cp, double eps, double2 *sin,
+                                          double2 (&out)[(P + 1) * (P + 1) * (P + 1)]) {
+  constexpr int Q = P + 1;
+  auto IDX = [](int i0, int i1, int i2) { return (i0 * Q + i1) * Q + i2; };
+  // nodal -> mode, direction by direction, in place in the private column
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int sd = d == 0 ? Q * Q : (d == 1 ? Q : 1);
+    const int s1 = d == 0 ? Q : Q * Q, s2 = d == 2 ? Q : 1;
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) {
+        const int base = a * s1 + b * s2;
+        double2 in[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) in[j] = sin[(base + j * sd) * STRIDE];
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int j = 0; j < Q; j++) CFMA(acc, T.TI[r][j], in[j]);
+          sin[(base + r * sd) * STRIDE] = acc;
+        }
+      }
+  }
+  const double kh[3] = {cp[0], cp[1], cp[2]};
+  const double *H = cp + 12;
+#pragma unroll
+  for (int k = 0; k < Q * Q * Q; k++) out[k] = make_double2(0.0, 0.0);
+  double dot = 0.0;
+#pragma unroll
+  for (int i0 = 0; i0 < Q; i0++)
+#pragma unroll
+    for (int i1 = 0; i1 < Q; i1++)
+#pragma unroll
+      for (int i2 = 0; i2 < Q; i2++) {
+        const int i[3] = {i0, i1, i2};
+        const double w = eps * T.om[i0] * T.om[i1] * T.om[i2];
+        const double2 centre = sin[IDX(i0, i1, i2) * STRIDE];
+        double2 F[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          F[d] = make_double2(0.0, 0.0);
+          if (i[d] < P) {
+            F[d].x = kh[d] * centre.y;
+            F[d].y = -kh[d] * centre.x;
+#pragma unroll
+            for (int t = 0; t < Q; t++) {
+              int j[3] = {i0, i1, i2};
+              j[d] = t;
+              const double2 val = sin[IDX(j[0], j[1], j[2]) * STRIDE];
+              CFMA(F[d], T.Dt[i[d]][t], val);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (i[c] < P) {
+            double2 mf;
+            mf.x = w * (H[3 * c] * F[0].x + H[3 * c + 1] * F[1].x + H[3 * c + 2] * F[2].x);
+            mf.y = w * (H[3 * c] * F[0].y + H[3 * c + 1] * F[1].y + H[3 * c + 2] * F[2].y);
+#pragma unroll
+            for (int t = 0; t < Q; t++) {
+              int j[3] = {i0, i1, i2};
+              j[c] = t;
+              CFMA(out[IDX(j[0], j[1], j[2])], T.Dt[i[c]][t], mf);
+            }
+            out[IDX(i0, i1, i2)].x -= kh[c] * mf.y;
+            out[IDX(i0, i1, i2)].y += kh[c] * mf.x;
+          }
+        }
+      }
+  // phi^H S0 phi in mode space
+#pragma unroll
+  for (int k = 0; k < Q * Q * Q; k++) {
+    const double2 a = sin[k * STRIDE];
+    dot = fma(a.x, out[k].x, dot);
+    dot = fma(a.y, out[k].y, dot);
+  }
+  // mode -> nodal (adjoint transform) in registers
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int sd = d == 0 ? Q * Q : (d == 1 ? Q : 1);
+    const int s1 = d == 0 ? Q : Q * Q, s2 = d == 2 ? Q : 1;
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) {
+        const int base = a * s1 + b * s2;
+        double2 in[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) in[j] = out[base + j * sd];
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int j = 0; j < Q; j++) CFMA(acc, T.TI[j][r], in[j]);
+          out[base + r * sd] = acc;
+        }
+      }
+  }
+  return dot;
+}
+
 }  // namespace dev
 }  // namespace bloch_b200

@@ -537,6 +537,117 @@ cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int l
   return cudaGetLastError();
 }
 
+// y += ca * eps_e * S_c x_e with the dense element matrix S_c of the element's affine class (L x L complex,
+// row-major S[l][k], from the Setup probe).  Same flops as the sum-factorised S0 at p <= 2 but only one
+// barrier and ~L dependent steps per thread: the low-LATENCY variant for the coarse multigrid levels,
+// where a launch has a few dozen CTAs and the thread-per-item kernel's serial chain is the whole cost.
+// lane <-> item, warp <-> a chunk of output rows; S is read with (half-)warp-uniform addresses.
+template <int P, int NWD>
+__global__ void __launch_bounds__(NWD * 32)
+k_h1_dense(const ElemData E, const double2 *__restrict__ S, const double2 *__restrict__ X,
+           double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca) {
+  using D = Dim<P>;
+  constexpr int L = D::LH1;
+  constexpr int RPW = (L + NWD - 1) / NWD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *sX = reinterpret_cast<double2 *>(smem_raw);      // [L][32] gathered inputs
+  double2 *sS = sX + L * 32;                                  // [n_class][L][L] class matrices
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < E.n_class * L * L; i += NWD * 32) sS[i] = S[i];
+  const long item = (long)blockIdx.x * 32 + lane;
+  const bool active = item < n_items;
+  const int e = active ? (int)(item / m) : 0;
+  const int v = active ? (int)(item - (long)e * m) : 0;
+  const int32_t *mh = E.map_h1 + (long)e * L;
+  for (int k = warp; k < L; k += NWD)
+    sX[k * 32 + lane] = active ? X[(long)(__ldg(mh + k) - 1) * ldx + v] : make_double2(0.0, 0.0);
+  __syncthreads();
+  if (!active) return;
+  const double2 *Sc = sS + E.cls[e] * L * L;
+  const int row0 = warp * RPW;
+  double2 acc[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; r++) acc[r] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < L; k++) {
+    const double2 xk = sX[k * 32 + lane];
+#pragma unroll
+    for (int r = 0; r < RPW; r++) {
+      if (row0 + r < L) {
+        const double2 a = Sc[(row0 + r) * L + k];
+        acc[r].x = fma(a.x, xk.x, acc[r].x); acc[r].x = fma(-a.y, xk.y, acc[r].x);
+        acc[r].y = fma(a.x, xk.y, acc[r].y); acc[r].y = fma(a.y, xk.x, acc[r].y);
+      }
+    }
+  }
+  const double cf = ca * E.eps[e];
+  double *Yd = reinterpret_cast<double *>(Y);
+#pragma unroll
+  for (int r = 0; r < RPW; r++) {
+    if (row0 + r < L) {
+      const long o = 2 * ((long)(__ldg(mh + row0 + r) - 1) * ldy + v);
+      atomicAdd(Yd + o, cf * acc[r].x);
+      atomicAdd(Yd + o + 1, cf * acc[r].y);
+    }
+  }
+}
+
+// y += ca * S0_e x with S0 = G^H M1(eps) G: one THREAD per (element, vector) item, the whole element
+// operator in registers (s0_item, elem_device.cuh), no block-level synchronisation after the class
+// parameters are staged.  Used for the stiffness-only scalar applies of the multigrid V-cycle (p <= 2),
+// where the cooperative tile kernel is bound by its barriers rather than by arithmetic.
+// EVEC: instead of the atomic scatter, the element-local result goes to the E-vector Y[(e*L + k)*m + v]
+// with plain coalesced stores; launch_h1_reduce then sums the copies of every dof.
+template <int P, int NT, bool EVEC>
+__global__ void __launch_bounds__(NT)
+k_h1_s0_item(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restrict__ X,
+             double2 *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca) {
+  using D = Dim<P>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *scol = reinterpret_cast<double2 *>(smem_raw) + threadIdx.x;
+  double *sCP = reinterpret_cast<double *>(reinterpret_cast<double2 *>(smem_raw) + D::LH1 * NT);
+  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NT) sCP[i] = E.cpar[i];
+  __syncthreads();
+  const long item = (long)blockIdx.x * NT + threadIdx.x;
+  if (item >= n_items) return;
+  const int e = (int)(item / m);
+  const int v = (int)(item - (long)e * m);
+  const int32_t *mh = E.map_h1 + (long)e * D::LH1;
+#pragma unroll
+  for (int k = 0; k < D::LH1; k++) scol[k * NT] = X[(long)(__ldg(mh + k) - 1) * ldx + v];
+  double2 out[D::LH1];
+  s0_item<P, NT>(T, sCP + kClassParDoubles * E.cls[e], ca * E.eps[e], scol, out);
+  if (EVEC) {
+#pragma unroll
+    for (int k = 0; k < D::LH1; k++) Y[((long)e * D::LH1 + k) * m + v] = out[k];
+    return;
+  }
+  double *Yd = reinterpret_cast<double *>(Y);
+#pragma unroll
+  for (int k = 0; k < D::LH1; k++) {
+    const long o = 2 * ((long)(__ldg(mh + k) - 1) * ldy + v);
+    atomicAdd(Yd + o, out[k].x);
+    atomicAdd(Yd + o + 1, out[k].y);
+  }
+}
+
+// y[g][v] = sum over the local copies of H1 dof g of the E-vector Z (ptr/loc: dof -> 1-based positions e*L + k)
+__global__ void k_h1_reduce(const int *__restrict__ ptr, const int32_t *__restrict__ loc,
+                            const double2 *__restrict__ Z, double2 *__restrict__ Y, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long g = t / m;
+    const int v = (int)(t - g * m);
+    const int b = __ldg(ptr + g), e = __ldg(ptr + g + 1);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int q = b; q < e; q++) {
+      const double2 z = Z[(long)(__ldg(loc + q) - 1) * m + v];
+      acc.x += z.x; acc.y += z.y;
+    }
+    Y[t] = acc;
+  }
+}
+
 template <int P, int NW>
 cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,
                     int ldy, int nvec, double ca, double cm, cudaStream_t s) {
@@ -560,6 +671,28 @@ cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x
   }
   const long n_items = (long)E.n_elem * nvec;
   const unsigned grid = (unsigned)((n_items + 31) / 32);
+  if constexpr (P <= 2) {
+    static const int item_kernel = [] { const char *e = std::getenv("BLOCH_H1_ITEM"); return e ? std::atoi(e) : 1; }();
+    const bool mode_evec = mode == 4;
+    if ((mode == 3 || mode == 4) && cm == 0.0 && item_kernel) {
+      constexpr int NT = 64;
+      const size_t sm = (size_t)D::LH1 * NT * sizeof(double2) + (size_t)E.n_class * kClassParDoubles * sizeof(double);
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaError_t err = cudaFuncSetAttribute(k_h1_s0_item<P, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(k_h1_s0_item<P, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (err != cudaSuccess) return err;
+        attr2 = true;
+      }
+      if (mode_evec)
+        k_h1_s0_item<P, NT, true><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca);
+      else
+        k_h1_s0_item<P, NT, false><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca);
+      return cudaGetLastError();
+    }
+  }
+  if (mode == 4) return cudaErrorInvalidValue;   // E-vector variant exists for the item kernel only
   if (mode == 3) {
     k_h1_op<P, NW, 3><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca, cm);
     return cudaGetLastError();
@@ -633,6 +766,38 @@ cudaError_t launch_h1_op(int p, int mode, const Tabs &T, const ElemData &E, cons
     case 4: return h1_op_t<4, 15>(mode, T, E, x, ldx, y, ldy, nvec, ca, cm, s);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_h1_dense(int p, const ElemData &E, const double2 *S, const double2 *x, int ldx, double2 *y,
+                            int ldy, int nvec, double ca, cudaStream_t s) {
+  const long n_items = (long)E.n_elem * nvec;
+  const unsigned grid = (unsigned)((n_items + 31) / 32);
+  const int L = (p + 1) * (p + 1) * (p + 1);
+  const size_t smem = ((size_t)L * 32 + (size_t)E.n_class * L * L) * sizeof(double2);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(k_h1_dense<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(k_h1_dense<2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  switch (p) {
+    case 1: k_h1_dense<1, 4><<<grid, 4 * 32, smem, s>>>(E, S, x, y, nvec, ldx, ldy, n_items, ca); break;
+    case 2: k_h1_dense<2, 9><<<grid, 9 * 32, smem, s>>>(E, S, x, y, nvec, ldx, ldy, n_items, ca); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_h1_reduce(const int *ptr, const int32_t *loc, const double2 *Z, double2 *Y, long n, int m,
+                             cudaStream_t s) {
+  long g = (n * m + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  k_h1_reduce<<<(unsigned)g, 256, 0, s>>>(ptr, loc, Z, Y, n, m);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y,

@@ -70,6 +70,15 @@ cudaError_t launch_field_avg(int p, const AvgTabs &A, const ElemData &E, const d
                              const double kappa[3], const double2 *X, int ldx, const double2 *Y, int ldy, int nvec,
                              double2 *part, double2 *out, cudaStream_t s);
 
+// y += ca * eps_e * S_class(e) x_e with dense element matrices S [n_class][L_h1][L_h1] (row-major), p <= 2
+cudaError_t launch_h1_dense(int p, const ElemData &E, const double2 *S, const double2 *x, int ldx, double2 *y,
+                            int ldy, int nvec, double ca, cudaStream_t s);
+
+// launch_h1_op mode 4 (p <= 2, cm == 0): like mode 3 but the element-local results are stored to the E-vector
+// y[(e*L_h1 + k)*nvec + v] (no atomics, y need not be zeroed); launch_h1_reduce sums the copies of each dof.
+cudaError_t launch_h1_reduce(const int *ptr, const int32_t *loc, const double2 *Z, double2 *Y, long n, int m,
+                             cudaStream_t s);
+
 // xf = nodal interpolation of the coarse ND block xc on the once-refined mesh (n_f = 2 n_c subdivisions)
 cudaError_t launch_nd_prolong(int p, const NdTransfer1D &T, const int32_t *map_f, const int32_t *map_c, int n_elem_f,
                               int n_f, const double2 *xc, int ldc, double2 *xf, int ldf, int m, cudaStream_t s);

@@ -15,6 +15,7 @@
 #include <deque>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <functional>
 
 #include "core.hpp"
@@ -127,13 +128,26 @@ __global__ void k_dense_apply(const D2 *__restrict__ inv, const D2 *__restrict__
   const int total = n * m;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int r = t / m, v = t - r * m;
-    D2 acc = make_double2(0.0, 0.0);
-    for (int c = 0; c < n; c++) {
-      const D2 a = inv[(long)r * n + c], y = b[(long)c * m + v];
-      acc.x = fma(a.x, y.x, acc.x); acc.x = fma(-a.y, y.y, acc.x);
-      acc.y = fma(a.x, y.y, acc.y); acc.y = fma(a.y, y.x, acc.y);
+    D2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+    int c = 0;
+    for (; c + 8 <= n; c += 8) {               // 8 independent load pairs in flight per step
+      D2 a[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { a[u] = __ldg(inv + (long)r * n + c + u); y[u] = __ldg(b + (long)(c + u) * m + v); }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        acc0.x = fma(a[u].x, y[u].x, acc0.x); acc0.x = fma(-a[u].y, y[u].y, acc0.x);
+        acc0.y = fma(a[u].x, y[u].y, acc0.y); acc0.y = fma(a[u].y, y[u].x, acc0.y);
+        acc1.x = fma(a[u + 1].x, y[u + 1].x, acc1.x); acc1.x = fma(-a[u + 1].y, y[u + 1].y, acc1.x);
+        acc1.y = fma(a[u + 1].x, y[u + 1].y, acc1.y); acc1.y = fma(a[u + 1].y, y[u + 1].x, acc1.y);
+      }
     }
-    x[t] = acc;
+    for (; c < n; c++) {
+      const D2 a = inv[(long)r * n + c], y = b[(long)c * m + v];
+      acc0.x = fma(a.x, y.x, acc0.x); acc0.x = fma(-a.y, y.y, acc0.x);
+      acc0.y = fma(a.x, y.y, acc0.y); acc0.y = fma(a.y, y.x, acc0.y);
+    }
+    x[t] = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
   }
 }
 // r = b - q
@@ -202,6 +216,218 @@ __global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__r
   }
 }
 
+
+// ---- fused variants (BLOCH_MG_FUSED, default on): fewer, fatter graph nodes --------------------
+// The V-cycle at these sizes is a chain of ~70 dependent few-microsecond nodes per PCG iteration,
+// i.e. bound by node-to-node latency.  Invariant used below: every operator-output buffer (level q,
+// the fine qvec, every coarse b) is ZERO between uses - the kernel that consumes it clears it -
+// so no memset node precedes the scatter-add kernels.
+
+// pre-smoothing from a zero guess: r = b ; d = c0 jac b ; x = d
+__global__ void k_cheb_first_b(const double *__restrict__ jac, const D2 *__restrict__ b, D2 *__restrict__ r,
+                               D2 *__restrict__ d, D2 *__restrict__ x, double c0, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[t / m];
+    const D2 v = b[t];
+    const D2 o = make_double2(s * v.x, s * v.y);
+    r[t] = v; d[t] = o; x[t] = o;
+  }
+}
+// r -= q ; q = 0 ; d = a d + b jac r ; x += d
+__global__ void k_cheb_step_z(const double *__restrict__ jac, D2 *__restrict__ q, D2 *__restrict__ r,
+                              D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = b * jac[t / m];
+    const D2 qq = q[t];
+    q[t] = make_double2(0.0, 0.0);
+    D2 rr = r[t];
+    rr.x -= qq.x; rr.y -= qq.y;
+    r[t] = rr;
+    D2 dd = d[t];
+    dd.x = a * dd.x + s * rr.x; dd.y = a * dd.y + s * rr.y;
+    d[t] = dd;
+    D2 xx = x[t];
+    xx.x += dd.x; xx.y += dd.y;
+    x[t] = xx;
+  }
+}
+// r = b - q ; q = 0
+__global__ void k_resid_z(const D2 *__restrict__ b, D2 *__restrict__ q, D2 *__restrict__ r, long total) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const D2 bb = b[t], qq = q[t];
+    q[t] = make_double2(0.0, 0.0);
+    r[t] = make_double2(bb.x - qq.x, bb.y - qq.y);
+  }
+}
+// post-smoothing start: r = b - q ; q = 0 ; (b = 0) ; d = c0 jac r ; x += d
+__global__ void k_resid_cheb_first(const double *__restrict__ jac, D2 *__restrict__ b, D2 *__restrict__ q,
+                                   D2 *__restrict__ r, D2 *__restrict__ d, D2 *__restrict__ x, double c0, long n,
+                                   int m, int clear_b) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[t / m];
+    const D2 bb = b[t], qq = q[t];
+    q[t] = make_double2(0.0, 0.0);
+    if (clear_b) b[t] = make_double2(0.0, 0.0);
+    const D2 rr = make_double2(bb.x - qq.x, bb.y - qq.y);
+    r[t] = rr;
+    const D2 o = make_double2(s * rr.x, s * rr.y);
+    d[t] = o;
+    D2 xx = x[t];
+    xx.x += o.x; xx.y += o.y;
+    x[t] = xx;
+  }
+}
+// xf[g][v] += interpolation of the parent's polynomial at fine dof g, evaluated once per dof through its
+// representative local copy rep[g] = e*L + i (the copies agree: conforming spaces).  No atomics, no
+// duplicate work.  `zero` (optional): buffer cleared as a side job.
+template <int P>
+__global__ void k_h1_prolong_rep(const __grid_constant__ Transfer1D T, const int32_t *__restrict__ rep,
+                                 const int32_t *__restrict__ map_c, long n0_f, int n_f,
+                                 const D2 *__restrict__ xc, D2 *__restrict__ xf, int m, D2 *__restrict__ zero,
+                                 long zero_count) {
+  constexpr int Q = P + 1, L = Q * Q * Q;
+  const long total = n0_f * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % m);
+    const long g = t / m;
+    const int ei = __ldg(rep + g);
+    const int i = ei % L, e = ei / L;
+    const int i0 = i / (Q * Q), i1 = (i / Q) % Q, i2 = i % Q;
+    int par, a0, a1, a2;
+    parent_of(e, n_f, par, a0, a1, a2);
+    const int32_t *mc = map_c + (long)par * L;
+    D2 acc = make_double2(0.0, 0.0);
+    for (int j0 = 0; j0 < Q; j0++) {
+      const double w0 = T.P[a0][i0][j0];
+      if (w0 == 0.0) continue;
+      for (int j1 = 0; j1 < Q; j1++) {
+        const double w1 = w0 * T.P[a1][i1][j1];
+        if (w1 == 0.0) continue;
+        for (int j2 = 0; j2 < Q; j2++) {
+          const double w = w1 * T.P[a2][i2][j2];
+          if (w == 0.0) continue;
+          const D2 c = xc[(long)(__ldg(mc + (j0 * Q + j1) * Q + j2) - 1) * m + v];
+          acc.x = fma(w, c.x, acc.x); acc.y = fma(w, c.y, acc.y);
+        }
+      }
+    }
+    D2 x = xf[t];
+    x.x += acc.x; x.y += acc.y;
+    xf[t] = x;
+  }
+  if (zero)
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < zero_count; t += (long)gridDim.x * blockDim.x)
+      zero[t] = make_double2(0.0, 0.0);
+}
+
+// ---- PCG scalars without memset / atomics on global memory: every dot product is written as
+// per-block partial sums part[block][m]; consumers add the PCG_BLOCKS partials themselves. ----
+constexpr int PCG_BLOCKS = 148;
+// all threads take part: thread t adds the partials of column t % m from blocks t / m, t / m + T / m, ...
+// (callers __syncthreads() afterwards; tot must not alias other live shared data)
+__device__ __forceinline__ void col_totals(const double *__restrict__ part, int m, double *tot /* smem [m] */) {
+  for (int j = threadIdx.x; j < m; j += blockDim.x) tot[j] = 0.0;
+  __syncthreads();
+  const int per = blockDim.x / m;              // threads per column
+  if (per >= 1 && (int)threadIdx.x < per * m) {
+    const int j = threadIdx.x % m, b0 = threadIdx.x / m;
+    double sum = 0.0;
+    for (int b = b0; b < PCG_BLOCKS; b += per) sum += part[b * m + j];
+    atomicAdd(&tot[j], sum);
+  } else if (per < 1) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      double sum = 0.0;
+      for (int b = 0; b < PCG_BLOCKS; b++) sum += part[b * m + j];
+      tot[j] = sum;
+    }
+  }
+}
+// part[block][j] = partial Re <A_j, B_j>
+__global__ void __launch_bounds__(TPB) k_dot_part(const D2 *__restrict__ A, const D2 *__restrict__ B, long n, int m,
+                                                  double *__restrict__ part) {
+  extern __shared__ double sm[];
+  const long total = n * m, usable = ((long)PCG_BLOCKS * TPB / m) * m;
+  const long start = blockIdx.x * (long)TPB + threadIdx.x;
+  for (int j = threadIdx.x; j < m; j += TPB) sm[j] = 0.0;
+  __syncthreads();
+  if (start < usable) {
+    double acc = 0.0;
+    for (long t = start; t < total; t += usable) {
+      const D2 a = A[t], b = B[t];
+      acc = fma(a.x, b.x, acc);
+      acc = fma(a.y, b.y, acc);
+    }
+    atomicAdd(&sm[start % m], acc);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += TPB) part[blockIdx.x * m + j] = sm[j];
+}
+// alpha = <r,z> / <p,q> ; phi += alpha p ; r -= alpha q ; q = 0 ; part_rr = partial |r|^2 ; block 0 saves <r,z>
+__global__ void __launch_bounds__(TPB) k_pcg_a(const D2 *__restrict__ p, D2 *__restrict__ q, D2 *__restrict__ phi,
+                                               D2 *__restrict__ r, const double *__restrict__ part_rz,
+                                               const double *__restrict__ part_pq, double *__restrict__ part_rr,
+                                               double *__restrict__ rz_saved, long n, int m) {
+  extern __shared__ double sm[];            // rz[m] | pq[m] | rr[m]
+  double *trz = sm, *tpq = sm + m, *trr = sm + 2 * m;
+  col_totals(part_rz, m, trz);
+  col_totals(part_pq, m, tpq);
+  for (int j = threadIdx.x; j < m; j += TPB) trr[j] = 0.0;
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < m; j += TPB) rz_saved[j] = trz[j];
+  const long total = n * m, usable = ((long)PCG_BLOCKS * TPB / m) * m;
+  const long start = blockIdx.x * (long)TPB + threadIdx.x;
+  if (start < usable) {
+    const int j = (int)(start % m);
+    const double alpha = tpq[j] != 0.0 ? trz[j] / tpq[j] : 0.0;
+    double acc = 0.0;
+    for (long t = start; t < total; t += usable) {
+      const D2 pp = p[t], qq = q[t];
+      q[t] = make_double2(0.0, 0.0);
+      D2 x = phi[t];
+      x.x = fma(alpha, pp.x, x.x); x.y = fma(alpha, pp.y, x.y);
+      phi[t] = x;
+      D2 rr = r[t];
+      rr.x = fma(-alpha, qq.x, rr.x); rr.y = fma(-alpha, qq.y, rr.y);
+      r[t] = rr;
+      acc = fma(rr.x, rr.x, acc);
+      acc = fma(rr.y, rr.y, acc);
+    }
+    atomicAdd(&trr[j], acc);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < m; j += TPB) part_rr[blockIdx.x * m + j] = trr[j];
+}
+// beta = <r,z>_new / <r,z>_old ; p = z + beta p
+__global__ void __launch_bounds__(TPB) k_pcg_b(const D2 *__restrict__ z, D2 *__restrict__ p,
+                                               const double *__restrict__ part_rzn, const double *__restrict__ rz_saved,
+                                               long n, int m) {
+  extern __shared__ double sm[];
+  col_totals(part_rzn, m, sm);
+  __syncthreads();
+  const long total = n * m, usable = ((long)PCG_BLOCKS * TPB / m) * m;
+  const long start = blockIdx.x * (long)TPB + threadIdx.x;
+  if (start < usable) {
+    const int j = (int)(start % m);
+    const double beta = rz_saved[j] != 0.0 ? sm[j] / rz_saved[j] : 0.0;
+    for (long t = start; t < total; t += usable) {
+      const D2 zz = z[t];
+      D2 pp = p[t];
+      pp.x = fma(beta, pp.x, zz.x); pp.y = fma(beta, pp.y, zz.y);
+      p[t] = pp;
+    }
+  }
+}
+
+template <int P>
+void prolong_rep_t(const Transfer1D &T, const int32_t *rep, const int32_t *mc, long n0f, int nf, const D2 *xc, D2 *xf,
+                   int m, D2 *zero, long zero_count, cudaStream_t s) {
+  k_h1_prolong_rep<P><<<grid_for(n0f * m), TPB, 0, s>>>(T, rep, mc, n0f, nf, xc, xf, m, zero, zero_count);
+}
+
 template <int P>
 void prolong_t(const Transfer1D &T, const int32_t *mf, const int32_t *mc, int nef, int nf, const D2 *xc, D2 *xf, int m, cudaStream_t s) {
   constexpr int L = (P + 1) * (P + 1) * (P + 1);
@@ -236,6 +462,13 @@ struct H1Level {
   DevBuf<D2> x, b, r, d, q;           // V-cycle work vectors, N0 x m
   DevBuf<D2> inv, dI, dA;             // dense inverse on the coarsest level (+ identity / operator scratch)
   DevBuf<double> dloc;                // element-local diagonals (scratch)
+  DevBuf<int> tp_ptr;                 // transpose of map_h1: dof -> its local copies (atomic-free apply)
+  DevBuf<int32_t> tp_loc;
+  DevBuf<D2> evec;                    // E-vector [n_elem * L][m]
+  bool use_evec = false;
+  DevBuf<D2> Sloc;                    // dense element matrices per class [n_class][L][L] (small levels, p <= 2)
+  bool have_S = false;
+  DevBuf<int32_t> rep;                // one (element, local index) copy e*L + i per dof (owner of the prolongation)
   bool dense = false;
 };
 
@@ -245,6 +478,9 @@ struct H1Multigrid {
   int m_alloc = 0;
   DevBuf<D2> z, pvec, qvec;           // PCG vectors on the fine level
   DevBuf<double> scal;                // rz | pq | rz_new | rr | alpha | beta  (m each) + 2m sums
+  DevBuf<double> part;                // fused path: per-block partial dots rz | pq | rr (PCG_BLOCKS x m each) + saved <r,z>
+  int zero_m = 0;
+  bool zero_valid = false;            // fused path: operator-output buffers are known to be zero
   // CUDA graphs of the two halves of one PCG iteration (re-captured after every mg_setup: the
   // Chebyshev coefficients are kernel arguments captured by value)
   cudaGraphExec_t gA = nullptr, gB = nullptr;
@@ -263,11 +499,14 @@ static void alloc_work(H1Multigrid *mg, int m) {
   for (auto &L : mg->lev) {
     const size_t sz = (size_t)L.N0 * m;
     L.x.alloc(sz); L.b.alloc(sz); L.r.alloc(sz); L.d.alloc(sz); L.q.alloc(sz);
+    if (L.use_evec) L.evec.alloc(L.tp_loc.n * (size_t)m);
   }
   const size_t sz0 = (size_t)mg->lev[0].N0 * m;
   mg->z.alloc(sz0); mg->pvec.alloc(sz0); mg->qvec.alloc(sz0);
   mg->scal.alloc(8 * (size_t)m);
+  mg->part.alloc((size_t)4 * PCG_BLOCKS * m + m);
   mg->m_alloc = m;
+  mg->zero_valid = false;
 }
 
 H1Multigrid *mg_create(bloch_handle_s *h) {
@@ -309,6 +548,42 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
     h_sync(s);
     if (L.N0 <= 8) break;
   }
+  // transpose maps for the atomic-free operator apply (element-local results + owner reduction)
+  {
+    static const double evec_min = env_double("BLOCH_H1_EVEC_MIN_ELEMS", 1024.0);
+    static const bool evec_on = env_double("BLOCH_H1_EVEC", 1.0) != 0.0;
+    for (size_t l = 0; l < mg->lev.size(); l++) {
+      H1Level &L = mg->lev[l];
+      const std::vector<int32_t> &nat = l == 0 ? h->maps.h1 : L.maps.h1;
+      const long ne = l == 0 ? h->mesh.n_elem : L.mesh.n_elem;
+      const int LH = h->L_h1;
+      L.use_evec = evec_on && p <= 2 && ne >= (long)evec_min;
+      // kernel local order k = (i0*Q + i1)*Q + i2  <->  natural i0 + Q*(i1 + Q*i2)
+      auto gid = [&](long e, int k) {
+        const int i0 = k / (Q * Q), i1 = (k / Q) % Q, i2 = k % Q;
+        return (long)nat[(size_t)e * LH + i0 + Q * (i1 + Q * i2)] - 1;
+      };
+      {   // representative copy of every dof (prolongation owner)
+        std::vector<int32_t> rep(L.N0, 0);
+        for (long e = 0; e < ne; e++)
+          for (int k = 0; k < LH; k++) rep[gid(e, k)] = (int32_t)(e * LH + k);
+        L.rep.upload(rep, s);
+        h_sync(s);
+      }
+      if (!L.use_evec) continue;
+      std::vector<int> ptr(L.N0 + 1, 0);
+      for (long e = 0; e < ne; e++)
+        for (int k = 0; k < LH; k++) ptr[gid(e, k) + 1]++;
+      for (long g = 0; g < L.N0; g++) ptr[g + 1] += ptr[g];
+      std::vector<int32_t> loc((size_t)ne * LH);
+      std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+      for (long e = 0; e < ne; e++)
+        for (int k = 0; k < LH; k++) loc[fill[gid(e, k)]++] = (int32_t)(e * LH + k + 1);
+      L.tp_ptr.upload(ptr, s);
+      L.tp_loc.upload(loc, s);
+      h_sync(s);
+    }
+  }
   // multiplicity weights of every level that restricts (all but the coarsest)
   for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
     H1Level &L = mg->lev[l];
@@ -326,7 +601,8 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
 void mg_destroy(H1Multigrid *mg) { delete mg; }
 
 // element-local diagonal of S0 per class on one level (probe launch of the production kernel)
-static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound);
+static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound,
+                        std::vector<D2> *Sloc = nullptr);
 
 void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
   cudaStream_t s = h->stream;
@@ -370,7 +646,11 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     // Jacobi diagonal and the rigorous local bound of lambda_max(D^-1 S0)
     std::vector<double> dloc;
     double bound = 0.0;
-    probe_level(h, E, dloc, &bound);
+    static const double dense_max = env_double("BLOCH_H1_DENSE_MAX_ELEMS", 1023.0);
+    std::vector<D2> Sl;
+    probe_level(h, E, dloc, &bound, (p <= 2 && E.n_elem <= (int)dense_max) ? &Sl : nullptr);
+    L.have_S = !Sl.empty();
+    if (L.have_S) L.Sloc.upload(Sl, s);
     L.lmax = 1.05 * bound;
     DevBuf<double> &dl = L.dloc;
     dl.upload(dloc, s);
@@ -433,7 +713,8 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
   }
 }
 
-static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound) {
+static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound,
+                        std::vector<D2> *Sloc) {
   // same probe problem as Setup() (core.cu): one private element per local unit vector; the probe
   // buffers were built there and are reused (no allocation per k-point)
   const int nc = Elev.n_class, L = h->L_h1;
@@ -453,6 +734,12 @@ static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<dou
   for (int c = 0; c < nc; c++) {
     for (int k = 0; k < L; k++) dloc[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
     if (bound) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
+  }
+  if (Sloc) {   // y[(c*L + k)*L + l] = S_c[l][k]  ->  row-major S_c[l][k]
+    Sloc->resize((size_t)nc * L * L);
+    for (int c = 0; c < nc; c++)
+      for (int k = 0; k < L; k++)
+        for (int l = 0; l < L; l++) (*Sloc)[((size_t)c * L + l) * L + k] = y[((size_t)(c * L + k)) * L + l];
   }
 }
 
@@ -529,8 +816,201 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   chebyshev(h, L, L.x.p, m, deg, ratio, true);
 }
 
+
+// ---- fused V-cycle (see the kernel block above for the zero-buffer invariant) ----
+static void apply_nz(bloch_handle_s *h, H1Level &L, const D2 *x, D2 *y, int m) {   // y must be zero on entry
+  if (L.use_evec) {   // atomic-free: element-local results, then every dof sums its copies (y is overwritten)
+    BLOCH_CUDA(launch_h1_op(h->p, 4, h->tabs, L.E, x, m, L.evec.p, m, m, h->stream, 1.0, 0.0));
+    BLOCH_CUDA(launch_h1_reduce(L.tp_ptr.p, L.tp_loc.p, L.evec.p, y, L.N0, m, h->stream));
+    h->count_launch(2);
+    return;
+  }
+  if (L.have_S) BLOCH_CUDA(launch_h1_dense(h->p, L.E, L.Sloc.p, x, m, y, m, m, 1.0, h->stream));
+  else BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, L.E, x, m, y, m, m, h->stream, 1.0, 0.0));
+  h->count_launch();
+}
+static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, double ratio, D2 *b, D2 *x) {
+  cudaStream_t s = h->stream;
+  H1Level &L = mg->lev[l];
+  const int nl = (int)mg->lev.size();
+  const long tot = L.N0 * m;
+  const unsigned g = grid_for(tot);
+  if (l == nl - 1) {
+    if (L.dense) {
+      k_dense_apply<<<g, TPB, 0, s>>>(L.inv.p, b, x, (int)L.N0, m);
+      h->count_launch();
+    } else {   // rare: coarsest level too large for a dense inverse
+      BLOCH_CUDA(cudaMemcpyAsync(L.r.p, b, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+      BLOCH_CUDA(cudaMemsetAsync(b, 0, sizeof(D2) * tot, s));
+      chebyshev(h, L, x, m, 40, 2000.0, false);
+    }
+    return;
+  }
+  H1Level &C = mg->lev[l + 1];
+  const int32_t *map_f = L.E.map_h1, *map_c = C.E.map_h1;
+  const int nef = L.E.n_elem;
+  const double lmax = L.lmax, lmin = lmax / ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+  auto cheb_tail = [&]() {   // steps 1 .. deg-1 of the Chebyshev recurrence on (r, d, x)
+    double rho = 1.0 / sigma1;
+    for (int k = 1; k < deg; k++) {
+      apply_nz(h, L, L.d.p, L.q.p, m);
+      const double rho_n = 1.0 / (2.0 * sigma1 - rho);
+      k_cheb_step_z<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, rho_n * rho, 2.0 * rho_n / delta, L.N0, m);
+      h->count_launch();
+      rho = rho_n;
+    }
+  };
+  // pre-smoothing from a zero guess
+  k_cheb_first_b<<<g, TPB, 0, s>>>(L.jac.p, b, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m);
+  cheb_tail();
+  // residual, restriction (coarse b is zero on entry)
+  apply_nz(h, L, x, L.q.p, m);
+  k_resid_z<<<g, TPB, 0, s>>>(b, L.q.p, L.r.p, tot);
+  switch (h->p) {
+    case 1: restrict_t<1>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    case 2: restrict_t<2>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    case 3: restrict_t<3>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    default: restrict_t<4>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+  }
+  h->count_launch(3);
+  vcycle_fused(mg, h, l + 1, m, deg, ratio, C.b.p, C.x.p);
+  // prolongation added straight into x; a dense coarse level has its right-hand side cleared here
+  const bool coarse_dense = (l + 1 == nl - 1) && C.dense;
+  D2 *zero = coarse_dense ? C.b.p : nullptr;
+  const long zc = coarse_dense ? C.N0 * m : 0;
+  switch (h->p) {
+    case 1: prolong_rep_t<1>(mg->T, L.rep.p, map_c, L.N0, L.n, C.x.p, x, m, zero, zc, s); break;
+    case 2: prolong_rep_t<2>(mg->T, L.rep.p, map_c, L.N0, L.n, C.x.p, x, m, zero, zc, s); break;
+    case 3: prolong_rep_t<3>(mg->T, L.rep.p, map_c, L.N0, L.n, C.x.p, x, m, zero, zc, s); break;
+    default: prolong_rep_t<4>(mg->T, L.rep.p, map_c, L.N0, L.n, C.x.p, x, m, zero, zc, s); break;
+  }
+  // post-smoothing; levels >= 1 clear their right-hand side for the next cycle's restriction
+  apply_nz(h, L, x, L.q.p, m);
+  k_resid_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, b, L.q.p, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m, l > 0 ? 1 : 0);
+  h->count_launch(2);
+  cheb_tail();
+}
+
+static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+  cudaStream_t s = h->stream;
+  alloc_work(mg, m);
+  H1Level &F = mg->lev[0];
+  const long N0 = F.N0, tot = N0 * m;
+  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
+  if (!mg->zero_valid || mg->zero_m != m) {   // establish the zero-buffer invariant for this block width
+    for (auto &L : mg->lev) {
+      BLOCH_CUDA(cudaMemsetAsync(L.q.p, 0, sizeof(D2) * L.N0 * m, s));
+      BLOCH_CUDA(cudaMemsetAsync(L.b.p, 0, sizeof(D2) * L.N0 * m, s));
+    }
+    BLOCH_CUDA(cudaMemsetAsync(mg->qvec.p, 0, sizeof(D2) * tot, s));
+    mg->zero_valid = true;
+    mg->zero_m = m;
+  }
+  double *part_rz = mg->part.p, *part_pq = part_rz + PCG_BLOCKS * m, *part_rr = part_pq + PCG_BLOCKS * m;
+  double *rz_saved = part_rr + PCG_BLOCKS * m;
+  double *sums = mg->scal.p + 6 * m;
+  if (h->beta == 0.0) {
+    BLOCH_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * m, s));
+    k_col_sum<<<grid_for(tot), TPB, 0, s>>>(rhs, N0, m, sums);
+    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(rhs, N0, m, sums);
+    h->count_launch(2);
+  }
+  BLOCH_CUDA(cudaMemsetAsync(phi, 0, sizeof(D2) * tot, s));
+  std::vector<double> hp((size_t)PCG_BLOCKS * m), rr0(m, 0.0), rrh(m);
+  auto fetch_rr = [&](std::vector<double> &out) {
+    BLOCH_CUDA(cudaMemcpyAsync(hp.data(), part_rr, sizeof(double) * PCG_BLOCKS * m, cudaMemcpyDeviceToHost, s));
+    h_sync(s);
+    for (int j = 0; j < m; j++) {
+      double sum = 0.0;
+      for (int b = 0; b < PCG_BLOCKS; b++) sum += hp[(size_t)b * m + j];
+      out[j] = sum;
+    }
+  };
+  const size_t sm1 = sizeof(double) * m, sm3 = 3 * sm1;
+  k_dot_part<<<PCG_BLOCKS, TPB, sm1, s>>>(rhs, rhs, N0, m, part_rr);
+  h->count_launch();
+  fetch_rr(rr0);
+  double mx = 0;
+  for (double v : rr0) mx = std::max(mx, v);
+  if (mx == 0.0) return 0;
+  vcycle_fused(mg, h, 0, m, deg, ratio, rhs, mg->z.p);
+  BLOCH_CUDA(cudaMemcpyAsync(mg->pvec.p, mg->z.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+  k_dot_part<<<PCG_BLOCKS, TPB, sm1, s>>>(rhs, mg->z.p, N0, m, part_rz);
+  h->count_launch();
+  auto half_a = [&]() {      // q = S0 p ; alpha ; phi += alpha p ; r -= alpha q ; rr = <r,r>
+    apply_nz(h, F, mg->pvec.p, mg->qvec.p, m);
+    k_dot_part<<<PCG_BLOCKS, TPB, sm1, s>>>(mg->pvec.p, mg->qvec.p, N0, m, part_pq);
+    k_pcg_a<<<PCG_BLOCKS, TPB, sm3, s>>>(mg->pvec.p, mg->qvec.p, phi, rhs, part_rz, part_pq, part_rr, rz_saved, N0, m);
+    h->count_launch(2);
+  };
+  auto half_b = [&]() {      // z = V(r) ; beta ; p = z + beta p
+    vcycle_fused(mg, h, 0, m, deg, ratio, rhs, mg->z.p);
+    k_dot_part<<<PCG_BLOCKS, TPB, sm1, s>>>(rhs, mg->z.p, N0, m, part_rz);
+    k_pcg_b<<<PCG_BLOCKS, TPB, sm1, s>>>(mg->z.p, mg->pvec.p, part_rz, rz_saved, N0, m);
+    h->count_launch(2);
+  };
+  static const bool use_graph = env_double("BLOCH_MG_GRAPH", 1.0) != 0.0;
+  auto capture = [&](cudaGraphExec_t *exec, const std::function<void()> &body) -> bool {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool ok = true;
+    try { body(); } catch (...) { ok = false; }
+    if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+    if (ok) ok = cudaGraphInstantiate(exec, graph, 0) == cudaSuccess;
+    cudaGraphDestroy(graph);
+    if (!ok) { cudaGetLastError(); *exec = nullptr; }
+    return ok;
+  };
+  static const bool timing = std::getenv("BLOCH_MG_TIMING") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
+  double tA = 0, tB = 0, tW = 0;
+  int nA = 0, nB = 0;
+  auto w0 = std::chrono::steady_clock::now();
+  int it = 0;
+  for (it = 1; it <= max_it; it++) {
+    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m;
+    if (use_graph && !graphs_ok && it == 2) {
+      mg->drop_graphs();
+      if (capture(&mg->gA, half_a) && capture(&mg->gB, half_b)) {
+        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m;
+        graphs_ok = true;
+      } else {
+        mg->drop_graphs();
+      }
+    }
+    if (timing) cudaEventRecord(e0, s);
+    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); else half_a();
+    if (timing) cudaEventRecord(e1, s);
+    fetch_rr(rrh);
+    if (timing && it > 2) { float ms; cudaEventElapsedTime(&ms, e0, e1); tA += ms; nA++; }
+    bool done = true;
+    for (int j = 0; j < m; j++)
+      if (rrh[j] > rel_tol * rel_tol * rr0[j]) done = false;
+    if (done) break;
+    if (timing) cudaEventRecord(e1, s);
+    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); else half_b();
+    if (timing) {
+      cudaEventRecord(e2, s);
+      cudaEventSynchronize(e2);
+      if (it > 2) { float ms; cudaEventElapsedTime(&ms, e1, e2); tB += ms; nB++; }
+    }
+  }
+  if (timing) {
+    tW = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    std::printf("[mg] %d its, wall %.3f ms; graph A avg %.1f us, graph B avg %.1f us (m = %d)\n", it, tW,
+                nA ? 1e3 * tA / nA : 0.0, nB ? 1e3 * tB / nB : 0.0, m);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  }
+  return it > max_it ? max_it : it;
+}
+
 // block PCG on the fine level, one V-cycle as preconditioner; rhs is overwritten by the residual
 int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+  static const bool fused = env_double("BLOCH_MG_FUSED", 1.0) != 0.0;
+  if (fused) return mg_solve_fused(mg, h, rhs, phi, m, rel_tol, max_it);
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
   H1Level &F = mg->lev[0];
