@@ -840,50 +840,57 @@ __global__ void k_unpack(const double2 *__restrict__ blk, double *__restrict__ r
 // Gram: each CTA reduces a row chunk into a register tile, then atomically adds into C.
 // thread (ti, tj) owns C entries (i, j) with i = ti + k*TI... simple generic version.
 constexpr int GRAM_THREADS = 256;
-constexpr int GRAM_ACC = 16;     // outputs per thread: ma*mb <= 4096, i.e. up to 64 basis columns
-constexpr int GRAM_ROWS = 16;   // rows staged per iteration (16*(ma+mb)*16 B <= 48 KB for ma+mb <= 192)
-__global__ void k_gram(const double2 *__restrict__ A, int ma, int lda, const double2 *__restrict__ B, int mb,
-                       int ldb, long n, double2 *__restrict__ C, long rows_per_cta) {
+constexpr int GRAM_ROWS = 16;   // rows staged per iteration: 16 x (64 + 64) x 16 B = 32 KB
+// Register-tiled: the 256 threads form a 16 x 16 grid, thread (ti, tj) owns the 4 x 4 outputs
+// C[ti + 16 a][tj + 16 b]; per staged row it reads 4 + 4 shared values for 16 complex MACs.
+__global__ void __launch_bounds__(GRAM_THREADS)
+k_gram(const double2 *__restrict__ A, int ma, int lda, const double2 *__restrict__ B, int mb,
+       int ldb, long n, double2 *__restrict__ C, long rows_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2 *sA = reinterpret_cast<double2 *>(smem_raw);   // [GRAM_ROWS][ma]
-  double2 *sB = sA + GRAM_ROWS * ma;                      // [GRAM_ROWS][mb]
+  double2 *sA = reinterpret_cast<double2 *>(smem_raw);   // [GRAM_ROWS][64] (zero padded)
+  double2 *sB = sA + GRAM_ROWS * 64;                      // [GRAM_ROWS][64]
   const long r0 = blockIdx.x * rows_per_cta;
   const long r1 = min(n, r0 + rows_per_cta);
-  const int nout = ma * mb;
-  // each thread accumulates outputs t, t+256, ... (at most GRAM_ACC -> ma*mb <= 256*GRAM_ACC)
-  double2 acc[GRAM_ACC];
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  double2 acc[4][4];
 #pragma unroll
-  for (int k = 0; k < GRAM_ACC; k++) acc[k] = make_double2(0.0, 0.0);
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = make_double2(0.0, 0.0);
   for (long r = r0; r < r1; r += GRAM_ROWS) {
     const int nr = (int)min((long)GRAM_ROWS, r1 - r);
-    for (int t = threadIdx.x; t < nr * ma; t += GRAM_THREADS) sA[t] = A[(r + t / ma) * lda + t % ma];
-    for (int t = threadIdx.x; t < nr * mb; t += GRAM_THREADS) sB[t] = B[(r + t / mb) * ldb + t % mb];
+    for (int t = threadIdx.x; t < GRAM_ROWS * 64; t += GRAM_THREADS) {
+      const int q = t >> 6, c = t & 63;
+      sA[t] = (q < nr && c < ma) ? A[(r + q) * lda + c] : make_double2(0.0, 0.0);
+      sB[t] = (q < nr && c < mb) ? B[(r + q) * ldb + c] : make_double2(0.0, 0.0);
+    }
     __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < GRAM_ROWS; q++) {
+      double2 x[4], y[4];
 #pragma unroll
-    for (int k = 0; k < GRAM_ACC; k++) {
-      const int o = threadIdx.x + k * GRAM_THREADS;
-      if (o < nout) {
-        const int i = o / mb, j = o - i * mb;
-        double2 a = acc[k];
-        for (int q = 0; q < nr; q++) {
-          const double2 x = sA[q * ma + i], y = sB[q * mb + j];
-          a.x = fma(x.x, y.x, a.x); a.x = fma(x.y, y.y, a.x);
-          a.y = fma(x.x, y.y, a.y); a.y = fma(-x.y, y.x, a.y);
+      for (int a = 0; a < 4; a++) { x[a] = sA[q * 64 + ti + 16 * a]; y[a] = sB[q * 64 + tj + 16 * a]; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          acc[a][b].x = fma(x[a].x, y[b].x, acc[a][b].x); acc[a][b].x = fma(x[a].y, y[b].y, acc[a][b].x);
+          acc[a][b].y = fma(x[a].x, y[b].y, acc[a][b].y); acc[a][b].y = fma(-x[a].y, y[b].x, acc[a][b].y);
         }
-        acc[k] = a;
-      }
     }
     __syncthreads();
   }
   double *Cd = reinterpret_cast<double *>(C);
 #pragma unroll
-  for (int k = 0; k < GRAM_ACC; k++) {
-    const int o = threadIdx.x + k * GRAM_THREADS;
-    if (o < nout) {
-      atomicAdd(Cd + 2 * o, acc[k].x);
-      atomicAdd(Cd + 2 * o + 1, acc[k].y);
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int i = ti + 16 * a, j = tj + 16 * b;
+      if (i < ma && j < mb) {
+        atomicAdd(Cd + 2 * (i * mb + j), acc[a][b].x);
+        atomicAdd(Cd + 2 * (i * mb + j) + 1, acc[a][b].y);
+      }
     }
-  }
 }
 
 // Y = beta*Y + X*C : one thread per (row, output column)
@@ -1029,14 +1036,14 @@ cudaError_t launch_unpack(const double2 *blk, double *reim, long n, int nvec, cu
 }
 cudaError_t launch_gram(const double2 *A, int ma, int lda, const double2 *B, int mb, int ldb, long n,
                         double2 *C, cudaStream_t s) {
-  if (ma * mb > GRAM_ACC * GRAM_THREADS) return cudaErrorInvalidValue;
+  if (ma > 64 || mb > 64) return cudaErrorInvalidValue;
   cudaError_t err = cudaMemsetAsync(C, 0, sizeof(double2) * ma * mb, s);
   if (err != cudaSuccess) return err;
   long ctas = 148 * 2;
   long rows = (n + ctas - 1) / ctas;
   rows = ((rows + GRAM_ROWS - 1) / GRAM_ROWS) * GRAM_ROWS;
   ctas = (n + rows - 1) / rows;
-  const size_t smem = (size_t)GRAM_ROWS * (ma + mb) * sizeof(double2);
+  const size_t smem = (size_t)GRAM_ROWS * 128 * sizeof(double2);
   k_gram<<<(unsigned)ctas, GRAM_THREADS, smem, s>>>(A, ma, lda, B, mb, ldb, n, C, rows);
   return cudaGetLastError();
 }

@@ -60,39 +60,45 @@ __global__ void k_resid_norm(const D2 *__restrict__ AS, const D2 *__restrict__ M
 
 // Rayleigh-Ritz rotation, in place on the basis arrays (pitch ld = 3m):
 //   P_new = sum_{i>=m} S_i C[i][:],  X_new = sum_{i<m} S_i C[i][:] + P_new
-// one warp per row, lane = output column; k = number of active basis columns (m, 2m or 3m)
-__global__ void k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k,
-                            int m, const D2 *__restrict__ C, long n) {
+// A CTA stages RP rows of one array in shared memory (coalesced), then thread (row, column) forms its two
+// sums; CW = 16 or 32 column slots per row (m <= 21), k = number of active basis columns (m, 2m or 3m).
+template <int CW>
+__global__ void __launch_bounds__(256)
+k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k, int m,
+            const D2 *__restrict__ C, long n) {
+  constexpr int RP = 256 / CW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  D2 *sC = reinterpret_cast<D2 *>(smem_raw);
-  for (int t = threadIdx.x; t < k * m; t += blockDim.x) sC[t] = C[t];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long r = warp; r < n; r += nwarps) {
+  D2 *sC = reinterpret_cast<D2 *>(smem_raw);     // [k][m]
+  D2 *sT = sC + k * m;                           // [RP][k]
+  for (int t = threadIdx.x; t < k * m; t += 256) sC[t] = C[t];
+  const int rr = threadIdx.x / CW, j = threadIdx.x % CW;
+  const long ntiles = (n + RP - 1) / RP;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long r0 = tile * RP;
+    const int nr = (int)min((long)RP, n - r0);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      D2 *row = (a == 0 ? S : (a == 1 ? AS : MS)) + r * ld;
-      D2 x = make_double2(0.0, 0.0), pn = make_double2(0.0, 0.0);
-      if (lane < m) {
+      D2 *base = (a == 0 ? S : (a == 1 ? AS : MS)) + r0 * ld;
+      __syncthreads();
+      for (int t = threadIdx.x; t < nr * k; t += 256) sT[t] = base[(long)(t / k) * ld + t % k];
+      __syncthreads();
+      if (rr < nr && j < m) {
+        const D2 *row = sT + rr * k;
+        D2 x = make_double2(0.0, 0.0), pn = make_double2(0.0, 0.0);
         for (int i = 0; i < m; i++) {
-          const D2 s = row[i], c = sC[i * m + lane];
+          const D2 s = row[i], c = sC[i * m + j];
           x.x = fma(s.x, c.x, x.x); x.x = fma(-s.y, c.y, x.x);
           x.y = fma(s.x, c.y, x.y); x.y = fma(s.y, c.x, x.y);
         }
         for (int i = m; i < k; i++) {
-          const D2 s = row[i], c = sC[i * m + lane];
+          const D2 s = row[i], c = sC[i * m + j];
           pn.x = fma(s.x, c.x, pn.x); pn.x = fma(-s.y, c.y, pn.x);
           pn.y = fma(s.x, c.y, pn.y); pn.y = fma(s.y, c.x, pn.y);
         }
+        D2 *out = base + (long)rr * ld;
+        out[j] = make_double2(x.x + pn.x, x.y + pn.y);
+        out[2 * m + j] = pn;
       }
-      __syncwarp();
-      if (lane < m) {
-        row[lane] = make_double2(x.x + pn.x, x.y + pn.y);
-        row[2 * m + lane] = pn;
-      }
-      __syncwarp();
     }
   }
 }
@@ -440,8 +446,13 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     lam = l;
     BLOCH_CUDA(cudaMemcpyAsync(dC.p, hC.data(), sizeof(D2) * hC.size(), cudaMemcpyHostToDevice, s));
     BLOCH_CUDA(cudaMemcpyAsync(dlam.p, lam.data(), sizeof(double) * mb, cudaMemcpyHostToDevice, s));
-    const unsigned g = (unsigned)std::min<long>((Nl + 7) / 8, 148L * 8);
-    k_rr_update<<<g, 256, sizeof(D2) * k * mb, s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+    if (mb <= 16) {
+      const unsigned g = (unsigned)std::min<long>((Nl + 15) / 16, 148L * 4);
+      k_rr_update<16><<<g, 256, sizeof(D2) * (k * mb + 16 * k), s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+    } else {
+      const unsigned g = (unsigned)std::min<long>((Nl + 7) / 8, 148L * 4);
+      k_rr_update<32><<<g, 256, sizeof(D2) * (k * mb + 8 * k), s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+    }
     count_launch();
     h_sync(s);   // hC / lam are stack-lifetime host buffers
     if (dropped) need_refresh = true;
