@@ -325,7 +325,7 @@ __global__ void k_h1_prolong_rep(const __grid_constant__ Transfer1D T, const int
 
 // ---- PCG scalars without memset / atomics on global memory: every dot product is written as
 // per-block partial sums part[block][m]; consumers add the PCG_BLOCKS partials themselves. ----
-constexpr int PCG_BLOCKS = 148;
+constexpr int PCG_BLOCKS = 148 * 4;   // enough threads in flight to stream the large levels from HBM
 // all threads take part: thread t adds the partials of column t % m from blocks t / m, t / m + T / m, ...
 // (callers __syncthreads() afterwards; tot must not alias other live shared data)
 __device__ __forceinline__ void col_totals(const double *__restrict__ part, int m, double *tot /* smem [m] */) {
@@ -551,13 +551,14 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
   // transpose maps for the atomic-free operator apply (element-local results + owner reduction)
   {
     static const double evec_min = env_double("BLOCH_H1_EVEC_MIN_ELEMS", 1024.0);
+    static const double evec_max = env_double("BLOCH_H1_EVEC_MAX_ELEMS", 4096.0);   // beyond: E-vector leaves L2
     static const bool evec_on = env_double("BLOCH_H1_EVEC", 1.0) != 0.0;
     for (size_t l = 0; l < mg->lev.size(); l++) {
       H1Level &L = mg->lev[l];
       const std::vector<int32_t> &nat = l == 0 ? h->maps.h1 : L.maps.h1;
       const long ne = l == 0 ? h->mesh.n_elem : L.mesh.n_elem;
       const int LH = h->L_h1;
-      L.use_evec = evec_on && p <= 2 && ne >= (long)evec_min;
+      L.use_evec = evec_on && p <= 2 && ne >= (long)evec_min && ne <= (long)evec_max;
       // kernel local order k = (i0*Q + i1)*Q + i2  <->  natural i0 + Q*(i1 + Q*i2)
       auto gid = [&](long e, int k) {
         const int i0 = k / (Q * Q), i1 = (k / Q) % Q, i2 = k % Q;
@@ -1009,10 +1010,17 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
 
 // block PCG on the fine level, one V-cycle as preconditioner; rhs is overwritten by the residual
 int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+  // Two schedules of the same iteration.  The fused one (fewer graph nodes, consume-and-clear buffers,
+  // atomic-free fine-level apply) wins while the fine level is a few hundred thousand entries and every
+  // node sits at its latency floor; once the level vectors outgrow L2 the plain schedule is faster
+  // (memset nodes are nearly free there, the extra stores of consume-and-clear are not): measured
+  // crossover at ~0.8 M entries (FCC p2: n_sub 12).
+  static const double fused_max = env_double("BLOCH_MG_FUSED_MAX_ENTRIES", 8.0e5);
   static const bool fused = env_double("BLOCH_MG_FUSED", 1.0) != 0.0;
-  if (fused) return mg_solve_fused(mg, h, rhs, phi, m, rel_tol, max_it);
+  if (fused && (double)mg->lev[0].N0 * m <= fused_max) return mg_solve_fused(mg, h, rhs, phi, m, rel_tol, max_it);
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
+  mg->zero_valid = false;   // this schedule leaves the operator-output buffers dirty
   H1Level &F = mg->lev[0];
   const long N0 = F.N0, tot = N0 * m;
   const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
