@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--pts-per-segment", type=int, default=8)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "4")),
                     help="concurrent k-point solves per GPU (independent handles on separate streams)")
+    ap.add_argument("--chunk", type=int, default=0,
+                    help="k-points per work unit of the stream pool (0 = steps / (2 * streams))")
     ap.add_argument("--apply-vectors", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--apply-study", action="store_true",
@@ -166,10 +168,21 @@ def run_b200(args):
         if T == 1:
             solve_range(eqs[0], idxs, out, e2e)
         else:
-            # contiguous chunks per stream: neighbouring k-points warm-start each other
-            bounds = [m.shard_kpoints(len(idxs), T, t) for t in range(T)]
-            th = [threading.Thread(target=solve_range, args=(eqs[t], idxs[lo:hi], out, e2e))
-                  for t, (lo, hi) in enumerate(bounds)]
+            # contiguous chunks (neighbouring k-points warm-start each other) handed out from a shared
+            # queue, so a stream that drew easy k-points takes another chunk instead of idling
+            csz = args.chunk if args.chunk > 0 else max(1, len(idxs) // (2 * T))
+            chunks = [idxs[i:i + csz] for i in range(0, len(idxs), csz)]
+            lock = threading.Lock()
+
+            def worker(eq):
+                while True:
+                    with lock:
+                        if not chunks:
+                            return
+                        mine = chunks.pop(0)
+                    solve_range(eq, mine, out, e2e)
+
+            th = [threading.Thread(target=worker, args=(eqs[t],)) for t in range(T)]
             [t.start() for t in th]
             [t.join() for t in th]
         return out

@@ -164,8 +164,11 @@ __global__ void k_add(D2 *__restrict__ x, const D2 *__restrict__ y, long total) 
   }
 }
 // Chebyshev: d = c0 jac r ; x (+)= d
+// (all Chebyshev coefficients are read from device memory - coef[0] = 1/theta, coef[2k-1], coef[2k] for step
+// k - so that the captured CUDA graphs stay valid when Setup() changes them with kappa)
 __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ d,
-                             D2 *__restrict__ x, double c0, long n, int m, int accumulate) {
+                             D2 *__restrict__ x, const double *__restrict__ coef, long n, int m, int accumulate) {
+  const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const double s = c0 * jac[t / m];
@@ -177,7 +180,9 @@ __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restric
 }
 // r -= q ; d = a d + b jac r ; x += d
 __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict__ q, D2 *__restrict__ r,
-                            D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+                            D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, int step, long n,
+                            int m) {
+  const double a = coef[2 * step - 1], b = coef[2 * step];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const double s = b * jac[t / m];
@@ -225,7 +230,8 @@ __global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__r
 
 // pre-smoothing from a zero guess: r = b ; d = c0 jac b ; x = d
 __global__ void k_cheb_first_b(const double *__restrict__ jac, const D2 *__restrict__ b, D2 *__restrict__ r,
-                               D2 *__restrict__ d, D2 *__restrict__ x, double c0, long n, int m) {
+                               D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, long n, int m) {
+  const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const double s = c0 * jac[t / m];
@@ -236,7 +242,9 @@ __global__ void k_cheb_first_b(const double *__restrict__ jac, const D2 *__restr
 }
 // r -= q ; q = 0 ; d = a d + b jac r ; x += d
 __global__ void k_cheb_step_z(const double *__restrict__ jac, D2 *__restrict__ q, D2 *__restrict__ r,
-                              D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+                              D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, int step, long n,
+                              int m) {
+  const double a = coef[2 * step - 1], b = coef[2 * step];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const double s = b * jac[t / m];
@@ -263,8 +271,9 @@ __global__ void k_resid_z(const D2 *__restrict__ b, D2 *__restrict__ q, D2 *__re
 }
 // post-smoothing start: r = b - q ; q = 0 ; (b = 0) ; d = c0 jac r ; x += d
 __global__ void k_resid_cheb_first(const double *__restrict__ jac, D2 *__restrict__ b, D2 *__restrict__ q,
-                                   D2 *__restrict__ r, D2 *__restrict__ d, D2 *__restrict__ x, double c0, long n,
-                                   int m, int clear_b) {
+                                   D2 *__restrict__ r, D2 *__restrict__ d, D2 *__restrict__ x,
+                                   const double *__restrict__ coef, long n, int m, int clear_b) {
+  const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const double s = c0 * jac[t / m];
@@ -462,6 +471,7 @@ struct H1Level {
   DevBuf<D2> x, b, r, d, q;           // V-cycle work vectors, N0 x m
   DevBuf<D2> inv, dI, dA;             // dense inverse on the coarsest level (+ identity / operator scratch)
   DevBuf<double> dloc;                // element-local diagonals (scratch)
+  DevBuf<double> cheb, cheb40;        // Chebyshev coefficient tables (smoother / coarsest-level fallback)
   DevBuf<int> tp_ptr;                 // transpose of map_h1: dof -> its local copies (atomic-free apply)
   DevBuf<int32_t> tp_loc;
   DevBuf<D2> evec;                    // E-vector [n_elem * L][m]
@@ -601,13 +611,17 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
 
 void mg_destroy(H1Multigrid *mg) { delete mg; }
 
+static std::vector<double> cheb_coefs(double lmax, double ratio, int degree);
+
 // element-local diagonal of S0 per class on one level (probe launch of the production kernel)
 static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound,
                         std::vector<D2> *Sloc = nullptr);
 
 void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
   cudaStream_t s = h->stream;
-  mg->drop_graphs();
+  // the captured graphs survive: everything kappa-dependent they use lives in device buffers that are
+  // rewritten in place (class tables, Jacobi diagonals, Chebyshev tables, coarse inverse)
+  const bool was_dense = mg->lev.back().dense;
   const int p = h->p;
   const int nl = (int)mg->lev.size();
   for (int l = 0; l < nl; l++) {
@@ -653,6 +667,8 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     L.have_S = !Sl.empty();
     if (L.have_S) L.Sloc.upload(Sl, s);
     L.lmax = 1.05 * bound;
+    L.cheb.upload(cheb_coefs(L.lmax, env_double("BLOCH_MG_SMOOTH_RATIO", 5.0), (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2)), s);
+    if (l == nl - 1) L.cheb40.upload(cheb_coefs(L.lmax, 2000.0, 40), s);
     DevBuf<double> &dl = L.dloc;
     dl.upload(dloc, s);
     L.diag.alloc(L.N0); L.jac.alloc(L.N0);
@@ -712,6 +728,8 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
       h_sync(s);
     }
   }
+  if (C.dense != was_dense) mg->drop_graphs();   // the coarse solve is a different node list
+  h_sync(s);                                      // host-side tables uploaded above are stack temporaries
 }
 
 static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<double> &dloc, double *bound,
@@ -750,21 +768,32 @@ static void level_apply(bloch_handle_s *h, H1Level &L, const D2 *x, D2 *y, int m
   BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, L.E, x, m, y, m, m, h->stream, 1.0, 0.0));
   h->count_launch();
 }
-// x (+)= Cheb_deg(D^-1 S0) applied to the residual held in L.r (destroyed)
-static void chebyshev(bloch_handle_s *h, H1Level &L, D2 *x, int m, int degree, double ratio, bool accumulate) {
-  cudaStream_t s = h->stream;
-  const double lmax = L.lmax, lmin = lmax / ratio;
+// Chebyshev coefficients of degree `degree` on [lmax / ratio, lmax]: out[0] = 1/theta, out[2k-1], out[2k] = the
+// (d, r) weights of step k
+static std::vector<double> cheb_coefs(double lmax, double ratio, int degree) {
+  const double lmin = lmax / ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
-  const unsigned g = grid_for(L.N0 * m);
-  k_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m, accumulate ? 1 : 0);
-  h->count_launch();
+  std::vector<double> c(2 * std::max(degree, 1), 0.0);
+  c[0] = 1.0 / theta;
   double rho = 1.0 / sigma1;
   for (int k = 1; k < degree; k++) {
-    level_apply(h, L, L.d.p, L.q.p, m);
     const double rho_n = 1.0 / (2.0 * sigma1 - rho);
-    k_cheb_step<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, rho_n * rho, 2.0 * rho_n / delta, L.N0, m);
-    h->count_launch();
+    c[2 * k - 1] = rho_n * rho;
+    c[2 * k] = 2.0 * rho_n / delta;
     rho = rho_n;
+  }
+  return c;
+}
+// x (+)= Cheb_deg(D^-1 S0) applied to the residual held in L.r (destroyed); cf = device coefficient table
+static void chebyshev(bloch_handle_s *h, H1Level &L, D2 *x, int m, int degree, const double *cf, bool accumulate) {
+  cudaStream_t s = h->stream;
+  const unsigned g = grid_for(L.N0 * m);
+  k_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, L.r.p, L.d.p, x, cf, L.N0, m, accumulate ? 1 : 0);
+  h->count_launch();
+  for (int k = 1; k < degree; k++) {
+    level_apply(h, L, L.d.p, L.q.p, m);
+    k_cheb_step<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, cf, k, L.N0, m);
+    h->count_launch();
   }
 }
 
@@ -780,7 +809,7 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
       h->count_launch();
     } else {
       BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
-      chebyshev(h, L, L.x.p, m, 40, 2000.0, false);
+      chebyshev(h, L, L.x.p, m, 40, L.cheb40.p, false);
     }
     return;
   }
@@ -789,7 +818,7 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   const int nef = L.E.n_elem;
   // pre-smoothing from a zero initial guess
   BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
-  chebyshev(h, L, L.x.p, m, deg, ratio, false);
+  chebyshev(h, L, L.x.p, m, deg, L.cheb.p, false);
   // residual, restriction
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
@@ -814,7 +843,7 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
   h->count_launch(3);
-  chebyshev(h, L, L.x.p, m, deg, ratio, true);
+  chebyshev(h, L, L.x.p, m, deg, L.cheb.p, true);
 }
 
 
@@ -843,27 +872,22 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
     } else {   // rare: coarsest level too large for a dense inverse
       BLOCH_CUDA(cudaMemcpyAsync(L.r.p, b, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
       BLOCH_CUDA(cudaMemsetAsync(b, 0, sizeof(D2) * tot, s));
-      chebyshev(h, L, x, m, 40, 2000.0, false);
+      chebyshev(h, L, x, m, 40, L.cheb40.p, false);
     }
     return;
   }
   H1Level &C = mg->lev[l + 1];
   const int32_t *map_f = L.E.map_h1, *map_c = C.E.map_h1;
   const int nef = L.E.n_elem;
-  const double lmax = L.lmax, lmin = lmax / ratio;
-  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
   auto cheb_tail = [&]() {   // steps 1 .. deg-1 of the Chebyshev recurrence on (r, d, x)
-    double rho = 1.0 / sigma1;
     for (int k = 1; k < deg; k++) {
       apply_nz(h, L, L.d.p, L.q.p, m);
-      const double rho_n = 1.0 / (2.0 * sigma1 - rho);
-      k_cheb_step_z<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, rho_n * rho, 2.0 * rho_n / delta, L.N0, m);
+      k_cheb_step_z<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, L.cheb.p, k, L.N0, m);
       h->count_launch();
-      rho = rho_n;
     }
   };
   // pre-smoothing from a zero guess
-  k_cheb_first_b<<<g, TPB, 0, s>>>(L.jac.p, b, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m);
+  k_cheb_first_b<<<g, TPB, 0, s>>>(L.jac.p, b, L.r.p, L.d.p, x, L.cheb.p, L.N0, m);
   cheb_tail();
   // residual, restriction (coarse b is zero on entry)
   apply_nz(h, L, x, L.q.p, m);
@@ -888,7 +912,7 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
   }
   // post-smoothing; levels >= 1 clear their right-hand side for the next cycle's restriction
   apply_nz(h, L, x, L.q.p, m);
-  k_resid_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, b, L.q.p, L.r.p, L.d.p, x, 1.0 / theta, L.N0, m, l > 0 ? 1 : 0);
+  k_resid_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, b, L.q.p, L.r.p, L.d.p, x, L.cheb.p, L.N0, m, l > 0 ? 1 : 0);
   h->count_launch(2);
   cheb_tail();
 }
