@@ -182,7 +182,7 @@ struct bloch_handle_s {
   bloch_b200::DevBuf<double> d_dloc;
 
   struct LobpcgWork {
-    bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM;
+    bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM, Lu, Lphi, Lg;
     bloch_b200::DevBuf<double> dlam, drn;
   } lw;
 

@@ -917,6 +917,18 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
   cheb_tail();
 }
 
+static void ensure_zero_buffers(H1Multigrid *mg, bloch_handle_s *h, int m) {
+  if (mg->zero_valid && mg->zero_m == m) return;   // establish the zero-buffer invariant for this block width
+  cudaStream_t s = h->stream;
+  for (auto &L : mg->lev) {
+    BLOCH_CUDA(cudaMemsetAsync(L.q.p, 0, sizeof(D2) * L.N0 * m, s));
+    BLOCH_CUDA(cudaMemsetAsync(L.b.p, 0, sizeof(D2) * L.N0 * m, s));
+  }
+  BLOCH_CUDA(cudaMemsetAsync(mg->qvec.p, 0, sizeof(D2) * mg->lev[0].N0 * m, s));
+  mg->zero_valid = true;
+  mg->zero_m = m;
+}
+
 static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
@@ -924,15 +936,7 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
   const long N0 = F.N0, tot = N0 * m;
   const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
   const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
-  if (!mg->zero_valid || mg->zero_m != m) {   // establish the zero-buffer invariant for this block width
-    for (auto &L : mg->lev) {
-      BLOCH_CUDA(cudaMemsetAsync(L.q.p, 0, sizeof(D2) * L.N0 * m, s));
-      BLOCH_CUDA(cudaMemsetAsync(L.b.p, 0, sizeof(D2) * L.N0 * m, s));
-    }
-    BLOCH_CUDA(cudaMemsetAsync(mg->qvec.p, 0, sizeof(D2) * tot, s));
-    mg->zero_valid = true;
-    mg->zero_m = m;
-  }
+  ensure_zero_buffers(mg, h, m);
   double *part_rz = mg->part.p, *part_pq = part_rz + PCG_BLOCKS * m, *part_rr = part_pq + PCG_BLOCKS * m;
   double *rz_saved = part_rr + PCG_BLOCKS * m;
   double *sums = mg->scal.p + 6 * m;
@@ -1030,6 +1034,25 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   }
   return it > max_it ? max_it : it;
+}
+
+void mg_vcycle(H1Multigrid *mg, bloch_handle_s *h, const D2 *b, D2 *x, int m) {
+  cudaStream_t s = h->stream;
+  alloc_work(mg, m);
+  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
+  static const double fused_max = env_double("BLOCH_MG_FUSED_MAX_ENTRIES", 8.0e5);
+  static const bool fused = env_double("BLOCH_MG_FUSED", 1.0) != 0.0;
+  H1Level &F = mg->lev[0];
+  if (fused && (double)F.N0 * m <= fused_max) {
+    ensure_zero_buffers(mg, h, m);
+    vcycle_fused(mg, h, 0, m, deg, ratio, const_cast<D2 *>(b), x);   // the level-0 right-hand side is only read
+  } else {
+    mg->zero_valid = false;
+    BLOCH_CUDA(cudaMemcpyAsync(F.b.p, b, sizeof(D2) * F.N0 * m, cudaMemcpyDeviceToDevice, s));
+    vcycle(mg, h, 0, m, deg, ratio);
+    BLOCH_CUDA(cudaMemcpyAsync(x, F.x.p, sizeof(D2) * F.N0 * m, cudaMemcpyDeviceToDevice, s));
+  }
 }
 
 // block PCG on the fine level, one V-cycle as preconditioner; rhs is overwritten by the residual

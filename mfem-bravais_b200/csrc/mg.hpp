@@ -13,4 +13,7 @@ void mg_destroy(H1Multigrid *mg);
 void mg_setup(H1Multigrid *mg, bloch_handle_s *h);
 // rhs (N0 x m contiguous) is overwritten by the final residual; returns the PCG iteration count
 int mg_solve(H1Multigrid *mg, bloch_handle_s *h, double2 *rhs, double2 *phi, int m, double rel_tol, int max_it);
+// x = B b: ONE V-cycle (a fixed symmetric positive definite linear operator, spectrally equivalent to S0^-1);
+// b (N0 x m contiguous) is preserved
+void mg_vcycle(H1Multigrid *mg, bloch_handle_s *h, const double2 *b, double2 *x, int m);
 }  // namespace bloch_b200

@@ -359,6 +359,42 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
     prob.apply(x, ldx, y, ldy, nvec, ca, cm);
   };
+  // Gradient lift.  The constrained pencil is solved as the UNCONSTRAINED pencil (A_tau, M) with
+  //     A_tau = A + tau M G B G^H M,   B = one multigrid V-cycle for S0 (fixed SPD linear operator).
+  // Divergence-free vectors do not see the extra term (G^H M x = 0), so every physical eigenpair is an exact
+  // eigenpair of (A_tau, M); gradients G phi, the kernel of A, are moved from 0 to tau * eig(B S0) in
+  // [~0.25 tau, tau], above the wanted bands.  Gradient contamination of the search directions then shows up
+  // as HIGH Ritz values that Rayleigh-Ritz ignores instead of spurious zeros, so W needs only a rough
+  // projection (relative 1e-2, a few PCG iterations) instead of one to 1e-2 * tol (16 iterations) per outer
+  // iteration; the price is one V-cycle per lifted operator application.
+  // (only with a warm start: tau must sit a modest factor above the wanted bands, and the Ritz values of a
+  // random block say nothing about them)
+  const bool warm_block = warm && !(prob.use_init && n_init > 0) && have_vectors == mb && d_X.n >= (size_t)Nl * mb;
+  const bool lift = prob.constrained && mg && use_mg && !two_pass && warm_block && env_double("BLOCH_LIFT", 1.0) != 0.0;
+  const double lift_factor = env_double("BLOCH_LIFT_TAU", 8.0);
+  const double lift_ptol = env_double("BLOCH_LIFT_PROJ_TOL", 1e-1);
+  const double lift_xtol = env_double("BLOCH_LIFT_X_TOL", 1e-1);
+  double tau = 0.0;
+  if (lift) { lw.Lu.alloc((size_t)N0 * mb); lw.Lphi.alloc((size_t)N0 * mb); lw.Lg.alloc((size_t)Nl * mb); }
+  auto opA = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec) {   // y = A_tau x
+    op(x, ldx, y, ldy, nvec, 1.0, 0.0);
+    if (!lift || tau <= 0.0) return;
+    BLOCH_CUDA(cudaMemsetAsync(lw.Lu.p, 0, sizeof(D2) * N0 * nvec, s));
+    BLOCH_CUDA(launch_h1_op(p, 2, tabs, E, x, ldx, lw.Lu.p, nvec, nvec, s));           // u = G^H M x
+    if (beta == 0.0) {   // S0 singular on constants at Gamma: u is orthogonal to them up to rounding
+      ProjWork &w = proj_work(this);
+      w.scal.alloc(8 * nvec + 2);
+      BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * 2 * nvec, s));
+      const unsigned g1 = std::min<unsigned>(grid_for(N0 * nvec), 148);
+      k_col_sum<<<g1, TPB, sizeof(double) * 2 * nvec, s>>>(lw.Lu.p, N0, nvec, w.scal.p);
+      k_col_shift<<<grid_for(N0 * nvec), TPB, 0, s>>>(lw.Lu.p, N0, nvec, w.scal.p);
+      count_launch(2);
+    }
+    mg_vcycle(mg, this, lw.Lu.p, lw.Lphi.p, nvec);                                      // phi = B u
+    BLOCH_CUDA(launch_h1_op(p, 1, tabs, E, lw.Lphi.p, nvec, lw.Lg.p, nvec, nvec, s));  // g = G phi
+    BLOCH_CUDA(launch_nd_apply(p, tabs, E, lw.Lg.p, nvec, y, ldy, nvec, 0.0, tau, s));  // y += tau M g
+    count_launch(3);
+  };
 
   // lambda_max(D^-1 (A + sigma M)) <= max over element classes of the local scaled spectra
   // (x^H A x = sum_e x_e^H A_e x_e <= mu sum_e x_e^H diag(A_e) x_e); computed once per handle from
@@ -480,9 +516,15 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     int its = 0;
     if (prob.constrained) project_ld(this, Wc.p, mb, mb, std::min(proj_tol, 1e-10), 3000, &its);
     BLOCH_CUDA(cudaMemcpy2DAsync(S.p, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
-    op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);
+    op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);    // X is divergence-free to 1e-10 here: A_tau X = A X
     op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
     if (!rayleigh_ritz(mb)) throw std::runtime_error("initial block is rank deficient");
+    if (lift) {
+      double top = 0.0;
+      for (int j = 0; j < mb; j++) top = std::max(top, std::fabs(lam[j]));
+      tau = lift_factor * std::max(top, 1e-3 / vol23);
+      if (verbose) std::printf("[lobpcg] gradient lift tau = %.4g (%.1f x top Ritz value)\n", tau, lift_factor);
+    }
   }
 
   double t_pre = 0, t_proj = 0, t_op = 0, t_rr = 0, t_res = 0;
@@ -528,8 +570,8 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     int its = 0;
     // inexact inner solves: the gradient content left in W only has to stay well below the
     // current eigen-residual level (it enters X scaled by the size of the update)
-    double ptol = proj_tol;
-    if (proj_adapt > 0.0) {
+    double ptol = lift ? lift_ptol : proj_tol;
+    if (!lift && proj_adapt > 0.0) {
       const double scale = std::max(1.0, std::fabs(lam[nb - 1]));
       ptol = std::min(1e-4, std::max(proj_tol, proj_adapt * maxres / scale));
     }
@@ -537,7 +579,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     t_proj += since(t0);
     t0 = tick();
     BLOCH_CUDA(cudaMemcpy2DAsync(S.p + mb, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
-    op(S.p + mb, ld, AS.p + mb, ld, mb, 1.0, 0.0);
+    opA(S.p + mb, ld, AS.p + mb, ld, mb);
     op(S.p + mb, ld, MS.p + mb, ld, mb, 0.0, 1.0);
     t_op += since(t0);
     t0 = tick();
@@ -548,7 +590,10 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     if (need_refresh || refresh_every <= 1 || (it % refresh_every) == refresh_every - 1) {
       // recompute A X and M X from X instead of carrying them by recurrence; after a degenerate
       // Rayleigh-Ritz the search direction block is discarded as well
-      op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);
+      // lifted mode: the gradient content X picked up from the roughly projected W / P is removed here
+      // (relative to its own small size), before A_tau X and M X are rebuilt from X
+      if (lift) { int its2 = 0; project_ld(this, S.p, ld, mb, lift_xtol, 3000, &its2); }
+      opA(S.p, ld, AS.p, ld, mb);
       op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
       if (need_refresh) have_P = false;
       need_refresh = false;

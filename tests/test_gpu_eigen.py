@@ -117,3 +117,35 @@ def test_golden_fixtures(bloch):
         eq.SetAbsoluteTolerance(1e-7)
         lam = eq.GetEigenvalues(2 * nb, np.array(c["kappa"]))[0::2]
         assert np.allclose(lam, c["eigenvalues"], rtol=1e-7, atol=1e-8), (c["lattice"], c["order"], lam, c["eigenvalues"])
+
+
+@pytest.mark.parametrize("name,n,p", [("FCC", 2, 2), ("CUB", 4, 1), ("BCC", 2, 1)])
+def test_warm_started_path_matches_oracle_at_every_point(bloch, name, n, p):
+    """A k-path on ONE handle: from the second point on the solver warm-starts from the previous
+    eigenvectors and runs its gradient-lifted iteration (roughly projected search directions, lifted
+    pencil A + tau M G B G^H M).  Every point, including Gamma reached from a neighbour, must give the
+    eigenvalues of the constrained pencil and divergence-free, M-orthonormal eigenvectors."""
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, p)
+    eps = bloch.sphere_eps(eq.element_centers(), 0.3, 7.0, 1.0)
+    eq.SetMassCoef(eps)
+    nb = 4
+    eq.SetNumEigs(2 * nb)
+    eq.SetAbsoluteTolerance(1e-8)
+    ops, _ = oracle_on_product_maps(eq, name, n, p, eps)
+    X = L.GetSymmetryPoint(1)
+    path = [X, 0.7 * X, 0.4 * X + np.array([0.1, 0.0, 0.2]), 0.1 * X, np.zeros(3), 0.5 * X]
+    for k in path:
+        eq.SetKappa(k)
+        eq.Setup()
+        eq.Solve()
+        lam = eq.band_eigenvalues()
+        ref = ops.set_kappa(k).eig_dense(nb)
+        assert np.allclose(lam, ref, rtol=1e-7, atol=1e-7), (k, lam, ref)
+        G, M = ops.G_c(), ops.M_c()
+        for i in range(nb):
+            er, ei = eq.GetEigenvectorE(i)
+            x = er + 1j * ei
+            assert np.abs(G.conj().T @ (M @ x)).max() < 1e-7          # divergence constraint
+            r = ops.A_c() @ x - lam[i] * (M @ x)
+            assert np.linalg.norm(r) < 5e-7 * max(1.0, np.linalg.norm(M @ x))
