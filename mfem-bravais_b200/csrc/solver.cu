@@ -370,12 +370,14 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   // (only with a warm start: tau must sit a modest factor above the wanted bands, and the Ritz values of a
   // random block say nothing about them)
   const bool warm_block = warm && !(prob.use_init && n_init > 0) && have_vectors == mb && d_X.n >= (size_t)Nl * mb;
-  const bool lift = prob.constrained && mg && use_mg && !two_pass && warm_block && env_double("BLOCH_LIFT", 1.0) != 0.0;
+  const bool lift_allowed = prob.constrained && mg && use_mg && !two_pass && env_double("BLOCH_LIFT", 1.0) != 0.0;
+  bool lift = false;            // switched on right after the initial Rayleigh-Ritz (warm start) or, from a cold
+                                // start, once the exactly projected iteration has settled the Ritz values
   const double lift_factor = env_double("BLOCH_LIFT_TAU", 8.0);
   const double lift_ptol = env_double("BLOCH_LIFT_PROJ_TOL", 1e-1);
   const double lift_xtol = env_double("BLOCH_LIFT_X_TOL", 1e-1);
   double tau = 0.0;
-  if (lift) { lw.Lu.alloc((size_t)N0 * mb); lw.Lphi.alloc((size_t)N0 * mb); lw.Lg.alloc((size_t)Nl * mb); }
+  if (lift_allowed) { lw.Lu.alloc((size_t)N0 * mb); lw.Lphi.alloc((size_t)N0 * mb); lw.Lg.alloc((size_t)Nl * mb); }
   auto opA = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec) {   // y = A_tau x
     op(x, ldx, y, ldy, nvec, 1.0, 0.0);
     if (!lift || tau <= 0.0) return;
@@ -519,13 +521,20 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);    // X is divergence-free to 1e-10 here: A_tau X = A X
     op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
     if (!rayleigh_ritz(mb)) throw std::runtime_error("initial block is rank deficient");
-    if (lift) {
-      double top = 0.0;
-      for (int j = 0; j < mb; j++) top = std::max(top, std::fabs(lam[j]));
-      tau = lift_factor * std::max(top, 1e-3 / vol23);
-      if (verbose) std::printf("[lobpcg] gradient lift tau = %.4g (%.1f x top Ritz value)\n", tau, lift_factor);
-    }
   }
+  double top_prev = 0.0;
+  auto top_ritz = [&]() {
+    double top = 0.0;
+    for (int j = 0; j < mb; j++) top = std::max(top, std::fabs(lam[j]));
+    return top;
+  };
+  auto enable_lift = [&]() {   // X (and P) are exactly projected at this point: A_tau = A on them
+    lift = true;
+    tau = lift_factor * std::max(top_ritz(), 1e-3 / vol23);
+    if (verbose) std::printf("[lobpcg] gradient lift on, tau = %.4g (%.1f x top Ritz value)\n", tau, lift_factor);
+  };
+  if (lift_allowed && warm_block) enable_lift();
+  top_prev = top_ritz();
 
   double t_pre = 0, t_proj = 0, t_op = 0, t_rr = 0, t_res = 0;
   auto tick = [&]() {
@@ -597,6 +606,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
       op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
       if (need_refresh) have_P = false;
       need_refresh = false;
+    }
+    if (lift_allowed && !lift) {
+      const double top = top_ritz();
+      if (it >= 1 && std::fabs(top - top_prev) <= 0.1 * top) enable_lift();
+      top_prev = top;
     }
     t_rr += since(t0);
   }
