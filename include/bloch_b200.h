@@ -147,6 +147,13 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec);
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec);
 
+/* Host-side dense solver of the Rayleigh-Ritz step (csrc/dense.hpp; the reference: hypre LOBPCG's LAPACK calls /
+ * dsygv, meta_material_solver.cpp:3285): lowest m eigenpairs of GA c = lambda GM c, n x n Hermitian row-major
+ * interleaved (re, im); c_reim is n x m.  values_only != 0: the pivoted-Cholesky variant of the reduced-basis sweep
+ * (tolerates nearly dependent bases).  Test hook - needs no GPU. */
+int bloch_debug_hegv(int n, int m, const double *ga_reim, const double *gm_reim, double *lambda, double *c_reim,
+                     int values_only);
+
 /* Assembled operators for interchange (the reference's -wm dump of Ar / Ai / M, maxwell_dispersion.cpp:553-590).
  * which = 0: A = S1 - i beta DKZ (complex Hermitian; Re = the reference's Ar block, Im = its (1,0) block with the
  * coefficient folded in), which = 1: M = M1(eps) (real).  CSR over the ND dofs of bloch_get_dofmap numbering.

@@ -2,6 +2,7 @@
 // MaxwellBlochWaveEquation (maxwell/maxwell_bloch.cpp): constructor :34-140, SetKappa :200-210,
 // Setup :337-620, GetEigenvalues :1052-1076, GetEigenvectorE/B :1371-1458.
 #include "core.hpp"
+#include "dense.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -862,6 +863,29 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// ---- host-side dense Rayleigh-Ritz solver, exposed for the CPU tests (no GPU involved) ----
+int bloch_debug_hegv(int n, int m, const double *ga_reim, const double *gm_reim, double *lambda, double *c_reim,
+                     int values_only) {
+  API_BEGIN
+  REQUIRE(n >= 1 && m >= 1 && m <= n && ga_reim && gm_reim && lambda, "bad argument");
+  dense::Mat GA((size_t)n * n), GM((size_t)n * n), Cm;
+  for (size_t i = 0; i < (size_t)n * n; i++) {
+    GA[i] = dense::cplx(ga_reim[2 * i], ga_reim[2 * i + 1]);
+    GM[i] = dense::cplx(gm_reim[2 * i], gm_reim[2 * i + 1]);
+  }
+  std::vector<double> lam;
+  if (values_only) {
+    if (!dense::hegv_lowest_values(n, m, GA, GM, lam)) return BLOCH_ERR_NOCONV;
+  } else {
+    REQUIRE(c_reim, "null eigenvector output");
+    if (!dense::hegv_lowest(n, m, GA, GM, lam, Cm)) return BLOCH_ERR_NOCONV;
+    for (size_t i = 0; i < (size_t)n * m; i++) { c_reim[2 * i] = Cm[i].real(); c_reim[2 * i + 1] = Cm[i].imag(); }
+  }
+  for (int i = 0; i < m; i++) lambda[i] = lam[i];
   return BLOCH_OK;
   API_END
 }

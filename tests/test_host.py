@@ -140,3 +140,40 @@ def test_sphere_coefficient_and_omega_format(bloch):
     c = np.array([[0.1, 0.1, 0.1], [0.2, 0.2, 0.0], [0.25, 0.0, 0.0], [0.3, 0.0, 0.0]])
     assert bloch.sphere_eps(c).tolist() == [10.0, 1.0, 10.0, 1.0]   # maxwell_dispersion.cpp:1464-1467
     assert omega_of_lambda([4.0, 0.0, -1e-9, -1.0]).tolist() == [2.0, 0.0, 0.0, -1.0]  # :1072-1083
+
+
+@pytest.mark.parametrize("n,m", [(12, 4), (48, 16), (63, 21)])
+def test_dense_rayleigh_ritz_solver_against_scipy(n, m):
+    """csrc/dense.hpp (Cholesky + Householder/QL, lowest-m back-transformation) on Hermitian pencils with
+    degenerate pairs like the Bloch spectra; and the pivoted-Cholesky values-only variant on a nearly dependent
+    basis.  Host code only."""
+    import ctypes as C
+    import scipy.linalg as sla
+    from mfem_bravais_b200 import capi
+    lib = capi.lib()
+    rng = np.random.default_rng(n)
+    D = 3 * n
+    lam_true = np.repeat(np.sort(rng.uniform(1, 50, (D + 1) // 2)), 2)[:D]    # every eigenvalue twice
+    Q, _ = np.linalg.qr(rng.standard_normal((D, D)) + 1j * rng.standard_normal((D, D)))
+    A = (Q * lam_true) @ Q.conj().T
+    X = rng.standard_normal((D, n)) + 1j * rng.standard_normal((D, n))
+    GA, GM = X.conj().T @ A @ X, X.conj().T @ X
+    GA, GM = 0.5 * (GA + GA.conj().T), 0.5 * (GM + GM.conj().T)
+    ref_w, ref_v = sla.eigh(GA, GM)
+    pack = lambda Z: np.ascontiguousarray(np.stack([Z.real, Z.imag], axis=-1))
+    lam, Cr = np.zeros(m), np.zeros((n, m, 2))
+    ga, gm = pack(GA), pack(GM)
+    capi.check(lib.bloch_debug_hegv(n, m, capi.dptr(ga), capi.dptr(gm), capi.dptr(lam), capi.dptr(Cr), 0))
+    assert np.allclose(lam, ref_w[:m], rtol=1e-11, atol=1e-11)
+    Cm = Cr[..., 0] + 1j * Cr[..., 1]
+    assert np.abs(GA @ Cm - (GM @ Cm) * lam).max() < 1e-9 * np.abs(GA).max()          # eigen-residual
+    assert np.abs(Cm.conj().T @ GM @ Cm - np.eye(m)).max() < 1e-10                    # GM-orthonormal
+    # nearly dependent basis: duplicate columns up to 1e-9 noise
+    X2 = np.concatenate([X, X[:, : n // 2] + 1e-9 * rng.standard_normal((D, n // 2))], axis=1)
+    G2A, G2M = X2.conj().T @ A @ X2, X2.conj().T @ X2
+    G2A, G2M = 0.5 * (G2A + G2A.conj().T), 0.5 * (G2M + G2M.conj().T)
+    lam2 = np.zeros(m)
+    n2 = X2.shape[1]
+    g2a, g2m = pack(G2A), pack(G2M)
+    capi.check(lib.bloch_debug_hegv(n2, m, capi.dptr(g2a), capi.dptr(g2m), capi.dptr(lam2), None, 1))
+    assert np.allclose(lam2, ref_w[:m], rtol=1e-6, atol=1e-6)
