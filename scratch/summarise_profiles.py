@@ -18,8 +18,8 @@ for row in csv.DictReader(lines):
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values())
 out.append("# ncu launch list, round %s\n" % R)
-out.append("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 3000 --csv python bench.py --steps 2 --warmup 3 --streams 1 --no-cpu-baseline`")
-out.append("(FCC order 2, n_sub 8, N = 49152, 16-column block; per-launch times are cold-cache and serialised: compare SHARES)\n")
+out.append("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 12000 -c 4000 --csv python bench.py --steps 4 --warmup 3 --streams 1 --no-cpu-baseline`")
+out.append("(FCC order 2, n_sub 8, N = 49152, 16-column block, window inside the warm-started lifted solves; per-launch times are cold-cache and serialised: compare SHARES)\n")
 out.append("| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("| `%s` | %d | %.1f | %.2f | %.1f %% |" % (k[:70], v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
