@@ -728,6 +728,11 @@ cudaError_t curl_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, 
 cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
                             double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s,
                             double2 *z) {
+  if (z == nullptr) {
+    bool launched = false;
+    cudaError_t err = launch_nd_item(p, T, E, x, ldx, y, ldy, nvec, ca, cm, s, &launched);
+    if (err != cudaSuccess || launched) return err;
+  }
   static int variant = -1;
   if (variant < 0) { const char *e = std::getenv("BLOCH_ND_WARPS"); variant = e ? std::atoi(e) : 0; }
   if (variant == 1) {

@@ -54,6 +54,10 @@ struct ElemData {            // device pointers, element order = mesh order
 cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
                             double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s,
                             double2 *z = nullptr);
+// Orders 1 and 2, z == nullptr: the barrier-free lane-pair-per-item kernel (nd_item.cu); launch_nd_apply
+// tries it first.  *launched = false (and nothing done) when it does not apply or BLOCH_ND_ITEM=0.
+cudaError_t launch_nd_item(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
+                           int nvec, double ca, double cm, cudaStream_t s, bool *launched);
 // y[g][v] = sum_{k in [ptr[g], ptr[g+1])} sign(loc[k]) * z[(|loc[k]|-1)*m + v]
 cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *z, double2 *y, long n,
                              int m, int ldy, cudaStream_t s);
