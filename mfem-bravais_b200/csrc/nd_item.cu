@@ -13,6 +13,7 @@
 // Per item and real part at p = 2: 1188 DFMA of contractions + ~350 pointwise, 54 gathers, 54 RED.ADD.F64.
 #include "kernels.hpp"
 
+#include <cmath>
 #include <cstdlib>
 
 #include "elem_device.cuh"
@@ -23,26 +24,55 @@ namespace {
 
 using namespace dev;
 
+// Tables of this kernel (orders <= 2), SCALED so that every mode coefficient carries the square root of its diagonal
+// 1-D mass weight:  TI = diag(sqrt(om)) TI,  Dt[a][r] = sqrt(om[a]) Dt[a][r] / sqrt(om[r]),  TIo[o] = sqrt(om[o]) TI
+// (the first pass of slab o also applies the weight of the slab's open direction; open Gauss-Lagrange directions
+// have the weights om[a], a < p, of the first p closed modes).  Both mode-space mass matrices are then the plain
+// pointwise 3x3 couplings G and H, and the Bloch shift -i kappa_hat stays the identity between mode a and open
+// point a: no weight products per grid point.
+constexpr int kItemMaxP = 2;
+struct ItemTabs {
+  double TI[kItemMaxP + 1][kItemMaxP + 1];
+  double TIo[kItemMaxP][kItemMaxP + 1][kItemMaxP + 1];
+  double Dt[kItemMaxP][kItemMaxP + 1];
+};
+
+ItemTabs item_tabs(const Tabs &T, int p) {
+  ItemTabs S = {};
+  double sq[kItemMaxP + 1];
+  for (int r = 0; r <= p; r++) sq[r] = std::sqrt(T.om[r]);
+  for (int r = 0; r <= p; r++)
+    for (int j = 0; j <= p; j++) {
+      S.TI[r][j] = sq[r] * T.TI[r][j];
+      for (int o = 0; o < p; o++) S.TIo[o][r][j] = sq[o] * sq[r] * T.TI[r][j];
+    }
+  for (int a = 0; a < p; a++)
+    for (int r = 0; r <= p; r++) S.Dt[a][r] = sq[a] * T.Dt[a][r] / sq[r];
+  return S;
+}
+
+// s[a][b] (Q x Q): apply M1 along b, then M2 along a.  FWD: out[r] = sum_j M[r][j] in[j]; ADJ: out[j] = sum_r M[r][j] in[r]
 template <int P, bool ADJ>
-__device__ __forceinline__ void slab_tf(double (&s)[P + 1][P + 1], const double (&Mx)[kMaxP + 1][kMaxP + 1]) {
+__device__ __forceinline__ void slab_tf(double (&s)[P + 1][P + 1], const double (&M1)[kItemMaxP + 1][kItemMaxP + 1],
+                                        const double (&M2)[kItemMaxP + 1][kItemMaxP + 1]) {
   constexpr int Q = P + 1;
   double u[Q][Q];
 #pragma unroll
   for (int a = 0; a < Q; a++)
 #pragma unroll
     for (int r = 0; r < Q; r++) {
-      double acc = (ADJ ? Mx[0][r] : Mx[r][0]) * s[a][0];
+      double acc = (ADJ ? M1[0][r] : M1[r][0]) * s[a][0];
 #pragma unroll
-      for (int j = 1; j < Q; j++) acc = fma(ADJ ? Mx[j][r] : Mx[r][j], s[a][j], acc);
+      for (int j = 1; j < Q; j++) acc = fma(ADJ ? M1[j][r] : M1[r][j], s[a][j], acc);
       u[a][r] = acc;
     }
 #pragma unroll
   for (int r = 0; r < Q; r++)
 #pragma unroll
     for (int b = 0; b < Q; b++) {
-      double acc = (ADJ ? Mx[0][r] : Mx[r][0]) * u[0][b];
+      double acc = (ADJ ? M2[0][r] : M2[r][0]) * u[0][b];
 #pragma unroll
-      for (int j = 1; j < Q; j++) acc = fma(ADJ ? Mx[j][r] : Mx[r][j], u[j][b], acc);
+      for (int j = 1; j < Q; j++) acc = fma(ADJ ? M2[j][r] : M2[r][j], u[j][b], acc);
       s[r][b] = acc;
     }
 }
@@ -62,9 +92,11 @@ __device__ __forceinline__ double partner(double x) {
 }
 
 // NT = threads per block = the register budget (65536 / NT per thread): 512 -> 128 registers, 16 warps per SM
-template <int P, bool HAS_A, bool HAS_M, int NT>
+// GV (gather variant): 0 = component by component (index loads, value loads, transform; compiler fences in between
+// keep the register pressure of the 168-register build down), 1 = all indices first (8-byte loads), no fences.
+template <int P, bool HAS_A, bool HAS_M, int NT, int GV>
 __global__ void __launch_bounds__(NT, 1)
-k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
+k_nd_item(const __grid_constant__ ItemTabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
           int m, int ldx, int ldy, long n_items, double ca, double cm) {
   using D = Dim<P>;
   constexpr int Q = P + 1;
@@ -81,25 +113,42 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
   const double sg = part ? -1.0 : 1.0;
   const long ntiles = (n_items + 15) >> 4;
   const bool small = n_items < 0x7fffffffL;
+  // 32-bit offsets in doubles (the launcher checks 2 * n_dofs * ld < 2^32):  (|s| - 1) * 2 ld + 2 v + part
+  const unsigned xstep = 2u * (unsigned)ldx, ystep = 2u * (unsigned)ldy;
+  const long tstride = (long)gridDim.x * nwarps;
 
-  for (long tile = (long)warp * gridDim.x + blockIdx.x; tile < ntiles; tile += (long)gridDim.x * nwarps) {
+  // element / vector of this lane's item in a tile; idle lanes of the last tile shadow a valid item and add zeros
+  auto locate = [&](long tile, int &e, int &v) -> bool {
     long item = tile * 16 + (lane >> 1);
-    const bool active = item < n_items;
-    if (!active) item = n_items - 1;            // idle lanes of the last tile shadow a valid item and add zeros
-    const int e = small ? (int)((unsigned)item / (unsigned)m) : (int)(item / m);
-    const int v = (int)(item - (long)e * m);
+    const bool act = item < n_items;
+    if (!act) item = n_items - 1;
+    e = small ? (int)((unsigned)item / (unsigned)m) : (int)(item / m);
+    v = (int)(item - (long)e * m);
+    return act;
+  };
+  long tile = (long)warp * gridDim.x + blockIdx.x;
+  for (; tile < ntiles; tile += tstride) {
+    int e, v;
+    const bool active = locate(tile, e, v);
     const int32_t *mp = E.map_nd + (long)e * D::LND;
     const double *cp = sCP + kClassParDoubles * __ldg(E.cls + e);
-    // 32-bit offsets in doubles (the launcher checks 2 * n_dofs * ld < 2^32):  (|s| - 1) * 2 ld + 2 v + part
-    const unsigned xstep = 2u * (unsigned)ldx, ystep = 2u * (unsigned)ldy;
     const unsigned xoff = 2u * (unsigned)v + (unsigned)part - xstep, yoff = 2u * (unsigned)v + (unsigned)part - ystep;
 
     // ---- signed gather + nodal -> mode in the closed directions, one component at a time ----
+    int aidx[GV == 1 ? D::LND : 1];
+    if (GV == 1) {
+      static_assert(D::LND % 2 == 0, "8-byte index loads");
+#pragma unroll
+      for (int k = 0; k < D::LND / 2; k++) {
+        const int2 t = __ldg(reinterpret_cast<const int2 *>(mp) + k);
+        aidx[2 * k] = t.x; aidx[2 * k + 1] = t.y;
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       int sidx[D::NB];
 #pragma unroll
-      for (int k = 0; k < D::NB; k++) sidx[k] = __ldg(mp + c * D::NB + k);
+      for (int k = 0; k < D::NB; k++) sidx[k] = GV == 1 ? aidx[c * D::NB + k] : __ldg(mp + c * D::NB + k);
       double xv[D::NB];
 #pragma unroll
       for (int k = 0; k < D::NB; k++) {
@@ -117,13 +166,13 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
             const int k = (o * Q + a) * Q + b;
             s[a][b] = xv[k];
           }
-        slab_tf<P, false>(s, T.TI);
+        slab_tf<P, false>(s, T.TIo[o], T.TI);
 #pragma unroll
         for (int a = 0; a < Q; a++)
 #pragma unroll
           for (int b = 0; b < Q; b++) col[D::nd(c, o, a, b) * 32] = s[a][b];
       }
-      asm volatile("" ::: "memory");   // keep the three components' gathers apart (register pressure)
+      if (GV == 0) asm volatile("" ::: "memory");   // keep the three components' gathers apart (register pressure)
     }
     __syncwarp();
 
@@ -163,9 +212,11 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
             }
         }
       }
-      // ---- pointwise RT mass, scaled by ca * muinv ----
+      // ---- pointwise RT mass, scaled by ca * muinv (mode-space weights are 1 with the scaled tables) ----
       const double wA = active ? ca * __ldg(E.muinv + e) : 0.0;   // idle lanes produce exact zeros
-      const double *G = cp + 3;
+      double G[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) G[k] = wA * cp[3 + k];
 #pragma unroll
       for (int i0 = 0; i0 < Q; i0++)
 #pragma unroll
@@ -175,17 +226,16 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
             const int i[3] = {i0, i1, i2};
             const int nopen = (i0 < P) + (i1 < P) + (i2 < P);
             if (nopen < 2) continue;
-            const double w = wA * (T.om[i0] * T.om[i1] * T.om[i2]);
             if (nopen == 3) {
               const int l0 = D::rt(0, i0, i1, i2), l1 = D::rt(1, i1, i2, i0), l2 = D::rt(2, i2, i0, i1);
               const double f0 = R[l0], f1 = R[l1], f2 = R[l2];
-              R[l0] = w * fma(G[0], f0, fma(G[1], f1, G[2] * f2));
-              R[l1] = w * fma(G[3], f0, fma(G[4], f1, G[5] * f2));
-              R[l2] = w * fma(G[6], f0, fma(G[7], f1, G[8] * f2));
+              R[l0] = fma(G[0], f0, fma(G[1], f1, G[2] * f2));
+              R[l1] = fma(G[3], f0, fma(G[4], f1, G[5] * f2));
+              R[l2] = fma(G[6], f0, fma(G[7], f1, G[8] * f2));
             } else {
               const int c = i0 == P ? 0 : (i1 == P ? 1 : 2);     // the only component living at this point
               const int l = D::rt(c, i[c], i[(c + 1) % 3], i[(c + 2) % 3]);
-              R[l] *= w * G[4 * c];
+              R[l] *= G[4 * c];
             }
           }
     }
@@ -194,7 +244,9 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
     if (HAS_M) {
       // ---- pointwise ND mass in mode space, in place, scaled by cm * eps ----
       const double wM = active ? cm * __ldg(E.eps + e) : 0.0;
-      const double *H = cp + 12;
+      double H[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) H[k] = wM * cp[12 + k];
 #pragma unroll
       for (int i0 = 0; i0 < Q; i0++)
 #pragma unroll
@@ -204,7 +256,6 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
             const int i[3] = {i0, i1, i2};
             const int nopen = (i0 < P) + (i1 < P) + (i2 < P);
             if (nopen == 0) continue;
-            const double w = wM * (T.om[i0] * T.om[i1] * T.om[i2]);
             double f[3];
             int loc[3];
 #pragma unroll
@@ -216,10 +267,11 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
             for (int c = 0; c < 3; c++)
               if (i[c] < P) {
                 double r = 0.0;
+                bool first = true;
 #pragma unroll
                 for (int d = 0; d < 3; d++)
-                  if (i[d] < P) r = fma(H[3 * c + d], f[d], r);
-                col[loc[c] * 32] = w * r;
+                  if (i[d] < P) { r = first ? H[3 * c + d] * f[d] : fma(H[3 * c + d], f[d], r); first = false; }
+                col[loc[c] * 32] = r;
               }
           }
     }
@@ -251,7 +303,7 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
               f[j1][j2] = acc;
             }
         }
-        slab_tf<P, true>(f, T.TI);
+        slab_tf<P, true>(f, T.TIo[o], T.TI);
 #pragma unroll
         for (int a = 0; a < Q; a++)
 #pragma unroll
@@ -267,7 +319,7 @@ k_nd_item(const __grid_constant__ Tabs T, const ElemData E, const double *__rest
   }
 }
 
-template <int P, bool HAS_A, bool HAS_M, int NT>
+template <int P, bool HAS_A, bool HAS_M, int NT, int GV>
 cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
   using D = Dim<P>;
@@ -279,7 +331,7 @@ cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t err = cudaFuncSetAttribute(k_nd_item<P, HAS_A, HAS_M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaError_t err = cudaFuncSetAttribute(k_nd_item<P, HAS_A, HAS_M, NT, GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess) return err;
     smem_cap = (size_t)optin;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -301,17 +353,17 @@ cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
     nw = (int)((ntiles + blocks - 1) / blocks);
   }
   const size_t smem = cp_bytes + per_warp * nw;
-  k_nd_item<P, HAS_A, HAS_M, NT><<<(unsigned)blocks, nw * 32, smem, s>>>(
-      T, E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca, cm);
+  k_nd_item<P, HAS_A, HAS_M, NT, GV><<<(unsigned)blocks, nw * 32, smem, s>>>(
+      item_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca, cm);
   return cudaGetLastError();
 }
 
-template <int P, int NT>
+template <int P, int NT, int GV>
 cudaError_t nd_item_p(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
-  if (ca != 0.0 && cm != 0.0) return nd_item_t<P, true, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
-  if (ca != 0.0) return nd_item_t<P, true, false, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
-  return nd_item_t<P, false, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  if (ca != 0.0 && cm != 0.0) return nd_item_t<P, true, true, NT, GV>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  if (ca != 0.0) return nd_item_t<P, true, false, NT, GV>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  return nd_item_t<P, false, true, NT, GV>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
 }
 
 }  // namespace
@@ -324,12 +376,15 @@ cudaError_t launch_nd_item(int p, const Tabs &T, const ElemData &E, const double
   if (enabled < 0) { const char *e = std::getenv("BLOCH_ND_ITEM"); enabled = e ? std::atoi(e) : 1; }
   *launched = false;
   if (!enabled || p > 2 || (ca == 0.0 && cm == 0.0)) return cudaSuccess;
-  static int threads = -1;    // BLOCH_ND_ITEM_THREADS: register budget / warps per SM trade-off at order 2
-  if (threads < 0) { const char *e = std::getenv("BLOCH_ND_ITEM_THREADS"); threads = e ? std::atoi(e) : 384; }
-  if (p == 1) return nd_item_p<1, 512>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  if (threads == 256) return nd_item_p<2, 256>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  if (threads == 512) return nd_item_p<2, 512>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  return nd_item_p<2, 384>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  // BLOCH_ND_ITEM_MODE (order 2): 1 = 12 warps per SM (168 registers), gather component by component (default);
+  // 2 = same, all indices first; 3 = 8 warps per SM (255 registers), all indices first
+  static int mode = -1;
+  if (mode < 0) { const char *e = std::getenv("BLOCH_ND_ITEM_MODE"); mode = e ? std::atoi(e) : 2; }
+  if (p == 1) return mode == 1 ? nd_item_p<1, 512, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched)
+                               : nd_item_p<1, 512, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (mode == 2) return nd_item_p<2, 384, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (mode == 3) return nd_item_p<2, 256, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  return nd_item_p<2, 384, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
 }
 
 }  // namespace bloch_b200

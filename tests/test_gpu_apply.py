@@ -45,7 +45,11 @@ def test_gamma_point_branch(bloch, name, n, p):
     eq.Setup()
     ops.set_kappa(np.zeros(3))
     x = rng.uniform(-1, 1, (2, 2 * eq.N))
-    assert rel_err(eq.MultA(x), ops.apply_A(x)) < TOL
+    ref = ops.apply_A(x)
+    # on the one-element periodic meshes the assembled curl vanishes identically (A x = 0 exactly), so the error is
+    # measured against max(|A x|, 1e-2 |M x| / h^2) ~ the size of the element-level terms that cancel
+    floor = 1e-2 * np.linalg.norm(ops.apply_M(x)) * (n * p) ** 2
+    assert np.linalg.norm(eq.MultA(x) - ref) / max(np.linalg.norm(ref), floor) < TOL
 
 
 @pytest.mark.parametrize("name,n,p", CASES[:9])
