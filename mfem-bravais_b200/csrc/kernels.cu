@@ -730,7 +730,9 @@ cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const doubl
                             double2 *z) {
   if (z == nullptr) {
     bool launched = false;
-    cudaError_t err = launch_nd_item(p, T, E, x, ldx, y, ldy, nvec, ca, cm, s, &launched);
+    cudaError_t err = launch_nd_comp(p, T, E, x, ldx, y, ldy, nvec, ca, cm, s, &launched);
+    if (err != cudaSuccess || launched) return err;
+    err = launch_nd_item(p, T, E, x, ldx, y, ldy, nvec, ca, cm, s, &launched);
     if (err != cudaSuccess || launched) return err;
   }
   static int variant = -1;

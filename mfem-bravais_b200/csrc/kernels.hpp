@@ -58,6 +58,10 @@ cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const doubl
 // tries it first.  *launched = false (and nothing done) when it does not apply or BLOCH_ND_ITEM=0.
 cudaError_t launch_nd_item(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
                            int nvec, double ca, double cm, cudaStream_t s, bool *launched);
+// Orders 1..3, z == nullptr: the barrier-free six-lanes-per-item kernel (nd_comp.cu), tried before launch_nd_item
+// for the orders selected by BLOCH_ND_COMP (bit mask, default: order 3).
+cudaError_t launch_nd_comp(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
+                           int nvec, double ca, double cm, cudaStream_t s, bool *launched);
 // y[g][v] = sum_{k in [ptr[g], ptr[g+1])} sign(loc[k]) * z[(|loc[k]|-1)*m + v]
 cudaError_t launch_nd_reduce(const int *ptr, const int32_t *loc, const double2 *z, double2 *y, long n,
                              int m, int ldy, cudaStream_t s);

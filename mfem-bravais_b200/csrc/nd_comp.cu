@@ -1,0 +1,362 @@
+// y += ca * A x + cm * M x on ND block vectors, orders 1..3: barrier-free "six lanes per item" kernel.
+//
+// Same mode-space element operator as k_nd_apply (kernels.cu) and k_nd_item (nd_item.cu).  Mapping:
+//   * one (element, vector) item is handled by SIX lanes = 3 vector components x (real, imaginary part); a warp
+//     works on 5 items (lanes 30, 31 shadow lanes 24, 25 and never write).  The kernel's local storage is cyclic
+//     (ND component c = [open c][closed c+1][closed c+2], RT component c = [closed c][open c+1][open c+2]), so
+//     the six lanes run ONE instruction stream with compile-time tensor indices; what differs per lane is only
+//     which lanes hold components c+1, c+2 (two lane offsets) and five scalars (kappa_hat, one row of G, H);
+//   * a lane keeps its ND component (p (p+1)^2 reals) in a lane-private shared-memory column and its RT component
+//     (p^2 (p+1) reals) in registers.  The curl reads the other components from the neighbours' columns, the
+//     pointwise RT mass (3 x 3 coupling G at a grid point) fetches them with shuffles (cyclic orbits of the grid
+//     point, so that old values are still in place), the adjoint curl reads the neighbours' RT columns and the ND
+//     mass part is folded into the adjoint stage (no in-place update, hence no ordering hazards);
+//   * no block barrier, three __syncwarp per tile; registers ~ 1/3 of the lane-pair kernel, so order 3 fits
+//     (RT component = 36 reals) and orders 1, 2 run with many more warps per SM.
+// Tables are the sqrt-weight scaled ones of nd_item.cu (all mode-space mass weights equal 1).
+#include "kernels.hpp"
+
+#include <cmath>
+#include <cstdlib>
+
+#include "elem_device.cuh"
+
+namespace bloch_b200 {
+
+namespace {
+
+using namespace dev;
+
+struct CompTabs {
+  double TI[kMaxP][kMaxP];             // orders <= 3: (p+1) x (p+1)
+  double TIo[kMaxP - 1][kMaxP][kMaxP];
+  double Dt[kMaxP - 1][kMaxP];
+};
+
+CompTabs comp_tabs(const Tabs &T, int p) {
+  CompTabs S = {};
+  double sq[kMaxP];
+  for (int r = 0; r <= p; r++) sq[r] = std::sqrt(T.om[r]);
+  for (int r = 0; r <= p; r++)
+    for (int j = 0; j <= p; j++) {
+      S.TI[r][j] = sq[r] * T.TI[r][j];
+      for (int o = 0; o < p; o++) S.TIo[o][r][j] = sq[o] * sq[r] * T.TI[r][j];
+    }
+  for (int a = 0; a < p; a++)
+    for (int r = 0; r <= p; r++) S.Dt[a][r] = sq[a] * T.Dt[a][r] / sq[r];
+  return S;
+}
+
+// s[a][b] (Q x Q): apply M1 along b, then M2 along a.  FWD: out[r] = sum_j M[r][j] in[j]; ADJ: out[j] = sum_r M[r][j] in[r]
+template <int P, bool ADJ>
+__device__ __forceinline__ void slab_tf(double (&s)[P + 1][P + 1], const double (&M1)[kMaxP][kMaxP],
+                                        const double (&M2)[kMaxP][kMaxP]) {
+  constexpr int Q = P + 1;
+  double u[Q][Q];
+#pragma unroll
+  for (int a = 0; a < Q; a++)
+#pragma unroll
+    for (int r = 0; r < Q; r++) {
+      double acc = (ADJ ? M1[0][r] : M1[r][0]) * s[a][0];
+#pragma unroll
+      for (int j = 1; j < Q; j++) acc = fma(ADJ ? M1[j][r] : M1[r][j], s[a][j], acc);
+      u[a][r] = acc;
+    }
+#pragma unroll
+  for (int r = 0; r < Q; r++)
+#pragma unroll
+    for (int b = 0; b < Q; b++) {
+      double acc = (ADJ ? M2[0][r] : M2[r][0]) * u[0][b];
+#pragma unroll
+      for (int j = 1; j < Q; j++) acc = fma(ADJ ? M2[j][r] : M2[r][j], u[j][b], acc);
+      s[r][b] = acc;
+    }
+}
+
+__device__ __forceinline__ double flip(double x, int s) {
+  return __hiloint2double(__double2hiint(x) ^ (s & (int)0x80000000), __double2loint(x));
+}
+
+// predicated fp64 reduction (no branch around the RED)
+__device__ __forceinline__ void red_add_if(double *p, double v, bool on) {
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q red.global.add.f64 [%0], %1; }" ::"l"(p), "d"(v), "r"((int)on)
+               : "memory");
+}
+
+constexpr int kItemsPerWarp = 5;
+
+template <int P, bool HAS_A, bool HAS_M, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
+          int m, int ldx, int ldy, long n_items, double ca, double cm) {
+  using D = Dim<P>;
+  constexpr int Q = P + 1, NB = D::NB, RB = D::RB;
+  constexpr int WCOLS = NB + (HAS_A ? RB : 0);        // column entries per lane
+  auto nd0 = [](int o, int j1, int j2) { return (o * Q + j1) * Q + j2; };    // local index in the own ND component
+  auto rt0 = [](int j, int o1, int o2) { return (j * P + o1) * P + o2; };    // ... in the own RT component
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sCP = reinterpret_cast<double *>(smem_raw);
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+  const int ncp = E.n_class * kClassParDoubles;
+  for (int i = threadIdx.x; i < ncp; i += blockDim.x) sCP[i] = E.cpar[i];
+  __syncthreads();
+  // lane roles: lane = 6 slot + 2 c + part; lanes 30, 31 shadow lanes 24, 25
+  const int rl = lane < 30 ? lane : lane - 6;
+  const int slot = rl / 6, c = (rl - 6 * slot) >> 1, part = rl & 1;
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+  const int lane1 = 6 * slot + 2 * c1 + part, lane2 = 6 * slot + 2 * c2 + part;
+  double *wbase = sCP + ((ncp + 1) & ~1) + (size_t)warp * (WCOLS * 32);
+  double *Fc = wbase + lane;                                          // own ND component
+  const double *F1 = wbase + lane1, *F2 = wbase + lane2;              // components c+1, c+2 of the same part
+  const double *F1p = wbase + (lane1 ^ 1), *F2p = wbase + (lane2 ^ 1);   // ... of the other part
+  const int rofs = NB * 32;                                           // RT columns behind the ND columns
+  const double sg = part ? -1.0 : 1.0;
+  const long ntiles = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
+  const bool small = n_items < 0x7fffffffL;
+  const unsigned xstep = 2u * (unsigned)ldx, ystep = 2u * (unsigned)ldy;
+  const long tstride = (long)gridDim.x * nwarps;
+
+  for (long tile = (long)warp * gridDim.x + blockIdx.x; tile < ntiles; tile += tstride) {
+    long item = tile * kItemsPerWarp + slot;
+    const bool active = item < n_items;
+    if (!active) item = n_items - 1;            // idle slots of the last tile shadow a valid item with zero weights
+    const bool writes = active && lane < 30;
+    const int e = small ? (int)((unsigned)item / (unsigned)m) : (int)(item / m);
+    const int v = (int)(item - (long)e * m);
+    const int32_t *mp = E.map_nd + (long)e * D::LND + c * NB;
+    const double *cp = sCP + kClassParDoubles * __ldg(E.cls + e);
+    // 32-bit offsets in doubles (the launcher checks 2 * n_dofs * ld < 2^32):  (|s| - 1) * 2 ld + 2 v + part
+    const unsigned xoff = 2u * (unsigned)v + (unsigned)part - xstep, yoff = 2u * (unsigned)v + (unsigned)part - ystep;
+
+    // ---- signed gather of the own component + nodal -> mode in its two closed directions ----
+    // (chunks of whole slabs with an even number of entries: 8-byte index loads; one slab at order 3)
+    {
+      constexpr int SL = (Q * Q) % 2 == 0 ? 1 : P;     // slabs per chunk
+      constexpr int CH = SL * Q * Q;                   // entries per chunk
+      static_assert(CH % 2 == 0 && NB % CH == 0, "8-byte index loads");
+#pragma unroll(P < 3 ? NB / CH : 1)      // order 3: rolled slab loop keeps the register pressure (and the code) small
+      for (int ch = 0; ch < NB / CH; ch++) {
+        int sidx[CH];
+#pragma unroll
+        for (int k = 0; k < CH / 2; k++) {
+          const int2 t = __ldg(reinterpret_cast<const int2 *>(mp + ch * CH) + k);
+          sidx[2 * k] = t.x; sidx[2 * k + 1] = t.y;
+        }
+        double xv[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+          const int s = sidx[k];
+          const unsigned off = (unsigned)(s < 0 ? -s : s) * xstep + xoff;
+          xv[k] = flip(__ldg(X + off), s);
+        }
+#pragma unroll
+        for (int os = 0; os < SL; os++) {
+          const int o = ch * SL + os;
+          double s[Q][Q];
+#pragma unroll
+          for (int a = 0; a < Q; a++)
+#pragma unroll
+            for (int b = 0; b < Q; b++) s[a][b] = xv[nd0(os, a, b)];
+          slab_tf<P, false>(s, T.TIo[o], T.TI);
+#pragma unroll
+          for (int a = 0; a < Q; a++)
+#pragma unroll
+            for (int b = 0; b < Q; b++) Fc[nd0(o, a, b) * 32] = s[a][b];
+        }
+      }
+    }
+    __syncwarp();
+
+    double ks1 = 0.0, ks2 = 0.0;
+    if (HAS_A) {
+      ks1 = sg * cp[c1];
+      ks2 = sg * cp[c2];
+      double R[RB];
+      // ---- Bloch curl: R_c = K_{c+1} F_{c+2} - K_{c+2} F_{c+1},  K_d = Dt - i kh_d (pointwise) ----
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        double A[P][Q], B[P][Q];
+#pragma unroll
+        for (int o = 0; o < P; o++)
+#pragma unroll
+          for (int r = 0; r < Q; r++) {
+            A[o][r] = F2[nd0(o, j, r) * 32];   // F_{c+2}[o2=o, j1=j, j2=r]
+            B[o][r] = F1[nd0(o, r, j) * 32];   // F_{c+1}[o1=o, j1=r, j2=j]
+          }
+#pragma unroll
+        for (int o1 = 0; o1 < P; o1++)
+#pragma unroll
+          for (int o2 = 0; o2 < P; o2++) {
+            const double pa = F2p[nd0(o2, j, o1) * 32];
+            const double pb = F1p[nd0(o1, o2, j) * 32];
+            double acc = ks1 * pa;
+            acc = fma(-ks2, pb, acc);
+#pragma unroll
+            for (int r = 0; r < Q; r++) {
+              acc = fma(T.Dt[o1][r], A[o2][r], acc);
+              acc = fma(-T.Dt[o2][r], B[o1][r], acc);
+            }
+            R[rt0(j, o1, o2)] = acc;
+          }
+      }
+      // ---- pointwise RT mass, scaled by ca * muinv: R'_c = G[c][c] R_c + G[c][c+1] R_{c+1} + G[c][c+2] R_{c+2} ----
+      // The same grid point is (x,y,z) in the own frame, (y,z,x) in the frame of component c+1 and (z,x,y) in
+      // that of c+2, so the three rotations of a point are fetched (shuffles) before any of them is updated.
+      const double wA = active ? ca * __ldg(E.muinv + e) : 0.0;   // idle slots produce exact zeros
+      const double g0 = wA * cp[3 + 3 * c + c], g1 = wA * cp[3 + 3 * c + c1], g2 = wA * cp[3 + 3 * c + c2];
+#pragma unroll
+      for (int o1 = 0; o1 < P; o1++)
+#pragma unroll
+        for (int o2 = 0; o2 < P; o2++) R[rt0(P, o1, o2)] *= g0;      // closed end mode: only this component lives there
+#pragma unroll
+      for (int x = 0; x < P; x++)
+#pragma unroll
+        for (int y = 0; y < P; y++)
+#pragma unroll
+          for (int z = 0; z < P; z++) {
+            const int k0 = rt0(x, y, z), k1 = rt0(y, z, x), k2 = rt0(z, x, y);
+            if (x == y && y == z) {
+              const double a0 = R[k0];
+              const double n1 = __shfl_sync(0xffffffffu, a0, lane1), n2 = __shfl_sync(0xffffffffu, a0, lane2);
+              R[k0] = fma(g0, a0, fma(g1, n1, g2 * n2));
+            } else if (k0 < k1 && k0 < k2) {
+              const double a0 = R[k0], a1 = R[k1], a2 = R[k2];
+              const double n1_0 = __shfl_sync(0xffffffffu, a0, lane1), n2_0 = __shfl_sync(0xffffffffu, a0, lane2);
+              const double n1_1 = __shfl_sync(0xffffffffu, a1, lane1), n2_1 = __shfl_sync(0xffffffffu, a1, lane2);
+              const double n1_2 = __shfl_sync(0xffffffffu, a2, lane1), n2_2 = __shfl_sync(0xffffffffu, a2, lane2);
+              R[k0] = fma(g0, a0, fma(g1, n1_1, g2 * n2_2));
+              R[k1] = fma(g0, a1, fma(g1, n1_2, g2 * n2_0));
+              R[k2] = fma(g0, a2, fma(g1, n1_0, g2 * n2_1));
+            }
+          }
+      // publish R' for the adjoint curl of the other components
+#pragma unroll
+      for (int k = 0; k < RB; k++) Fc[rofs + k * 32] = R[k];
+    }
+    __syncwarp();
+
+    // ---- ND mass part + adjoint curl, mode -> nodal (adjoint), signed scatter-add; one slab at a time ----
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    if (HAS_M) {
+      const double wM = active ? cm * __ldg(E.eps + e) : 0.0;
+      h0 = wM * cp[12 + 3 * c + c]; h1 = wM * cp[12 + 3 * c + c1]; h2 = wM * cp[12 + 3 * c + c2];
+    }
+#pragma unroll(P < 3 ? P : 1)
+    for (int o = 0; o < P; o++) {
+      double f[Q][Q];
+#pragma unroll
+      for (int a = 0; a < Q; a++)
+#pragma unroll
+        for (int b = 0; b < Q; b++) {
+          double acc = 0.0;
+          if (HAS_M) {
+            // F'_c(o,a,b) = H[c][c] F_c(o,a,b) + H[c][c+1] F_{c+1}(a,b,o) + H[c][c+2] F_{c+2}(b,o,a)
+            acc = h0 * Fc[nd0(o, a, b) * 32];
+            if (a < P) acc = fma(h1, F1[nd0(a < P ? a : 0, b, o) * 32], acc);
+            if (b < P) acc = fma(h2, F2[nd0(b < P ? b : 0, o, a) * 32], acc);
+          }
+          f[a][b] = acc;
+        }
+      if (HAS_A) {
+        const double *R1 = F1 + rofs, *R2 = F2 + rofs, *R1p = F1p + rofs, *R2p = F2p + rofs;
+        double Y1[Q][P], Y2[Q][P];
+#pragma unroll
+        for (int a = 0; a < Q; a++)
+#pragma unroll
+          for (int q = 0; q < P; q++) {
+            Y1[a][q] = R1[rt0(a, q, o) * 32];   // R'_{c+1}[j=a, o1=q, o2=o]
+            Y2[a][q] = R2[rt0(a, o, q) * 32];   // R'_{c+2}[j=a, o1=o, o2=q]
+          }
+#pragma unroll
+        for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+          for (int j2 = 0; j2 < Q; j2++) {
+            double acc = f[j1][j2];
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+              acc = fma(T.Dt[q][j2], Y1[j1][q], acc);
+              acc = fma(-T.Dt[q][j1], Y2[j2][q], acc);
+            }
+            if (j2 < P) acc = fma(-ks2, R1p[rt0(j1, j2 < P ? j2 : 0, o) * 32], acc);
+            if (j1 < P) acc = fma(ks1, R2p[rt0(j2, o, j1 < P ? j1 : 0) * 32], acc);
+            f[j1][j2] = acc;
+          }
+      }
+      slab_tf<P, true>(f, T.TIo[o], T.TI);
+#pragma unroll
+      for (int a = 0; a < Q; a++)
+#pragma unroll
+        for (int b = 0; b < Q; b++) {
+          const int s = __ldg(mp + nd0(o, a, b));
+          const unsigned off = (unsigned)(s < 0 ? -s : s) * ystep + yoff;
+          red_add_if(Y + off, flip(f[a][b], s), writes);
+        }
+    }
+    __syncwarp();   // all lanes are done with this tile's columns before the next tile overwrites them
+  }
+}
+
+template <int P, bool HAS_A, bool HAS_M, int NT>
+cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
+                      double ca, double cm, cudaStream_t s, bool *fits) {
+  using D = Dim<P>;
+  static int sms = 0;
+  static size_t smem_cap = 0;
+  const size_t cp_bytes = (size_t)((E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
+  const size_t per_warp = (size_t)(D::NB + (HAS_A ? D::RB : 0)) * 32 * sizeof(double);
+  if (sms == 0) {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaError_t err = cudaFuncSetAttribute(k_nd_comp<P, HAS_A, HAS_M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err != cudaSuccess) return err;
+    smem_cap = (size_t)optin;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int nwarps = (int)((smem_cap - cp_bytes) / per_warp);
+  if (nwarps > NT / 32) nwarps = NT / 32;
+  const double max_off = 2.0 * (double)E.n_elem * D::LND * (double)(ldx > ldy ? ldx : ldy);   // n_dofs <= n_elem * LND
+  *fits = nwarps >= 4 && max_off < 4.0e9;
+  if (!*fits) return cudaSuccess;
+  const long n_items = (long)E.n_elem * nvec;
+  if (n_items == 0) return cudaSuccess;
+  const long ntiles = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
+  long blocks = (ntiles + nwarps - 1) / nwarps;
+  if (blocks > sms) blocks = sms;
+  int nw = nwarps;
+  if (ntiles < (long)sms * nwarps) {      // few tiles: spread them over all SMs with fewer warps per block
+    blocks = ntiles < sms ? ntiles : sms;
+    nw = (int)((ntiles + blocks - 1) / blocks);
+  }
+  const size_t smem = cp_bytes + per_warp * nw;
+  k_nd_comp<P, HAS_A, HAS_M, NT><<<(unsigned)blocks, nw * 32, smem, s>>>(
+      comp_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items,
+      ca, cm);
+  return cudaGetLastError();
+}
+
+template <int P, int NT>
+cudaError_t nd_comp_p(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
+                      double ca, double cm, cudaStream_t s, bool *fits) {
+  if (ca != 0.0 && cm != 0.0) return nd_comp_t<P, true, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  if (ca != 0.0) return nd_comp_t<P, true, false, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  return nd_comp_t<P, false, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+}
+
+}  // namespace
+
+// Returns cudaSuccess with *launched = false when this variant does not apply or is not selected
+// (BLOCH_ND_COMP: bit mask of the orders that use it, default = order 3 only).
+cudaError_t launch_nd_comp(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy,
+                           int nvec, double ca, double cm, cudaStream_t s, bool *launched) {
+  static int mask = -1;
+  if (mask < 0) { const char *e = std::getenv("BLOCH_ND_COMP"); mask = e ? std::atoi(e) : 4; }
+  *launched = false;
+  if (p < 1 || p > 3 || !(mask & (1 << (p - 1))) || (ca == 0.0 && cm == 0.0)) return cudaSuccess;
+  if (p == 1) return nd_comp_p<1, 1024>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (p == 2) return nd_comp_p<2, 768>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  return nd_comp_p<3, 320>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+}
+
+}  // namespace bloch_b200

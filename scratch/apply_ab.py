@@ -7,7 +7,7 @@ import mfem_bravais_b200 as m
 
 st = torch.cuda.Stream()
 flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
-cases = [("CUB", 1, 48), ("FCC", 2, 8), ("FCC", 2, 16), ("HEX", 2, 16)]
+cases = [("CUB", 1, 48), ("FCC", 2, 8), ("FCC", 2, 16), ("HEX", 2, 16), ("BCC", 3, 8), ("BCC", 3, 12)]
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] + str(c[1]) in sys.argv[1:]] or cases
 for name, p, n in cases:
@@ -35,7 +35,7 @@ for name, p, n in cases:
         t = float(np.median(ts))
         print(json.dumps({"case": f"{name} p{p} n{n}", "N": eq.N, "nv": nv, "us": round(t * 1e6, 1),
                           "gdofs": round(eq.N * nv / t / 1e9, 2), "hbm_frac": round(32 * eq.N * nv / t / 6544.7e9, 4),
-                          "item": os.environ.get("BLOCH_ND_ITEM", "1"), "mode": os.environ.get("BLOCH_ND_ITEM_MODE", "2")}),
+                          "item": os.environ.get("BLOCH_ND_ITEM", "1"), "comp": os.environ.get("BLOCH_ND_COMP", "4")}),
               flush=True)
         del x, y
     del eq
