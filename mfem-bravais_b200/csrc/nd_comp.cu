@@ -130,40 +130,45 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
     const unsigned xoff = 2u * (unsigned)v + (unsigned)part - xstep, yoff = 2u * (unsigned)v + (unsigned)part - ystep;
 
     // ---- signed gather of the own component + nodal -> mode in its two closed directions ----
-    // (chunks of whole slabs with an even number of entries: 8-byte index loads; one slab at order 3)
+    // All indices of the component first (8-byte loads), then slab by slab with the NEXT slab's values in flight
+    // while the current one is transformed; the compiler fences keep it from hoisting every load to the top
+    // (register pressure).
     {
-      constexpr int SL = (Q * Q) % 2 == 0 ? 1 : P;     // slabs per chunk
-      constexpr int CH = SL * Q * Q;                   // entries per chunk
-      static_assert(CH % 2 == 0 && NB % CH == 0, "8-byte index loads");
-#pragma unroll(P < 3 ? NB / CH : 1)      // order 3: rolled slab loop keeps the register pressure (and the code) small
-      for (int ch = 0; ch < NB / CH; ch++) {
-        int sidx[CH];
+      static_assert(NB % 2 == 0, "8-byte index loads");
+      int sidx[NB];
 #pragma unroll
-        for (int k = 0; k < CH / 2; k++) {
-          const int2 t = __ldg(reinterpret_cast<const int2 *>(mp + ch * CH) + k);
-          sidx[2 * k] = t.x; sidx[2 * k + 1] = t.y;
+      for (int k = 0; k < NB / 2; k++) {
+        const int2 t = __ldg(reinterpret_cast<const int2 *>(mp) + k);
+        sidx[2 * k] = t.x; sidx[2 * k + 1] = t.y;
+      }
+      double xa[Q * Q], xb[Q * Q];
+#pragma unroll
+      for (int k = 0; k < Q * Q; k++) {
+        const int s = sidx[k];
+        xa[k] = flip(__ldg(X + ((unsigned)(s < 0 ? -s : s) * xstep + xoff)), s);
+      }
+#pragma unroll
+      for (int o = 0; o < P; o++) {
+        if (o + 1 < P) {
+#pragma unroll
+          for (int k = 0; k < Q * Q; k++) {
+            const int s = sidx[(o + 1) * Q * Q + k];
+            xb[k] = flip(__ldg(X + ((unsigned)(s < 0 ? -s : s) * xstep + xoff)), s);
+          }
         }
-        double xv[CH];
+        double s[Q][Q];
 #pragma unroll
-        for (int k = 0; k < CH; k++) {
-          const int s = sidx[k];
-          const unsigned off = (unsigned)(s < 0 ? -s : s) * xstep + xoff;
-          xv[k] = flip(__ldg(X + off), s);
-        }
+        for (int a = 0; a < Q; a++)
 #pragma unroll
-        for (int os = 0; os < SL; os++) {
-          const int o = ch * SL + os;
-          double s[Q][Q];
+          for (int b = 0; b < Q; b++) s[a][b] = xa[a * Q + b];
+        slab_tf<P, false>(s, T.TIo[o], T.TI);
 #pragma unroll
-          for (int a = 0; a < Q; a++)
+        for (int a = 0; a < Q; a++)
 #pragma unroll
-            for (int b = 0; b < Q; b++) s[a][b] = xv[nd0(os, a, b)];
-          slab_tf<P, false>(s, T.TIo[o], T.TI);
+          for (int b = 0; b < Q; b++) Fc[nd0(o, a, b) * 32] = s[a][b];
+        if (P == 3) asm volatile("" ::: "memory");
 #pragma unroll
-          for (int a = 0; a < Q; a++)
-#pragma unroll
-            for (int b = 0; b < Q; b++) Fc[nd0(o, a, b) * 32] = s[a][b];
-        }
+        for (int k = 0; k < Q * Q; k++) xa[k] = xb[k];
       }
     }
     __syncwarp();
@@ -244,6 +249,9 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
     }
 #pragma unroll(P < 3 ? P : 1)
     for (int o = 0; o < P; o++) {
+      int sc[Q * Q];                      // this slab's scatter indices, requested before the arithmetic needs them
+#pragma unroll
+      for (int k = 0; k < Q * Q; k++) sc[k] = __ldg(mp + o * Q * Q + k);
       double f[Q][Q];
 #pragma unroll
       for (int a = 0; a < Q; a++)
@@ -288,7 +296,7 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
       for (int a = 0; a < Q; a++)
 #pragma unroll
         for (int b = 0; b < Q; b++) {
-          const int s = __ldg(mp + nd0(o, a, b));
+          const int s = sc[a * Q + b];
           const unsigned off = (unsigned)(s < 0 ? -s : s) * ystep + yoff;
           red_add_if(Y + off, flip(f[a][b], s), writes);
         }

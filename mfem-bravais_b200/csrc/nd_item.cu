@@ -383,7 +383,7 @@ cudaError_t launch_nd_item(int p, const Tabs &T, const ElemData &E, const double
   if (p == 1) return mode == 1 ? nd_item_p<1, 512, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched)
                                : nd_item_p<1, 512, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
   if (mode == 2) return nd_item_p<2, 384, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  if (mode == 3) return nd_item_p<2, 256, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (mode == 3) return nd_item_p<2, 512, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
   return nd_item_p<2, 384, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
 }
 

@@ -40,13 +40,18 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
-md = ["# ncu --set full captures of k_nd_apply, round %s\n" % R,
-      "`ncu --set full --clock-control none --import-source on -k regex:k_nd_apply -s 3 -c 1 python scratch/apply_once.py <lattice> <p> <n_sub> 10`\n"]
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+md = ["# ncu --set full captures of the ND operator apply kernels, round %s\n" % R,
+      "`ncu --set full --clock-control none --import-source on -k regex:k_nd_(item|comp) -s 6 -c 1 python scratch/apply_one.py <lattice> <p> <n_sub> <vectors>`\n",
+      "k_nd_item = lane pair per item (orders 1-2, nd_item.cu), k_nd_comp = six lanes per item (order 3, nd_comp.cu); the superseded "
+      "cooperative-tile kernel k_nd_apply (kernels.cu) measured 26.3 us / 865 us on the first / third workload below.\n"]
 traffic = {}
-for tag, desc, N in [("fcc_p2_n8", "FCC order 2 n_sub 8 (bench workload), N = 49152, 10 vectors", 49152),
-                     ("bcc_p3_n12", "BCC order 3 n_sub 12 (roofline study), N = 2239488, 10 vectors", 2239488)]:
-    rep = "gpurun_out/prof_nd_apply_%s_%s.ncu-rep" % (tag, R)
+for tag, desc, N, nvec in [("fcc_p2_n8", "k_nd_item: FCC order 2 n_sub 8 (bench workload), N = 49152, 10 vectors", 49152, 10),
+                           ("fcc_p2_n16", "k_nd_item: FCC order 2 n_sub 16, N = 393216, 16 vectors (solver block)", 393216, 16),
+                           ("bcc_p3_n12", "k_nd_comp: BCC order 3 n_sub 12 (roofline study), N = 2239488, 10 vectors", 2239488, 10)]:
+    rep = "gpurun_out/prof_nd_%s_%s.ncu-rep" % (tag, R)
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -63,9 +68,9 @@ for tag, desc, N in [("fcc_p2_n8", "FCC order 2 n_sub 8 (bench workload), N = 49
         v, u = vals[k]
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     tr = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
-    alg = 32.0 * N * 10
-    traffic[tag] = {"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": alg, "ratio": tr / alg, "N": N, "vectors": 10}
-    md.append("\nDRAM traffic %.1f MB per launch vs algorithmic %.1f MB (32 B x N x 10) -> ratio %.2f\n" % (tr / 1e6, alg / 1e6, tr / alg))
+    alg = 32.0 * N * nvec
+    traffic[tag] = {"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": alg, "ratio": tr / alg, "N": N, "vectors": nvec}
+    md.append("\nDRAM traffic %.1f MB per launch vs algorithmic %.1f MB (32 B x N x %d) -> ratio %.2f\n" % (tr / 1e6, alg / 1e6, nvec, tr / alg))
 open("profiles/ncu_nd_apply_%s.md" % R, "w").write("\n".join(md))
 json.dump(traffic, open("profiles/traffic_%s.json" % R, "w"), indent=1)
 for f in ["bench_%s.json" % R, "apply_study_%s.json" % R]:
