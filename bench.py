@@ -329,7 +329,7 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline(args, steps=1, assumed_iterations=int(round(np.mean(its_all))))
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -359,7 +359,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": res["sample"]}, "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "k-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def apply_study(args):
@@ -406,11 +406,20 @@ def apply_study(args):
                         "tflops": gd * flops_per_dof / 1e3, "fp64_frac": gd * flops_per_dof / 1e3 / fp64})
             del x, y
         del eq
-    print(json.dumps({"apply_study": out, "hbm_peak_gbs": hbm, "hbm_peak_source": how, "fp64_peak_tflops": fp64,
+    _emit(json.dumps({"apply_study": out, "hbm_peak_gbs": hbm, "hbm_peak_source": how, "fp64_peak_tflops": fp64,
                       "note": "timing = cudaMemset of y + k_nd_apply, CUDA events, L2 flushed between launches"}))
 
 
+def _emit(line):
+    """The JSON line goes to the process's ORIGINAL stdout; everything else that writes to fd 1 while the
+    benchmark runs (e.g. NCCL's version banner at communicator creation) is sent to stderr."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.apply_study:
         apply_study(a)

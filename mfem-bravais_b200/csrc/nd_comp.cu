@@ -83,9 +83,11 @@ __device__ __forceinline__ void red_add_if(double *p, double v, bool on) {
                : "memory");
 }
 
-constexpr int kItemsPerWarp = 5;
 
-template <int P, bool HAS_A, bool HAS_M, int NT>
+// IPW = items per warp: 5 (lanes 0..29; the item on lanes 12..17 straddles the two half-warps that serve a 64-bit
+// shared-memory access, which costs bank conflicts on the neighbour-column reads) or 4 (two items per half-warp,
+// lanes 12..15 and 28..31 idle: conflict-free but 20 % fewer items per instruction)
+template <int P, bool HAS_A, bool HAS_M, int NT, int IPW>
 __global__ void __launch_bounds__(NT, 1)
 k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
           int m, int ldx, int ldy, long n_items, double ca, double cm) {
@@ -101,11 +103,16 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
   const int ncp = E.n_class * kClassParDoubles;
   for (int i = threadIdx.x; i < ncp; i += blockDim.x) sCP[i] = E.cpar[i];
   __syncthreads();
-  // lane roles: lane = 6 slot + 2 c + part; lanes 30, 31 shadow lanes 24, 25
-  const int rl = lane < 30 ? lane : lane - 6;
-  const int slot = rl / 6, c = (rl - 6 * slot) >> 1, part = rl & 1;
+  // lane roles: lane = base(slot) + 2 c + part; spare lanes shadow the lane 6 below them and never write
+  constexpr int kItemsPerWarp = IPW;
+  const int hb = IPW == 4 ? (lane & 16) : 0;                 // IPW 4: each half-warp holds two items on its lanes 0..11
+  const int hl = IPW == 4 ? (lane & 15) : lane;
+  const bool spare = IPW == 4 ? hl >= 12 : lane >= 30;
+  const int rl = spare ? hl - 6 : hl;
+  const int s6 = rl / 6, c = (rl - 6 * s6) >> 1, part = rl & 1;
+  const int slot = IPW == 4 ? (hb >> 3) + s6 : s6;
   const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
-  const int lane1 = 6 * slot + 2 * c1 + part, lane2 = 6 * slot + 2 * c2 + part;
+  const int lane1 = hb + 6 * s6 + 2 * c1 + part, lane2 = hb + 6 * s6 + 2 * c2 + part;
   double *wbase = sCP + ((ncp + 1) & ~1) + (size_t)warp * (WCOLS * 32);
   double *Fc = wbase + lane;                                          // own ND component
   const double *F1 = wbase + lane1, *F2 = wbase + lane2;              // components c+1, c+2 of the same part
@@ -121,7 +128,7 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
     long item = tile * kItemsPerWarp + slot;
     const bool active = item < n_items;
     if (!active) item = n_items - 1;            // idle slots of the last tile shadow a valid item with zero weights
-    const bool writes = active && lane < 30;
+    const bool writes = active && !spare;
     const int e = small ? (int)((unsigned)item / (unsigned)m) : (int)(item / m);
     const int v = (int)(item - (long)e * m);
     const int32_t *mp = E.map_nd + (long)e * D::LND + c * NB;
@@ -305,7 +312,7 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
   }
 }
 
-template <int P, bool HAS_A, bool HAS_M, int NT>
+template <int P, bool HAS_A, bool HAS_M, int NT, int IPW>
 cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
   using D = Dim<P>;
@@ -317,7 +324,7 @@ cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t err = cudaFuncSetAttribute(k_nd_comp<P, HAS_A, HAS_M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaError_t err = cudaFuncSetAttribute(k_nd_comp<P, HAS_A, HAS_M, NT, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess) return err;
     smem_cap = (size_t)optin;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -329,7 +336,7 @@ cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
   if (!*fits) return cudaSuccess;
   const long n_items = (long)E.n_elem * nvec;
   if (n_items == 0) return cudaSuccess;
-  const long ntiles = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
+  const long ntiles = (n_items + IPW - 1) / IPW;
   long blocks = (ntiles + nwarps - 1) / nwarps;
   if (blocks > sms) blocks = sms;
   int nw = nwarps;
@@ -338,18 +345,18 @@ cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
     nw = (int)((ntiles + blocks - 1) / blocks);
   }
   const size_t smem = cp_bytes + per_warp * nw;
-  k_nd_comp<P, HAS_A, HAS_M, NT><<<(unsigned)blocks, nw * 32, smem, s>>>(
+  k_nd_comp<P, HAS_A, HAS_M, NT, IPW><<<(unsigned)blocks, nw * 32, smem, s>>>(
       comp_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items,
       ca, cm);
   return cudaGetLastError();
 }
 
-template <int P, int NT>
+template <int P, int NT, int IPW>
 cudaError_t nd_comp_p(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
-  if (ca != 0.0 && cm != 0.0) return nd_comp_t<P, true, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
-  if (ca != 0.0) return nd_comp_t<P, true, false, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
-  return nd_comp_t<P, false, true, NT>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  if (ca != 0.0 && cm != 0.0) return nd_comp_t<P, true, true, NT, IPW>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  if (ca != 0.0) return nd_comp_t<P, true, false, NT, IPW>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
+  return nd_comp_t<P, false, true, NT, IPW>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, fits);
 }
 
 }  // namespace
@@ -362,9 +369,12 @@ cudaError_t launch_nd_comp(int p, const Tabs &T, const ElemData &E, const double
   if (mask < 0) { const char *e = std::getenv("BLOCH_ND_COMP"); mask = e ? std::atoi(e) : 4; }
   *launched = false;
   if (p < 1 || p > 3 || !(mask & (1 << (p - 1))) || (ca == 0.0 && cm == 0.0)) return cudaSuccess;
-  if (p == 1) return nd_comp_p<1, 1024>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  if (p == 2) return nd_comp_p<2, 768>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  return nd_comp_p<3, 320>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  static int ipw = -1;
+  if (ipw < 0) { const char *e = std::getenv("BLOCH_ND_COMP_ITEMS"); ipw = e ? std::atoi(e) : 5; }
+  if (p == 1) return nd_comp_p<1, 1024, 5>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (p == 2) return nd_comp_p<2, 768, 5>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  if (ipw == 4) return nd_comp_p<3, 320, 4>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
+  return nd_comp_p<3, 320, 5>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
 }
 
 }  // namespace bloch_b200
