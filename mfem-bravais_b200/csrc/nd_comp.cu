@@ -316,19 +316,26 @@ template <int P, bool HAS_A, bool HAS_M, int NT, int IPW>
 cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
   using D = Dim<P>;
-  static int sms = 0;
-  static size_t smem_cap = 0;
+  // per-device one-time setup (a process may hold handles on several devices)
+  constexpr int kMaxDev = 64;
+  static int sms_of[kMaxDev] = {};
+  static size_t cap_of[kMaxDev] = {};
   const size_t cp_bytes = (size_t)((E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
   const size_t per_warp = (size_t)(D::NB + (HAS_A ? D::RB : 0)) * 32 * sizeof(double);
-  if (sms == 0) {
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) { *fits = false; return cudaSuccess; }
+  if (sms_of[dev] == 0) {
+    int optin = 0, n_sm = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaError_t err = cudaFuncSetAttribute(k_nd_comp<P, HAS_A, HAS_M, NT, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess) return err;
-    smem_cap = (size_t)optin;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cap_of[dev] = (size_t)optin;
+    sms_of[dev] = n_sm;
   }
+  const int sms = sms_of[dev];
+  const size_t smem_cap = cap_of[dev];
   int nwarps = (int)((smem_cap - cp_bytes) / per_warp);
   if (nwarps > NT / 32) nwarps = NT / 32;
   const double max_off = 2.0 * (double)E.n_elem * D::LND * (double)(ldx > ldy ? ldx : ldy);   // n_dofs <= n_elem * LND

@@ -94,10 +94,10 @@ __device__ __forceinline__ double partner(double x) {
 // NT = threads per block = the register budget (65536 / NT per thread): 512 -> 128 registers, 16 warps per SM
 // GV (gather variant): 0 = component by component (index loads, value loads, transform; compiler fences in between
 // keep the register pressure of the 168-register build down), 1 = all indices first (8-byte loads), no fences.
-template <int P, bool HAS_A, bool HAS_M, int NT, int GV>
-__global__ void __launch_bounds__(NT, 1)
-k_nd_item(const __grid_constant__ ItemTabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
-          int m, int ldx, int ldy, long n_items, double ca, double cm) {
+template <int P, bool HAS_A, bool HAS_M, int GV>
+__device__ __forceinline__ void nd_item_body(const ItemTabs &T, const ElemData &E, const double *__restrict__ X,
+                                             double *__restrict__ Y, int m, int ldx, int ldy, long n_items, double ca,
+                                             double cm) {
   using D = Dim<P>;
   constexpr int Q = P + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,22 +320,37 @@ k_nd_item(const __grid_constant__ ItemTabs T, const ElemData E, const double *__
 }
 
 template <int P, bool HAS_A, bool HAS_M, int NT, int GV>
+__global__ void __launch_bounds__(NT, 1)
+k_nd_item(const __grid_constant__ ItemTabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
+          int m, int ldx, int ldy, long n_items, double ca, double cm) {
+  nd_item_body<P, HAS_A, HAS_M, GV>(T, E, X, Y, m, ldx, ldy, n_items, ca, cm);
+}
+
+template <int P, bool HAS_A, bool HAS_M, int NT, int GV>
 cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, double2 *y, int ldy, int nvec,
                       double ca, double cm, cudaStream_t s, bool *fits) {
   using D = Dim<P>;
-  static int sms = 0;
-  static size_t smem_cap = 0;
+  auto kern = k_nd_item<P, HAS_A, HAS_M, NT, GV>;
+  // per-device one-time setup (a process may hold handles on several devices)
+  constexpr int kMaxDev = 64;
+  static int sms_of[kMaxDev] = {};
+  static size_t cap_of[kMaxDev] = {};
   const size_t cp_bytes = (size_t)((E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
   const size_t per_warp = (size_t)D::LND * 32 * sizeof(double);
-  if (sms == 0) {
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) { *fits = false; return cudaSuccess; }
+  if (sms_of[dev] == 0) {
+    int optin = 0, n_sm = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t err = cudaFuncSetAttribute(k_nd_item<P, HAS_A, HAS_M, NT, GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess) return err;
-    smem_cap = (size_t)optin;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cap_of[dev] = (size_t)optin;
+    sms_of[dev] = n_sm;
   }
+  const int sms = sms_of[dev];
+  const size_t smem_cap = cap_of[dev];
   int nwarps = (int)((smem_cap - cp_bytes) / per_warp);
   if (nwarps > NT / 32) nwarps = NT / 32;
   const double max_off = 2.0 * (double)E.n_elem * D::LND * (double)(ldx > ldy ? ldx : ldy);   // n_dofs <= n_elem * LND
@@ -353,7 +368,7 @@ cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
     nw = (int)((ntiles + blocks - 1) / blocks);
   }
   const size_t smem = cp_bytes + per_warp * nw;
-  k_nd_item<P, HAS_A, HAS_M, NT, GV><<<(unsigned)blocks, nw * 32, smem, s>>>(
+  kern<<<(unsigned)blocks, nw * 32, smem, s>>>(
       item_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca, cm);
   return cudaGetLastError();
 }
@@ -376,14 +391,14 @@ cudaError_t launch_nd_item(int p, const Tabs &T, const ElemData &E, const double
   if (enabled < 0) { const char *e = std::getenv("BLOCH_ND_ITEM"); enabled = e ? std::atoi(e) : 1; }
   *launched = false;
   if (!enabled || p > 2 || (ca == 0.0 && cm == 0.0)) return cudaSuccess;
-  // BLOCH_ND_ITEM_MODE (order 2): 1 = 12 warps per SM (168 registers), gather component by component (default);
-  // 2 = same, all indices first; 3 = 8 warps per SM (255 registers), all indices first
+  // BLOCH_ND_ITEM_MODE: 2 = all indices first (default), 1 = gather component by component behind compiler fences.
+  // Order 2 runs 12 warps per SM at 168 registers: 16 warps (128 registers) spill 700 B per lane and measured 1.75x
+  // slower, 14 warps at 144 registers do not launch (register file granularity), 8 warps at 255 measured equal.
   static int mode = -1;
   if (mode < 0) { const char *e = std::getenv("BLOCH_ND_ITEM_MODE"); mode = e ? std::atoi(e) : 2; }
   if (p == 1) return mode == 1 ? nd_item_p<1, 512, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched)
                                : nd_item_p<1, 512, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
   if (mode == 2) return nd_item_p<2, 384, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
-  if (mode == 3) return nd_item_p<2, 512, 1>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
   return nd_item_p<2, 384, 0>(T, E, x, ldx, y, ldy, nvec, ca, cm, s, launched);
 }
 
