@@ -35,7 +35,7 @@ for name, p, n in cases:
         t = float(np.median(ts))
         print(json.dumps({"case": f"{name} p{p} n{n}", "N": eq.N, "nv": nv, "us": round(t * 1e6, 1),
                           "gdofs": round(eq.N * nv / t / 1e9, 2), "hbm_frac": round(32 * eq.N * nv / t / 6544.7e9, 4),
-                          "item": os.environ.get("BLOCH_ND_ITEM", "1"), "comp": os.environ.get("BLOCH_ND_COMP", "4"), "mode": os.environ.get("BLOCH_ND_ITEM_MODE", "2")}),
+                          "item": os.environ.get("BLOCH_ND_ITEM", "1"), "comp": os.environ.get("BLOCH_ND_COMP", "4"), "ov": os.environ.get("BLOCH_ND_ITEM_OVERLAY", "0")}),
               flush=True)
         del x, y
     del eq
