@@ -5,10 +5,15 @@ include/) may import this module; only tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs use it, and only as the checker
 or as the timed CPU baseline.
 
-PARITY UNPINNED: the reference has no golden vectors, no assertions and cannot be
-built here (MFEM dev branch + hypre + MPI are absent).  This
-file is therefore a *restatement* of the reference algorithm, assembled-matrix
-style, with every third-party (MFEM) convention that is not visible in the
+PARITY UNPINNED for the finite-element operators: the reference has no golden
+vectors, no assertions and cannot be built here (MFEM dev branch + hypre + MPI are
+absent).  The LATTICE layer (class Lattice below: vectors,
+symmetry points, k-paths, coarse Wigner-Seitz hex cells, periodic identification) IS
+pinned: the reference's own lib/bravais.cpp is compiled unmodified against an
+interface stand-in for MFEM (oracle/ref_shim, oracle/Makefile) and its output
+(tests/golden/ref_bravais.json) is compared table by table in tests/test_ref_bravais.py.
+For everything else this file is a *restatement* of the reference algorithm,
+assembled-matrix style, with every third-party (MFEM) convention that is not visible in the
 reference tree written down explicitly:
 
   * spaces: H1_p, ND_p, RT_{p-1} (= MFEM RT_FECollection(p-1),

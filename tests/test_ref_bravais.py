@@ -1,0 +1,159 @@
+"""Pins the lattice layer against the REFERENCE'S OWN CODE: tests/golden/ref_bravais.json is the output of
+oracle/_ref/ref_bravais_dump, i.e. /root/reference/lib/bravais.cpp compiled unmodified (oracle/Makefile) and run in
+the build container.  Compared here with the oracle's restated tables (oracle/bloch_oracle.py::Lattice) and with the
+product's lattice API (csrc/bravais.cpp through the C ABI): lattice / reciprocal / translation vectors, volumes, face
+radii, symmetry points and labels, k-paths and intermediate points, the coarse Wigner-Seitz hex cells (vertex and
+element tables, lib/bravais.cpp:2275-2313, 2494-2526, 2804-2893) and the periodic vertex identification that the
+reference's MakePeriodicMesh (lib/bravais.cpp:9548-9832) derives from the translation vectors.  CPU only."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.bloch_oracle import Lattice, Mesh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "ref_bravais.json")))
+NAMES = ["CUB", "FCC", "BCC", "HEX"]
+
+
+def _classes(pairs, n):
+    """partition of range(n) from a vertex -> representative map, as a sorted list of frozensets"""
+    groups = {}
+    for v in range(n):
+        groups.setdefault(pairs[v], set()).add(v)
+    return sorted((frozenset(g) for g in groups.values()), key=min)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_tables_equal_reference_code(name):
+    g, o = GOLD[name], Lattice(name)
+    assert np.allclose(g["lattice_vectors"], o.lat, atol=1e-15)
+    assert np.allclose(g["reciprocal_vectors"], o.rec, atol=1e-15)
+    assert abs(g["cell_volume"] - o.volume) < 1e-15 and abs(g["bz_volume"] * o.volume - 1.0) < 1e-14
+    assert [s["label"] for s in g["symmetry_points"]] == list(o.sp)           # same order
+    for i, s in enumerate(g["symmetry_points"]):
+        assert np.allclose(s["kappa"], o.kappa(s["label"]), atol=1e-14)
+        # label -> index: the reference fills its map for CUB / FCC / BCC; its HEX lattice never does (every lookup
+        # returns -1, a quirk recorded in the golden file and NOT reproduced by the product)
+        assert s["index_of_label"] == (i if name != "HEX" else -1)
+    labels = [s["label"] for s in g["symmetry_points"]]
+    assert len(g["paths"]) == len(o.paths)
+    for gp, op in zip(g["paths"], o.paths):
+        assert [labels[seg["e0"]] for seg in gp] + [labels[gp[-1]["e1"]]] == op
+        for seg in gp:       # intermediate point = midpoint of the segment (lib/bravais.cpp:59-74)
+            mid = 0.5 * (o.kappa(labels[seg["e0"]]) + o.kappa(labels[seg["e1"]]))
+            assert np.allclose(seg["mid"], mid, atol=1e-14)
+    # every translation vector of the reference is a lattice vector of the oracle
+    t = np.array(g["translation_vectors"]) @ o.rec.T
+    assert np.allclose(t, np.round(t), atol=1e-13) and np.abs(np.round(t)).max() == 1
+
+
+@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
+def test_oracle_ws_cell_equals_reference_code(name):
+    g, o = GOLD[name]["ws_mesh"], Lattice(name)
+    assert np.allclose(g["vertices"], o.ws_vert, atol=1e-15)
+    assert all(e["geom"] == 5 for e in g["elements"])                             # Geometry::CUBE
+    assert np.array_equal(np.array([e["v"] for e in g["elements"]]), o.ws_hex)
+    # periodic identification of the coarse vertices: the reference matches boundary vertices through its translation
+    # vectors (tolerance 1e-8 diam); the oracle identifies positions modulo the lattice
+    n = len(g["vertices"])
+    ref_map = {}
+    for e0, e1 in zip(g["elements"], GOLD[name]["ws_mesh_periodic"]["elements"]):
+        for a, b in zip(e0["v"], e1["v"]):
+            assert ref_map.setdefault(a, b) == b
+    frac = np.array(o.ws_vert) @ o.rec.T
+    rep = {}
+    for v in range(n):
+        rep[v] = next(u for u in range(n) if np.allclose(frac[v] - frac[u], np.round(frac[v] - frac[u]), atol=1e-9))
+    assert _classes(ref_map, n) == _classes(rep, n)
+    # Euler number 0 of the periodic coarse complex is only meaningful after refinement (a single period collapses
+    # entities); what must hold already here: number of vertex classes = number of lattice-inequivalent positions
+    assert len(_classes(rep, n)) == len({tuple(np.round((f - np.floor(f + 1e-9)) % 1.0, 6) % 1.0) for f in frac})
+
+
+def test_hex_reference_cell_is_the_same_prism():
+    """The reference's current HEX cell is 24 wedges (lib/bravais.cpp:6305-6326); the product and the oracle use its
+    6-hex layout (:6167-6199).  Both must tile the same hexagonal prism: same volume, same extreme vertices."""
+    g, o = GOLD["HEX"]["ws_mesh"], Lattice("HEX")
+    V = np.array(g["vertices"])
+    assert all(e["geom"] == 6 for e in g["elements"])                             # Geometry::PRISM
+    vol = 0.0
+    for e in g["elements"]:
+        p = V[e["v"]]
+        vol += abs(np.linalg.det(np.stack([p[1] - p[0], p[2] - p[0], p[3] - p[0]]))) / 2.0
+    assert abs(vol - o.volume) < 1e-13 and abs(Mesh(o, 1).volume - o.volume) < 1e-13
+    hull_ref = {tuple(np.round(v, 12)) for v in V if abs(np.hypot(v[0], v[1]) - 1 / np.sqrt(3)) < 1e-12 and abs(abs(v[2]) - 0.5) < 1e-12}
+    hull_orc = {tuple(np.round(v, 12)) for v in o.ws_vert if abs(np.hypot(v[0], v[1]) - 1 / np.sqrt(3)) < 1e-12 and abs(abs(v[2]) - 0.5) < 1e-12}
+    assert len(hull_ref) == 12 and hull_ref == hull_orc
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_product_lattice_api_equals_reference_code(bloch, name):
+    g, L = GOLD[name], bloch.BravaisLattice(name)
+    assert L.GetLatticeTypeLabel() == g["label"]
+    assert np.allclose(L.GetLatticeVectors(), g["lattice_vectors"], atol=1e-15)
+    assert np.allclose(L.GetReciprocalLatticeVectors(), g["reciprocal_vectors"], atol=1e-15)
+    assert abs(L.GetUnitCellVolume() - g["cell_volume"]) < 1e-15
+    assert np.allclose(L.GetTranslationVectors(), g["translation_vectors"], atol=1e-15)      # same order, same signs
+    assert np.allclose(L.GetFaceRadii(), g["face_radii"], atol=1e-15)
+    assert L.GetNumberSymmetryPoints() == len(g["symmetry_points"])
+    for i, s in enumerate(g["symmetry_points"]):
+        assert L.GetSymmetryPointLabel(i) == s["label"] and np.allclose(L.GetSymmetryPoint(i), s["kappa"], atol=1e-14)
+    assert L.GetNumberPaths() == len(g["paths"])
+    for p, gp in enumerate(g["paths"]):
+        assert L.GetNumberPathSegments(p) == len(gp)
+        for s, seg in enumerate(gp):
+            assert tuple(L.GetPathSegmentEndPointIndices(p, s)) == (seg["e0"], seg["e1"])
+            assert L.GetIntermediatePointLabel(p, s) == seg["mid_label"]
+            assert np.allclose(L.GetIntermediatePoint(p, s), seg["mid"], atol=1e-14)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_map_to_primitive_cell_against_reference_code(bloch, name):
+    """The reference ADDS n_i a_i with n_i = floor/ceil(b_i . pt) (lib/bravais.cpp:187) where a subtraction is meant,
+    so on these samples it hands the input back unchanged (recorded in the golden file).  The product implements the
+    documented intent; it must return a lattice-equivalent point that is never longer than the reference's."""
+    g, L, o = GOLD[name], bloch.BravaisLattice(name), Lattice(name)
+    for r in g["map_to_primitive_cell"]:
+        pt, ref_ipt = np.array(r["pt"]), np.array(r["ipt"])
+        _, ipt = L.MapToPrimitiveCell(pt)
+        shift = (pt - np.asarray(ipt)) @ o.rec.T
+        assert np.allclose(shift, np.round(shift), atol=1e-12)
+        assert np.linalg.norm(ipt) <= np.linalg.norm(ref_ipt) + 1e-12
+
+
+@pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
+def test_product_coarse_mesh_equals_reference_code(bloch, name):
+    """Topology-only handle (no GPU): element geometry and H1 vertex numbering of the unrefined cell."""
+    g = GOLD[name]
+    eq = bloch.MaxwellBlochWaveEquation(bloch.BravaisLattice(name), 1, 1, device=-2)     # BLOCH_DEVICE_NONE
+    x0, cls, J = eq.element_geometry()
+    V = np.array(g["ws_mesh"]["vertices"])
+    hexes = [e["v"] for e in g["ws_mesh"]["elements"]]
+    assert len(x0) == len(hexes)
+    gid, _ = eq.dofmap("h1")                    # natural local order: i fastest
+    ref = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], float)
+    prod_map = {}
+    for e, hv in enumerate(hexes):
+        P = x0[e] + ref @ J[cls[e]].T           # product's vertex positions of element e
+        assert {tuple(np.round(p, 12)) for p in P} == {tuple(np.round(V[v], 12)) for v in hv}
+        for l, p in enumerate(P):
+            v = next(v for v in hv if np.allclose(V[v], p, atol=1e-12))
+            assert prod_map.setdefault(v, int(gid[e, l])) == int(gid[e, l])
+    ref_map = {}
+    for e0, e1 in zip(g["ws_mesh"]["elements"], g["ws_mesh_periodic"]["elements"]):
+        for a, b in zip(e0["v"], e1["v"]):
+            ref_map[a] = b
+    n = len(V)
+    assert _classes(prod_map, n) == _classes(ref_map, n)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/lib/bravais.cpp"), reason="reference tree not present")
+def test_golden_is_what_the_reference_code_prints():
+    root = os.path.dirname(HERE)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "_ref/ref_bravais_dump"])
+    out = subprocess.run([os.path.join(root, "oracle", "_ref", "ref_bravais_dump")], capture_output=True, text=True, check=True)
+    assert json.loads(out.stdout) == GOLD
