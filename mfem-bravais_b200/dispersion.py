@@ -1,6 +1,8 @@
 """maxwell_dispersion-style sweep logic (maxwell/maxwell_dispersion.cpp:475-648, 1062-1087,
 1449-1556): k-path walk with symmetry-point cache, piecewise-constant coefficients sampled at
 element centres, omega = sqrt(lambda) formatting."""
+import os
+
 import numpy as np
 
 
@@ -110,6 +112,81 @@ def write_matrices(eq, prefix, label=""):
     return [write_hypre_ij("%s/Ar%s.mat" % (prefix, label), A.real),
             write_hypre_ij("%s/Ai%s.mat" % (prefix, label), A.imag),
             write_hypre_ij("%s/M%s.mat" % (prefix, label), M)]
+
+
+_HEX_REF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+_HEX_FACES = [(3, 2, 1, 0), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)]
+
+
+def write_mfem_mesh(eq, path, lattice=None, eps=None, muinv=None):
+    """Interchange: the refined Wigner-Seitz cell of `eq` as a NON-periodic MFEM mesh file
+    (`MFEM mesh v1.0`, hexahedra in MFEM vertex order, boundary = faces of a single element).  Together with the
+    lattice's translation vectors (written to `<path>.trans`, one per line) this is exactly the input of the
+    reference's pipeline - Wigner-Seitz mesh, refine, `MakePeriodicMesh(mesh, trans_vecs)` (lib/bravais.cpp:343-355,
+    9548-9832; in current MFEM: `Mesh::MakePeriodic(mesh, mesh.CreatePeriodicVertexMapping(trans))`) - so a real
+    MFEM/hypre run elsewhere works on the very same elements, in the same order.  Element attributes enumerate the
+    distinct (eps, 1/mu) pairs (element-wise constants), listed in `<path>.coef` as `attribute eps muinv`, so that
+    `PWConstantCoefficient`s reproduce the coefficients exactly.  Returns (n_vertices, n_elements, n_boundary)."""
+    x0, cls, J = eq.element_geometry()
+    ne = len(x0)
+    eps = np.ones(ne) if eps is None else np.asarray(eps, float)
+    muinv = np.ones(ne) if muinv is None else np.asarray(muinv, float)
+    pairs = {}
+    attr = np.zeros(ne, dtype=int)
+    for e in range(ne):
+        attr[e] = pairs.setdefault((float(eps[e]), float(muinv[e])), len(pairs) + 1)
+    vid, verts, hexes = {}, [], np.zeros((ne, 8), dtype=int)
+    for e in range(ne):
+        P = x0[e] + _HEX_REF @ J[cls[e]].T
+        for l in range(8):
+            key = tuple(np.round(P[l], 10) + 0.0)
+            if key not in vid:
+                vid[key] = len(verts)
+                verts.append(P[l])
+            hexes[e, l] = vid[key]
+    faces = {}
+    for e in range(ne):
+        for f in _HEX_FACES:
+            fv = tuple(int(hexes[e, k]) for k in f)
+            faces.setdefault(tuple(sorted(fv)), []).append(fv)
+    bdr = [v[0] for v in faces.values() if len(v) == 1]
+    with open(path, "w") as f:
+        f.write("MFEM mesh v1.0\n\n#\n# Wigner-Seitz cell written by mfem_bravais_b200 (non-periodic; translation vectors in %s.trans)\n"
+                "# MFEM geometry types: SQUARE = 3, CUBE = 5\n#\n\ndimension\n3\n\nelements\n%d\n" % (os.path.basename(path), ne))
+        for e in range(ne):
+            f.write("%d 5 %s\n" % (attr[e], " ".join(str(int(v)) for v in hexes[e])))
+        f.write("\nboundary\n%d\n" % len(bdr))
+        for fv in bdr:
+            f.write("1 3 %d %d %d %d\n" % fv)
+        f.write("\nvertices\n%d\n3\n" % len(verts))
+        for v in verts:
+            f.write("%.17g %.17g %.17g\n" % tuple(v + 0.0))
+    with open(path + ".coef", "w") as f:
+        for (e_, m_), a_ in sorted(pairs.items(), key=lambda kv: kv[1]):
+            f.write("%d %.17g %.17g\n" % (a_, e_, m_))
+    if lattice is not None:
+        with open(path + ".trans", "w") as f:
+            for t in lattice.GetTranslationVectors():
+                f.write("%.17g %.17g %.17g\n" % tuple(t))
+    return len(verts), ne, len(bdr)
+
+
+def read_mfem_mesh(path):
+    """Minimal reader of the files written by write_mfem_mesh (tests): (vertices[nv,3], hexes[ne,8], attr[ne], bdr[nb,4])."""
+    toks = [ln.strip() for ln in open(path) if ln.strip() and not ln.startswith("#")]
+    assert toks[0] == "MFEM mesh v1.0" and toks[toks.index("dimension") + 1] == "3"
+    i = toks.index("elements")
+    ne = int(toks[i + 1])
+    el = np.array([[int(t) for t in toks[i + 2 + e].split()] for e in range(ne)])
+    assert (el[:, 1] == 5).all()
+    i = toks.index("boundary")
+    nb = int(toks[i + 1])
+    bd = np.array([[int(t) for t in toks[i + 2 + b].split()] for b in range(nb)])
+    i = toks.index("vertices")
+    nv = int(toks[i + 1])
+    assert toks[i + 2] == "3"
+    V = np.array([[float(t) for t in toks[i + 3 + v].split()] for v in range(nv)])
+    return V, el[:, 2:], el[:, 0], bd[:, 2:]
 
 
 def homogenization_sweep(eq, kappa0, num_beta, n_bands, a=1.0, num_a_per_lambda=10.0, tol=1e-6):

@@ -177,3 +177,61 @@ def test_dense_rayleigh_ritz_solver_against_scipy(n, m):
     g2a, g2m = pack(G2A), pack(G2M)
     capi.check(lib.bloch_debug_hegv(n2, m, capi.dptr(g2a), capi.dptr(g2m), capi.dptr(lam2), None, 1))
     assert np.allclose(lam2, ref_w[:m], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,n", [("CUB", 2), ("FCC", 2), ("BCC", 1), ("HEX", 2)])
+def test_mfem_mesh_export(bloch, name, n, tmp_path):
+    """write_mfem_mesh: the refined Wigner-Seitz cell as a non-periodic `MFEM mesh v1.0` file + translation vectors,
+    the input of the reference's MakePeriodicMesh pipeline (lib/bravais.cpp:343-355, 9548-9832)."""
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, 1, device=-2)
+    eps = bloch.sphere_eps(eq.element_centers())
+    path = str(tmp_path / "cell.mesh")
+    nv, ne, nb = bloch.write_mfem_mesh(eq, path, lattice=L, eps=eps)
+    V, H, attr, B = bloch.read_mfem_mesh(path)
+    assert (len(V), len(H), len(B)) == (nv, ne, nb) and ne == eq.n_elem
+    # positively oriented MFEM hexes filling the cell
+    vol = 0.0
+    for h in H:
+        P = V[h]
+        d = np.linalg.det(np.stack([P[1] - P[0], P[3] - P[0], P[4] - P[0]]))
+        assert d > 0
+        vol += d
+    assert abs(vol - L.GetUnitCellVolume()) < 1e-13
+    # attributes reproduce the element-wise coefficients through the .coef table
+    table = {int(a): (float(e), float(m)) for a, e, m in (ln.split() for ln in open(path + ".coef"))}
+    assert [table[a][0] for a in attr] == list(eps) and len(table) == len(set(eps))
+    # Euler characteristic of the solid cell = 1, of its boundary surface = 2
+    edges = {tuple(sorted((h[a], h[b]))) for h in H for a, b in
+             [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]}
+    faces = {tuple(sorted(h[list(f)])) for h in H for f in [(3, 2, 1, 0), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)]}
+    assert len(V) - len(edges) + len(faces) - len(H) == 1
+    bv = set(B.ravel())
+    be = {tuple(sorted((q[a], q[(a + 1) % 4]))) for q in B for a in range(4)}
+    assert len(bv) - len(be) + len(B) == 2
+    # the translation vectors pair up the boundary vertices exactly like the product's periodic H1 numbering:
+    # vertices u, v are identified iff they differ by an integer combination of translation vectors
+    T = np.loadtxt(path + ".trans").reshape(-1, 3)
+    assert np.allclose(T, L.GetTranslationVectors())
+    gid, _ = eq.dofmap("h1")
+    x0, cls, J = eq.element_geometry()
+    ref = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], float)
+    key = {tuple(np.round(v, 9) + 0.0): i for i, v in enumerate(V)}
+    g_of_v = {}
+    for e in range(ne):
+        P = x0[e] + ref @ J[cls[e]].T
+        for l in range(8):
+            v = key[tuple(np.round(P[l], 9) + 0.0)]
+            assert g_of_v.setdefault(v, int(gid[e, l])) == int(gid[e, l])
+    rec = L.GetReciprocalLatticeVectors()
+    for u in bv:
+        for t in np.concatenate([T, -T]):
+            k = tuple(np.round(V[u] + t, 9) + 0.0)
+            if k in key:
+                assert g_of_v[key[k]] == g_of_v[u]
+    frac = V @ rec.T
+    classes = {}
+    for v in range(len(V)):
+        f = frac[v] - np.floor(frac[v] + 1e-9)
+        classes.setdefault(tuple(np.round(f, 6) % 1.0), set()).add(g_of_v[v])
+    assert all(len(s) == 1 for s in classes.values()) and len(classes) == eq.N_h1
