@@ -114,6 +114,84 @@ def write_matrices(eq, prefix, label=""):
             write_hypre_ij("%s/M%s.mat" % (prefix, label), M)]
 
 
+# ---- plane-wave initial vectors (CreateInitialVectors, maxwell/maxwell_dispersion.cpp:735-1060) ----
+_MODE_TABLES = {      # integer shifts n of the reciprocal lattice tried by the reference, per lattice (:806-856)
+    "default": [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)],
+    "FCC": [(0, 0, 0)] + [(a, b, c) for a in (1, -1) for b in (1, -1) for c in (1, -1)],
+    "BCC": [(0, 0, 0)] + [(0, b, c) for b in (1, -1) for c in (1, -1)] + [(a, 0, c) for a in (1, -1) for c in (1, -1)]
+           + [(a, b, 0) for a in (1, -1) for b in (1, -1)],
+}
+
+
+def _gauss_legendre01(p):
+    x, _ = np.polynomial.legendre.leggauss(p)
+    return 0.5 * (x + 1.0)
+
+
+def _gauss_lobatto01(n):
+    if n == 2:
+        return np.array([0.0, 1.0])
+    inner = np.polynomial.legendre.Legendre.basis(n - 1).deriv().roots()
+    return 0.5 * (np.concatenate([[-1.0], np.sort(inner.real), [1.0]]) + 1.0)
+
+
+def nd_interpolate(eq, field):
+    """Nodal interpolation into the Nedelec space of `eq` (what ParGridFunction::ProjectCoefficient does for a smooth
+    vector field): dof k = t_k . J^T v(x_k) = (edge vector J e_c) . v(x_k) at the ND node x_k (open direction c on the
+    Gauss-Legendre points, closed directions on the Gauss-Lobatto points).  `field(x[n,3]) -> complex v[n,3]`.
+    Returns the vector in the boundary layout [re(N); im(N)]."""
+    p = eq.order
+    g, l = _gauss_legendre01(p), _gauss_lobatto01(p + 1)
+    x0, cls, J = eq.element_geometry()
+    gid, sign = eq.dofmap("nd")
+
+    def grid(ax, ay, az):
+        kk, jj, ii = np.meshgrid(az, ay, ax, indexing="ij")          # i fastest
+        return np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1)
+
+    nodes = [grid(g, l, l), grid(l, g, l), grid(l, l, g)]
+    out = np.zeros(eq.N, complex)
+    nb = p * (p + 1) ** 2
+    for c in range(3):
+        X = x0[:, None, :] + np.einsum("eij,kj->eki", J[cls], nodes[c])      # [ne, nb, 3]
+        v = field(X.reshape(-1, 3)).reshape(len(x0), nb, 3)
+        t = J[cls][:, :, c]                                                    # physical edge vector of direction c
+        loc = np.einsum("ei,eki->ek", t, v)
+        sl = slice(c * nb, (c + 1) * nb)
+        out[gid[:, sl].ravel()] = (sign[:, sl] * loc).ravel()                 # copies agree (tangential continuity)
+    return np.concatenate([out.real, out.imag])
+
+
+def plane_wave_initial_vectors(eq, lattice, kappa, count=None, literal=True):
+    """The reference's initial block (CreateInitialVectors): for every shift n of the lattice's mode table the
+    plane waves E0 exp(i 2 pi sum_j n_j b_j . x) - the periodic envelopes of exp(i (kappa + 2 pi G) . x) - with E0 the
+    two unit vectors orthogonal to k (three Cartesian ones when |k| < 1e-2), nodally interpolated into ND.  The
+    reference builds the real pairs (E, iE) (:1039-1057); in this complex-native solver iE is not an independent
+    vector, so one complex vector per (n, E0) is returned, ordered by |kappa + 2 pi G| (lowest empty-lattice
+    frequencies first), at most `count`.  literal=True keeps the reference's k = kappa + sum_j n_j b_j (its reciprocal
+    vectors carry no 2 pi, `sic` in SURVEY.md section 8(a) row a16); literal=False uses the physical wave vector."""
+    kappa = np.asarray(kappa, float)
+    b = lattice.GetReciprocalLatticeVectors()
+    table = _MODE_TABLES.get(lattice.GetLatticeTypeLabel(), _MODE_TABLES["default"])
+    waves = []
+    for n in table:
+        G = np.asarray(n, float) @ b
+        k = kappa + (G if literal else 2.0 * np.pi * G)
+        if np.linalg.norm(k) < 1e-2:
+            pol = list(np.eye(3))
+        else:
+            w, V = np.linalg.eigh(np.eye(3) - np.outer(k, k) / (k @ k))       # eigenvalues 0, 1, 1
+            pol = [V[:, 1], V[:, 2]]
+        for e0 in pol:
+            waves.append((np.linalg.norm(kappa + 2.0 * np.pi * G), G, e0))
+    waves.sort(key=lambda t: t[0])
+    if count is not None:
+        waves = waves[:count]
+    vecs = [nd_interpolate(eq, lambda X, G=G, e0=e0: np.exp(2j * np.pi * (X @ G))[:, None] * e0[None, :])
+            for _, G, e0 in waves]
+    return np.array(vecs)
+
+
 _HEX_REF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
 _HEX_FACES = [(3, 2, 1, 0), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)]
 

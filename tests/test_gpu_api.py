@@ -114,3 +114,26 @@ def test_errors_on_live_handle(bloch):
         eq.GetEigenvectorE(0)                                   # before any Solve
     with pytest.raises(bloch.BlochError):
         eq.SetNumEigs(400000)
+
+
+def test_plane_wave_initial_vectors_drive_the_solver(bloch):
+    """The reference's CreateInitialVectors block (maxwell_dispersion.cpp:735-1060) as the starting block: same
+    bands as the built-in guess; on the empty lattice, where the plane waves are the eigenfunctions, the solver
+    needs far fewer iterations."""
+    L = bloch.BravaisLattice("FCC")
+    k = 0.6 * L.GetSymmetryPoint(1) + np.array([0.05, 0.02, -0.03])
+    for empty in (False, True):
+        eq = bloch.MaxwellBlochWaveEquation(L, 2, 2)
+        eq.SetMassCoef(np.ones(eq.n_elem) if empty else bloch.sphere_eps(eq.element_centers()))
+        eq.SetAbsoluteTolerance(1e-8)
+        lam = eq.GetEigenvalues(8, k)[0::2]
+        cold = eq.GetSolverStats()["iterations"]
+        eq2 = bloch.MaxwellBlochWaveEquation(L, 2, 2)
+        eq2.SetMassCoef(np.ones(eq2.n_elem) if empty else bloch.sphere_eps(eq2.element_centers()))
+        eq2.SetAbsoluteTolerance(1e-8)
+        W = bloch.plane_wave_initial_vectors(eq2, L, k, literal=False)
+        lam2 = eq2.GetEigenvalues(8, k, init_vecs=W)[0::2]
+        assert np.allclose(lam, lam2, rtol=1e-7)
+        assert eq2.GetSolverStats()["converged_bands"] >= 4
+        if empty:
+            assert eq2.GetSolverStats()["iterations"] < cold

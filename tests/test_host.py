@@ -235,3 +235,50 @@ def test_mfem_mesh_export(bloch, name, n, tmp_path):
         f = frac[v] - np.floor(frac[v] + 1e-9)
         classes.setdefault(tuple(np.round(f, 6) % 1.0), set()).add(g_of_v[v])
     assert all(len(s) == 1 for s in classes.values()) and len(classes) == eq.N_h1
+
+
+@pytest.mark.parametrize("name,n,p", [("CUB", 2, 1), ("FCC", 2, 2), ("BCC", 1, 3), ("HEX", 2, 1)])
+def test_plane_wave_initial_vectors(bloch, name, n, p):
+    """CreateInitialVectors (maxwell_dispersion.cpp:735-1060) restated on the host: ND nodal interpolation against the
+    oracle's literal dof functionals, and the physics on the oracle's assembled empty-lattice pencil - each wave is
+    divergence-free to discretisation accuracy when E0 is orthogonal to the true wave vector, and its Rayleigh
+    quotient is the empty-lattice band |kappa + 2 pi G|^2.  No GPU (topology-only handle)."""
+    from helpers import oracle_on_product_maps
+    from oracle.bloch_oracle import RefElem
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, p, device=-2)
+    kappa = 0.5 * L.GetSymmetryPoint(1) + np.array([0.11, -0.07, 0.05])
+    # (1) interpolation = t_k . J^T v(x_k) with the oracle's node table
+    G = np.array([1.0, -1.0, 0.0]) @ L.GetReciprocalLatticeVectors()
+    e0 = np.array([0.3, 0.5, -0.2])
+    f = lambda X: np.exp(2j * np.pi * (X @ G))[:, None] * e0[None, :]
+    v = bloch.nd_interpolate(eq, f)
+    vc = v[:eq.N] + 1j * v[eq.N:]
+    ref = RefElem(p)
+    x0, cls, J = eq.element_geometry()
+    gid, sign = eq.dofmap("nd")
+    for e in range(0, eq.n_elem, max(1, eq.n_elem // 7)):
+        X = x0[e] + ref.nd_nodes @ J[cls[e]].T
+        t = J[cls[e]][:, ref.nd_comp].T
+        loc = np.einsum("ki,ki->k", t, f(X))
+        assert np.allclose(vc[gid[e]], sign[e] * loc, atol=1e-13)
+    # (2) the block of the reference recipe
+    W = bloch.plane_wave_initial_vectors(eq, L, kappa, literal=False)
+    tab = {"FCC": 9, "BCC": 13}.get(name, 7)
+    assert W.shape == (2 * tab, 2 * eq.N)                   # generic kappa: two polarisations per shift
+    assert bloch.plane_wave_initial_vectors(eq, L, np.zeros(3)).shape[0] == 2 * tab + 1     # k = 0: three
+    assert bloch.plane_wave_initial_vectors(eq, L, kappa, count=5).shape[0] == 5
+    ops, _ = oracle_on_product_maps(eq, name, n, p, np.ones(eq.n_elem))
+    ops.set_kappa(kappa)
+    A, M, Gc = ops.A_c(), ops.M_c(), ops.G_c()
+    Wc = W[:4, :eq.N] + 1j * W[:4, eq.N:]                   # the four lowest waves
+    b = L.GetReciprocalLatticeVectors()
+    lows = sorted(np.linalg.norm(kappa + 2 * np.pi * np.array(nn, float) @ b) ** 2
+                  for nn in ([(0, 0, 0)] + [tuple(int(s) for s in row) for row in np.vstack([np.eye(3), -np.eye(3)])]
+                             if tab == 7 else [(0, 0, 0)]))
+    h = 1.0 / (n * p)
+    for x in Wc[:2]:
+        rq = np.vdot(x, A @ x).real / np.vdot(x, M @ x).real
+        assert abs(rq - lows[0]) < 0.6 * h ** (2 * p) * max(1.0, lows[0]) + 1e-9     # lowest band |kappa|^2 (exact pair)
+        div = Gc.conj().T @ (M @ x)
+        assert np.linalg.norm(div) < 1e-8 * np.linalg.norm(M @ x)                     # exactly divergence-free
