@@ -118,8 +118,9 @@ def test_errors_on_live_handle(bloch):
 
 def test_plane_wave_initial_vectors_drive_the_solver(bloch):
     """The reference's CreateInitialVectors block (maxwell_dispersion.cpp:735-1060) as the starting block: same
-    bands as the built-in guess; on the empty lattice, where the plane waves are the eigenfunctions, the solver
-    needs far fewer iterations."""
+    bands as the built-in guess, with and without the dielectric sphere.  (No claim on the iteration count: the
+    reference's FCC mode table (+-1,+-1,+-1) misses the nearest reciprocal-lattice shifts, so its block lacks some of
+    the lowest bands - measured 25 iterations vs 18 from the random block on the empty lattice.)"""
     L = bloch.BravaisLattice("FCC")
     k = 0.6 * L.GetSymmetryPoint(1) + np.array([0.05, 0.02, -0.03])
     for empty in (False, True):
@@ -134,6 +135,4 @@ def test_plane_wave_initial_vectors_drive_the_solver(bloch):
         W = bloch.plane_wave_initial_vectors(eq2, L, k, literal=False)
         lam2 = eq2.GetEigenvalues(8, k, init_vecs=W)[0::2]
         assert np.allclose(lam, lam2, rtol=1e-7)
-        assert eq2.GetSolverStats()["converged_bands"] >= 4
-        if empty:
-            assert eq2.GetSolverStats()["iterations"] < cold
+        assert eq2.GetSolverStats()["converged_bands"] >= 4 and cold > 0
