@@ -5,9 +5,13 @@
 // maxwell/maxwell_dispersion.cpp:398-420), HypreParVector of length 2N -> [re(N); im(N)].
 // Header-only; link with -lbloch_b200.
 #pragma once
+#include <algorithm>
+#include <array>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdint>
+#include <map>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -38,6 +42,13 @@ public:
   double GetUnitCellVolume() const { return bloch_lattice_volume(h_); }
   void GetLatticeVectors(std::vector<std::vector<double>> &a) const { a = mat(true); }
   void GetReciprocalLatticeVectors(std::vector<std::vector<double>> &b) const { b = mat(false); }
+  void GetTranslationVectors(std::vector<std::vector<double>> &t) const {
+    const int nt = bloch_lattice_num_translations(h_);
+    std::vector<double> trn(3 * nt), rad(nt);
+    check(bloch_lattice_translations(h_, trn.data(), rad.data()), "GetTranslationVectors");
+    t.assign(nt, std::vector<double>(3));
+    for (int i = 0; i < nt; i++) for (int d = 0; d < 3; d++) t[i][d] = trn[3 * i + d];
+  }
   unsigned GetNumberSymmetryPoints() const { return bloch_lattice_num_symmetry_points(h_); }
   unsigned GetNumberPaths() const { return bloch_lattice_num_paths(h_); }
   unsigned GetNumberPathSegments(int p) const { return bloch_lattice_num_path_segments(h_, p); }
@@ -78,7 +89,7 @@ class MaxwellBlochWaveEquation {
 public:
   // reference: MaxwellBlochWaveEquation(ParMesh &pmesh, int order); the periodic WS mesh is named
   // by (lattice, n_sub) here, n_sub = 2^(serial + parallel refinements)
-  MaxwellBlochWaveEquation(const BravaisLattice &lat, int n_sub, int order, int device = -1) {
+  MaxwellBlochWaveEquation(const BravaisLattice &lat, int n_sub, int order, int device = -1) : order_(order) {
     check(bloch_create(&h_, lat.handle(), n_sub, order, device), "bloch_create");
     int64_t ne, n, nrt, nh1;
     int nc;
@@ -232,9 +243,207 @@ public:
     stat(times_, meanTime, stdDevTime);
     stat(iters_, meanIter, stdDevIter);
   }
+
+  // ---- interchange: the refined Wigner-Seitz cell as a NON-periodic `MFEM mesh v1.0` file (hexahedra in MFEM vertex
+  // order, boundary = faces of a single element), `<path>.trans` = the lattice's translation vectors and `<path>.coef`
+  // = `attribute eps muinv` for the distinct element-wise coefficient pairs: the input of the reference's
+  // MakePeriodicMesh pipeline (lib/bravais.cpp:343-355, 9548-9832), so that an MFEM/hypre run elsewhere works on the
+  // very same elements.  Same files as the Python mirror's write_mfem_mesh.
+  void WriteMesh(const std::string &path, const BravaisLattice &lat, const std::vector<double> &eps,
+                 const std::vector<double> &muinv) const {
+    std::vector<double> x0, J;
+    std::vector<int> cls;
+    geometry(x0, cls, J);
+    static const double ref[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    static const int hexf[6][4] = {{3, 2, 1, 0}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+    std::map<std::pair<double, double>, int> pairs;
+    std::vector<int> attr(n_elem_);
+    for (int64_t e = 0; e < n_elem_; e++) {
+      const std::pair<double, double> key(eps.empty() ? 1.0 : eps[e], muinv.empty() ? 1.0 : muinv[e]);
+      auto it = pairs.find(key);
+      if (it == pairs.end()) it = pairs.emplace(key, (int)pairs.size() + 1).first;
+      attr[e] = it->second;
+    }
+    std::map<std::array<long long, 3>, int> vid;
+    std::vector<std::array<double, 3>> verts;
+    std::vector<std::array<int, 8>> hexes(n_elem_);
+    for (int64_t e = 0; e < n_elem_; e++) {
+      const double *Je = &J[9 * cls[e]];
+      for (int l = 0; l < 8; l++) {
+        std::array<double, 3> p;
+        std::array<long long, 3> key;
+        for (int i = 0; i < 3; i++) {
+          p[i] = x0[3 * e + i] + Je[3 * i + 0] * ref[l][0] + Je[3 * i + 1] * ref[l][1] + Je[3 * i + 2] * ref[l][2];
+          key[i] = std::llround(p[i] * 1e10);
+        }
+        auto it = vid.find(key);
+        if (it == vid.end()) { it = vid.emplace(key, (int)verts.size()).first; verts.push_back(p); }
+        hexes[e][l] = it->second;
+      }
+    }
+    std::map<std::array<int, 4>, std::pair<int, std::array<int, 4>>> faces;
+    for (int64_t e = 0; e < n_elem_; e++)
+      for (auto &f : hexf) {
+        std::array<int, 4> fv = {hexes[e][f[0]], hexes[e][f[1]], hexes[e][f[2]], hexes[e][f[3]]}, key = fv;
+        std::sort(key.begin(), key.end());
+        auto &slot = faces[key];
+        if (slot.first++ == 0) slot.second = fv;
+      }
+    FILE *f = std::fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("WriteMesh: cannot open " + path);
+    size_t nb = 0;
+    for (auto &kv : faces) nb += kv.second.first == 1;
+    std::fprintf(f, "MFEM mesh v1.0\n\n#\n# Wigner-Seitz cell written by bloch_b200 (non-periodic; translation vectors in the .trans file)\n"
+                    "# MFEM geometry types: SQUARE = 3, CUBE = 5\n#\n\ndimension\n3\n\nelements\n%lld\n", (long long)n_elem_);
+    for (int64_t e = 0; e < n_elem_; e++) {
+      std::fprintf(f, "%d 5", attr[e]);
+      for (int l = 0; l < 8; l++) std::fprintf(f, " %d", hexes[e][l]);
+      std::fprintf(f, "\n");
+    }
+    std::fprintf(f, "\nboundary\n%zu\n", nb);
+    for (auto &kv : faces)
+      if (kv.second.first == 1) { auto &q = kv.second.second; std::fprintf(f, "1 3 %d %d %d %d\n", q[0], q[1], q[2], q[3]); }
+    std::fprintf(f, "\nvertices\n%zu\n3\n", verts.size());
+    for (auto &v : verts) std::fprintf(f, "%.17g %.17g %.17g\n", v[0] + 0.0, v[1] + 0.0, v[2] + 0.0);
+    std::fclose(f);
+    f = std::fopen((path + ".coef").c_str(), "w");
+    std::vector<std::pair<int, std::pair<double, double>>> rows;
+    for (auto &kv : pairs) rows.push_back({kv.second, kv.first});
+    std::sort(rows.begin(), rows.end());
+    for (auto &r : rows) std::fprintf(f, "%d %.17g %.17g\n", r.first, r.second.first, r.second.second);
+    std::fclose(f);
+    std::vector<std::vector<double>> t;
+    lat.GetTranslationVectors(t);
+    f = std::fopen((path + ".trans").c_str(), "w");
+    for (auto &v : t) std::fprintf(f, "%.17g %.17g %.17g\n", v[0], v[1], v[2]);
+    std::fclose(f);
+  }
+
+  // ---- CreateInitialVectors (maxwell/maxwell_dispersion.cpp:735-1060): plane waves E0 exp(i 2 pi sum_j n_j b_j . x)
+  // for the lattice's table of shifts n, E0 = two unit vectors orthogonal to k (three Cartesian ones when |k| < 1e-2),
+  // nodally interpolated into ND (dof = edge vector . field at the ND node).  One complex vector [re(N); im(N)] per
+  // (n, E0) - the reference's second vector of each pair is i times the first -, ordered by |kappa + 2 pi G|, at most
+  // `count` (<= 0: all).  literal keeps the reference's k = kappa + sum_j n_j b_j (no 2 pi on b, sic).
+  void CreateInitialVectors(const BravaisLattice &lat, const std::vector<double> &kappa, std::vector<double> &vecs,
+                            int &num_vecs, int count = 0, bool literal = true) const {
+    std::vector<std::vector<double>> b;
+    lat.GetReciprocalLatticeVectors(b);
+    const std::string label = lat.GetLatticeTypeLabel();
+    std::vector<std::array<int, 3>> table = {{0, 0, 0}};
+    if (label == "FCC") {
+      for (int a : {1, -1}) for (int c : {1, -1}) for (int d : {1, -1}) table.push_back({a, c, d});
+    } else if (label == "BCC") {
+      for (int c : {1, -1}) for (int d : {1, -1}) table.push_back({0, c, d});
+      for (int a : {1, -1}) for (int d : {1, -1}) table.push_back({a, 0, d});
+      for (int a : {1, -1}) for (int c : {1, -1}) table.push_back({a, c, 0});
+    } else {
+      for (int d = 0; d < 3; d++) for (int sgn : {1, -1}) { std::array<int, 3> n = {0, 0, 0}; n[d] = sgn; table.push_back(n); }
+    }
+    struct Wave { double key; double G[3], e0[3]; };
+    std::vector<Wave> waves;
+    const double two_pi = 2.0 * M_PI;
+    for (auto &n : table) {
+      double G[3], k[3], kt[3];
+      for (int d = 0; d < 3; d++) {
+        G[d] = n[0] * b[0][d] + n[1] * b[1][d] + n[2] * b[2][d];
+        kt[d] = kappa[d] + two_pi * G[d];
+        k[d] = literal ? kappa[d] + G[d] : kt[d];
+      }
+      const double nk = std::sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);
+      const double key = std::sqrt(kt[0] * kt[0] + kt[1] * kt[1] + kt[2] * kt[2]);
+      auto push = [&](const double *e) { Wave w; w.key = key; for (int d = 0; d < 3; d++) { w.G[d] = G[d]; w.e0[d] = e[d]; } waves.push_back(w); };
+      if (nk < 1e-2) {
+        const double ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+        push(ex); push(ey); push(ez);
+      } else {
+        int least = 0;
+        for (int d = 1; d < 3; d++) if (std::fabs(k[d]) < std::fabs(k[least])) least = d;
+        double u[3] = {0, 0, 0}, v[3];
+        u[least] = 1.0;
+        const double uk = k[least] / (nk * nk);
+        double nu = 0;
+        for (int d = 0; d < 3; d++) { u[d] -= uk * k[d]; nu += u[d] * u[d]; }
+        nu = std::sqrt(nu);
+        for (int d = 0; d < 3; d++) u[d] /= nu;
+        v[0] = (k[1] * u[2] - k[2] * u[1]) / nk; v[1] = (k[2] * u[0] - k[0] * u[2]) / nk; v[2] = (k[0] * u[1] - k[1] * u[0]) / nk;
+        push(u); push(v);
+      }
+    }
+    std::stable_sort(waves.begin(), waves.end(), [](const Wave &a, const Wave &c) { return a.key < c.key; });
+    if (count > 0 && (int)waves.size() > count) waves.resize(count);
+    num_vecs = (int)waves.size();
+    // ND nodes: open direction on the Gauss-Legendre points, closed directions on the Gauss-Lobatto points of [0,1]
+    const int p = order_, q = p + 1, nb = p * q * q;
+    std::vector<double> g(p), l(q);
+    points01(p, g, l);
+    std::vector<double> x0, J;
+    std::vector<int> cls;
+    geometry(x0, cls, J);
+    const int L = bloch_local_size(h_, 1);
+    std::vector<int32_t> map((size_t)n_elem_ * L);
+    check(bloch_get_dofmap(h_, 1, map.data()), "bloch_get_dofmap");
+    vecs.assign((size_t)num_vecs * 2 * N_, 0.0);
+    for (int w = 0; w < num_vecs; w++) {
+      double *re = &vecs[(size_t)w * 2 * N_], *im = re + N_;
+      for (int64_t e = 0; e < n_elem_; e++) {
+        const double *Je = &J[9 * cls[e]];
+        for (int c = 0; c < 3; c++) {
+          const int n0 = c == 0 ? p : q, n1 = c == 1 ? p : q, n2 = c == 2 ? p : q;
+          const double t[3] = {Je[c], Je[3 + c], Je[6 + c]};                 // physical edge vector of direction c
+          const double amp = t[0] * waves[w].e0[0] + t[1] * waves[w].e0[1] + t[2] * waves[w].e0[2];
+          for (int k2 = 0; k2 < n2; k2++) for (int k1 = 0; k1 < n1; k1++) for (int k0 = 0; k0 < n0; k0++) {
+            const double xi[3] = {c == 0 ? g[k0] : l[k0], c == 1 ? g[k1] : l[k1], c == 2 ? g[k2] : l[k2]};
+            double ph = 0;
+            for (int i = 0; i < 3; i++) {
+              const double x = x0[3 * e + i] + Je[3 * i] * xi[0] + Je[3 * i + 1] * xi[1] + Je[3 * i + 2] * xi[2];
+              ph += waves[w].G[i] * x;
+            }
+            const int32_t s = map[(size_t)e * L + c * nb + k0 + n0 * (k1 + n1 * k2)];
+            const int64_t gid = (s < 0 ? -s : s) - 1;
+            const double sg = s < 0 ? -1.0 : 1.0;
+            re[gid] = sg * amp * std::cos(two_pi * ph);
+            im[gid] = sg * amp * std::sin(two_pi * ph);
+          }
+        }
+      }
+    }
+  }
   bloch_handle handle() const { return h_; }
 
 private:
+  void geometry(std::vector<double> &x0, std::vector<int> &cls, std::vector<double> &J) const {
+    int64_t ne;
+    int nc;
+    bloch_num_elements(h_, &ne, &nc);
+    x0.resize(3 * ne); cls.resize(ne); J.resize(9 * (size_t)nc);
+    check(bloch_element_geometry(h_, x0.data(), cls.data(), J.data()), "bloch_element_geometry");
+  }
+  // p Gauss-Legendre and p+1 Gauss-Lobatto points on [0,1] (Newton on the Legendre polynomials)
+  static void points01(int p, std::vector<double> &g, std::vector<double> &l) {
+    auto leg = [](int n, double x, double &P, double &dP) {
+      double p0 = 1.0, p1 = x;
+      if (n == 0) { P = 1; dP = 0; return; }
+      for (int k = 2; k <= n; k++) { const double pk = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k; p0 = p1; p1 = pk; }
+      P = p1; dP = n * (x * p1 - p0) / (x * x - 1.0);
+    };
+    for (int i = 0; i < p; i++) {
+      double z = -std::cos(M_PI * (i + 0.75) / (p + 0.5)), P, dP;
+      for (int it = 0; it < 100; it++) { leg(p, z, P, dP); const double dz = P / dP; z -= dz; if (std::fabs(dz) < 1e-16) break; }
+      g[i] = 0.5 * (z + 1.0);
+    }
+    l[0] = 0.0; l[p] = 1.0;
+    for (int i = 1; i < p; i++) {
+      double z = -std::cos(M_PI * i / p), P, dP;
+      for (int it = 0; it < 100; it++) {
+        leg(p, z, P, dP);
+        const double ddP = (2.0 * z * dP - p * (p + 1) * P) / (1.0 - z * z);
+        const double dz = dP / ddP;
+        z -= dz;
+        if (std::fabs(dz) < 1e-16) break;
+      }
+      l[i] = 0.5 * (z + 1.0);
+    }
+  }
   void push_beta_zeta() {
     if (zeta_.size() == 3) {
       double k[3] = {beta_ * zeta_[0], beta_ * zeta_[1], beta_ * zeta_[2]};
@@ -243,6 +452,7 @@ private:
   }
   bloch_handle h_ = nullptr;
   int64_t n_elem_ = 0, N_ = 0, Nrt_ = 0, Nh1_ = 0;
+  int order_ = 1;
   int nev_ = 20;
   double beta_ = 0;
   std::vector<double> zeta_;

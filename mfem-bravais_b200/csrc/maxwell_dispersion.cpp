@@ -56,7 +56,7 @@ static void WriteDispersionData(std::ostream &os, int c, const std::string &labe
 
 int main(int argc, char **argv) {
   int bl_type = 1, order = 1, sr = 0, pr = 2, np = 0, nb = 10, dev = -1;
-  bool write_mats = false;
+  bool write_mats = false, write_mesh = false, plane_wave_init = false;
   double a = -1.0;
   std::string out = ".";
   for (int i = 1; i < argc; i++) {
@@ -76,6 +76,8 @@ int main(int argc, char **argv) {
     else if (f == "-dev") dev = std::atoi(next("-dev"));
     else if (f == "-out") out = next("-out");
     else if (f == "-wm" || f == "--write-mats") write_mats = true;
+    else if (f == "-wmesh" || f == "--write-mesh") write_mesh = true;      // ws-cell.mesh (+ .trans, .coef) for MFEM cross-checks
+    else if (f == "-iv" || f == "--plane-wave-init") plane_wave_init = true; // CreateInitialVectors block per k-point (:531)
     else if (f == "-no-vis" || f == "-no-visit" || f == "-no-wm" || f == "-mp" || f == "-no-mp") {}
     else { std::cerr << "unknown option " << f << std::endl; return 1; }
   }
@@ -94,6 +96,19 @@ int main(int argc, char **argv) {
     eq.SetMassCoef(eps);
     eq.SetStiffnessCoef(mu);
     eq.SetAbsoluteTolerance(1e-6);
+    if (write_mesh) eq.WriteMesh(out + "/ws-cell.mesh", bravais, eps, mu);
+    // the reference rebuilds its plane-wave block for every kappa (CreateInitialVectors, :735-1060) and hands it to
+    // GetEigenvalues; the default here is the solver's own guess (seeded random + warm start from the previous point)
+    std::vector<double> init;
+    auto solve = [&](const std::vector<double> &kap, std::vector<double> &ev) {
+      if (plane_wave_init) {
+        int nv = 0;
+        eq.CreateInitialVectors(bravais, kap, init, nv);
+        eq.GetEigenvalues(2 * nb, kap, &init, ev);
+      } else {
+        eq.GetEigenvalues(2 * nb, kap, nullptr, ev);
+      }
+    };
 
     std::ofstream ofs_disp(out + "/disp.dat");
     std::map<std::string, std::vector<double>> sp_eigs;   // symmetry-point cache (:506, 604-614)
@@ -114,7 +129,7 @@ int main(int argc, char **argv) {
           if (i == 0 && sp_eigs.count(label)) {
             eigenvalues = sp_eigs[label];
           } else {
-            eq.GetEigenvalues(2 * nb, kappa, nullptr, eigenvalues);
+            solve(kappa, eigenvalues);
             if (i == 0) sp_eigs[label] = eigenvalues;
             if (write_mats && label != "-") {            // Ar / Ai / M dump (:553-590), hypre IJ text format
               eq.WriteMatrix(0, false, out + "/Ar" + label + ".mat");
@@ -127,7 +142,7 @@ int main(int argc, char **argv) {
         if (s + 1 == bravais.GetNumberPathSegments(p)) {   // close the path at its last symmetry point
           std::string label = bravais.GetSymmetryPointLabel(e1);
           if (!sp_eigs.count(label)) {
-            eq.GetEigenvalues(2 * nb, kappa1, nullptr, eigenvalues);
+            solve(kappa1, eigenvalues);
             sp_eigs[label] = eigenvalues;
           }
           WriteDispersionData(ofs_disp, c++, label, sp_eigs[label]);

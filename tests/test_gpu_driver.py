@@ -73,3 +73,23 @@ def test_cpp_driver_matrix_dump(bloch, tmp_path):
     Mr = bloch.read_hypre_ij(str(tmp_path / "MX.mat.00000"))
     assert abs(Ar - A.real).max() < 1e-12 and abs(Ai - A.imag).max() < 1e-12 and abs(Mr - M).max() < 1e-12
     assert abs(Ai + Ai.T).max() < 1e-12 and abs(Ai).max() > 0          # the beta DKZ block is antisymmetric
+
+
+def test_cpp_driver_plane_wave_init_and_mesh_export(bloch, tmp_path):
+    """-iv: the reference's CreateInitialVectors block per k-point (maxwell_dispersion.cpp:531, 735-1060) gives the
+    same disp.dat as the built-in starting guess; -wmesh writes the cell for MFEM cross-checks."""
+    exe = os.path.join(ROOT, "mfem-bravais_b200", "lib", "maxwell_dispersion_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    outs = []
+    for extra in ([], ["-iv", "-wmesh"]):
+        d = tmp_path / ("b" if extra else "a")
+        d.mkdir()
+        r = subprocess.run([exe, "-bl", "1", "-o", "1", "-sr", "0", "-pr", "2", "-p", "2", "-np", "0", "-nb", "4",
+                            "-out", str(d)] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rows = [l.split("\t") for l in open(d / "disp.dat") if l.strip()]
+        outs.append(np.array([[float(x) for x in row[2:]] for row in rows]))
+    assert outs[0].shape == outs[1].shape and np.allclose(outs[0], outs[1], rtol=1e-5, atol=2e-5)
+    V, H, attr, B = bloch.read_mfem_mesh(str(tmp_path / "b" / "ws-cell.mesh"))
+    assert len(H) == 64 and set(attr) == {1, 2} and len(B) == 6 * 16

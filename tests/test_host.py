@@ -282,3 +282,61 @@ def test_plane_wave_initial_vectors(bloch, name, n, p):
         assert abs(rq - lows[0]) < 0.6 * h ** (2 * p) * max(1.0, lows[0]) + 1e-9     # lowest band |kappa|^2 (exact pair)
         div = Gc.conj().T @ (M @ x)
         assert np.linalg.norm(div) < 1e-8 * np.linalg.norm(M @ x)                     # exactly divergence-free
+
+
+@pytest.mark.parametrize("name,n,p", [("FCC", 2, 2), ("CUB", 2, 1), ("BCC", 1, 3)])
+def test_cpp_wrapper_mesh_and_initial_vectors_match_python(bloch, name, n, p, tmp_path):
+    """include/maxwell_bloch_b200.hpp (the C++ host side): WriteMesh and CreateInitialVectors produce what the Python
+    mirror produces (same files; same plane-wave block up to the free choice of the two polarisations per shift).
+    Compiles a small program against the header with a topology-only handle - no GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "maxwell_bloch_b200.hpp"
+#include <cstdlib>
+using namespace bloch_b200;
+int main(int argc, char **argv) {
+  BravaisLattice L(std::atoi(argv[1]));
+  MaxwellBlochWaveEquation eq(L, std::atoi(argv[2]), std::atoi(argv[3]), BLOCH_DEVICE_NONE);
+  std::vector<double> c, eps(eq.GetNE());
+  eq.GetElementCenters(c);
+  for (int64_t e = 0; e < eq.GetNE(); e++)
+    eps[e] = std::sqrt(c[3 * e] * c[3 * e] + c[3 * e + 1] * c[3 * e + 1] + c[3 * e + 2] * c[3 * e + 2]) <= 0.25 ? 10.0 : 1.0;
+  eq.WriteMesh(argv[4], L, eps, {});
+  std::vector<double> kappa = {0.7, -0.4, 1.1}, vecs;
+  int nv = 0;
+  eq.CreateInitialVectors(L, kappa, vecs, nv, 0, false);
+  FILE *f = std::fopen(argv[5], "wb");
+  std::fwrite(vecs.data(), sizeof(double), vecs.size(), f);
+  std::fclose(f);
+  std::printf("%d\n", nv);
+  return 0;
+}
+''')
+    exe = str(tmp_path / "t")
+    libdir = os.path.join(root, "mfem-bravais_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), str(src), "-L" + libdir,
+                           "-lbloch_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    from mfem_bravais_b200 import capi
+    cm, cv = str(tmp_path / "cpp.mesh"), str(tmp_path / "cpp.vecs")
+    nv = int(subprocess.check_output([exe, str(capi.LATTICE_TYPES[name]), str(n), str(p), cm, cv]).split()[0])
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, p, device=-2)
+    pm = str(tmp_path / "py.mesh")
+    bloch.write_mfem_mesh(eq, pm, lattice=L, eps=bloch.sphere_eps(eq.element_centers()))
+    Vc, Hc, ac, Bc = bloch.read_mfem_mesh(cm)
+    Vp, Hp, ap, Bp = bloch.read_mfem_mesh(pm)
+    assert np.array_equal(Hc, Hp) and np.array_equal(ac, ap) and np.allclose(Vc, Vp, atol=1e-15)
+    assert {tuple(sorted(q)) for q in Bc} == {tuple(sorted(q)) for q in Bp}
+    assert open(cm + ".coef").read() == open(pm + ".coef").read()
+    assert np.allclose(np.loadtxt(cm + ".trans"), np.loadtxt(pm + ".trans"))
+    Wp = bloch.plane_wave_initial_vectors(eq, L, [0.7, -0.4, 1.1], literal=False)
+    Wc = np.fromfile(cv).reshape(nv, 2 * eq.N)
+    assert Wc.shape == Wp.shape
+    zp = (Wp[:, :eq.N] + 1j * Wp[:, eq.N:]).T
+    zc = (Wc[:, :eq.N] + 1j * Wc[:, eq.N:]).T
+    # same subspace (on the coarsest meshes the +-G waves alias at the nodes, so the blocks may be rank deficient)
+    for a, b in ((zp, zc), (zc, zp)):
+        coef = np.linalg.lstsq(a, b, rcond=None)[0]
+        assert np.linalg.norm(a @ coef - b) < 1e-9 * np.linalg.norm(b)
