@@ -102,6 +102,28 @@ int main() {
       std::printf(", \"moved\": %d}", moved ? 1 : 0);
     }
     std::printf("],\n");
+    // plane-wave phases of CreateInitialVectors: Real/ImagModeCoefficient::Eval (lib/bravais.cpp:8953-8976) at a few
+    // points (the shim's ElementTransformation maps an integration point to itself)
+    {
+      RealModeCoefficient cr;
+      ImagModeCoefficient ci;
+      cr.SetReciprocalLatticeVectors(b); ci.SetReciprocalLatticeVectors(b);
+      const int modes[3][3] = {{1, 0, 0}, {1, -1, 1}, {0, 2, -1}};
+      ElementTransformation T;
+      std::printf("  \"mode_coefficient\": [");
+      bool first = true;
+      for (auto &n : modes) {
+        cr.SetModeIndices(n[0], n[1], n[2]); ci.SetModeIndices(n[0], n[1], n[2]);
+        for (int k = 0; k < 4; k++) {
+          IntegrationPoint ip;
+          ip.Set3(0.11 + 0.17 * k, -0.23 + 0.05 * k * k, 0.31 - 0.09 * k);
+          std::printf("%s{\"n\": [%d, %d, %d], \"x\": [%.17g, %.17g, %.17g], \"re\": %.17g, \"im\": %.17g}", first ? "" : ", ",
+                      n[0], n[1], n[2], ip.x, ip.y, ip.z, cr.Eval(T, ip), ci.Eval(T, ip));
+          first = false;
+        }
+      }
+      std::printf("],\n");
+    }
     Mesh *ws = L->GetWignerSeitzMesh(false);
     mesh_json("ws_mesh", ws);
     Mesh *per = MakePeriodicMesh(ws, t);

@@ -125,6 +125,17 @@ def test_map_to_primitive_cell_against_reference_code(bloch, name):
         assert np.linalg.norm(ipt) <= np.linalg.norm(ref_ipt) + 1e-12
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_plane_wave_phase_convention_equals_reference_code(bloch, name):
+    """Real/ImagModeCoefficient of the reference (the phases of CreateInitialVectors): cos / sin(2 pi sum_j n_j b_j . x).
+    The product's plane_wave_initial_vectors interpolates E0 exp(2 pi i G . x) with G = sum_j n_j b_j."""
+    b = np.array(bloch.BravaisLattice(name).GetReciprocalLatticeVectors())
+    for r in GOLD[name]["mode_coefficient"]:
+        G = np.array(r["n"], float) @ b
+        z = np.exp(2j * np.pi * (np.array(r["x"]) @ G))
+        assert abs(z.real - r["re"]) < 1e-14 and abs(z.imag - r["im"]) < 1e-14
+
+
 @pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
 def test_product_coarse_mesh_equals_reference_code(bloch, name):
     """Topology-only handle (no GPU): element geometry and H1 vertex numbering of the unrefined cell."""
