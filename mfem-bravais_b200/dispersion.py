@@ -12,6 +12,19 @@ def sphere_eps(centers, radius=0.25, eps_in=10.0, eps_out=1.0):
     return np.where(r <= radius, eps_in, eps_out)
 
 
+def lattice_coefficient(lattice, centers, frac=0.5, val0=0.0, val1=1.0):
+    """bravais::LatticeCoefficient (lib/bravais.cpp:9834-9862) at element centres: rods along the lattice's
+    translation vectors, radius frac * (inscribed face radius); val1 inside any rod, val0 elsewhere."""
+    x = np.asarray(centers, float)
+    out = np.full(len(x), float(val0))
+    T, R = lattice.GetTranslationVectors(), lattice.GetFaceRadii()
+    for t, r in zip(T, R):
+        a = t / np.linalg.norm(t)
+        perp = x - np.outer(x @ a, a)
+        out[np.linalg.norm(perp, axis=1) < frac * r] = val1
+    return out
+
+
 def k_path(lattice, labels, npts):
     """kappa points along the path through the named symmetry points, `npts` per segment:
     kappa0 + i/npts (kappa1 - kappa0), i = 1..npts (segment start points are the previous

@@ -124,6 +124,24 @@ int main() {
       }
       std::printf("],\n");
     }
+    // LatticeCoefficient (rods along the translation vectors, lib/bravais.cpp:9834-9862) on a pseudo-random point set
+    {
+      LatticeCoefficient lc(*L, 0.5, 1.0, 10.0);
+      ElementTransformation T;
+      std::printf("  \"lattice_coefficient\": {\"frac\": 0.5, \"val0\": 1.0, \"val1\": 10.0, \"samples\": [");
+      unsigned long long lcg2 = 777;
+      for (int k = 0; k < 40; k++) {
+        double x[3];
+        for (int d = 0; d < 3; d++) {
+          lcg2 = (lcg2 * 6364136223846793005ULL + 1442695040888963407ULL);
+          x[d] = ((double)(lcg2 >> 11) / 9007199254740992.0) - 0.5;
+        }
+        IntegrationPoint ip;
+        ip.Set3(x[0], x[1], x[2]);
+        std::printf("%s[%.17g, %.17g, %.17g, %.17g]", k ? ", " : "", x[0], x[1], x[2], lc.Eval(T, ip));
+      }
+      std::printf("]},\n");
+    }
     Mesh *ws = L->GetWignerSeitzMesh(false);
     mesh_json("ws_mesh", ws);
     Mesh *per = MakePeriodicMesh(ws, t);

@@ -136,6 +136,14 @@ def test_plane_wave_phase_convention_equals_reference_code(bloch, name):
         assert abs(z.real - r["re"]) < 1e-14 and abs(z.imag - r["im"]) < 1e-14
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_lattice_coefficient_equals_reference_code(bloch, name):
+    g = GOLD[name]["lattice_coefficient"]
+    S = np.array(g["samples"])
+    got = bloch.lattice_coefficient(bloch.BravaisLattice(name), S[:, :3], g["frac"], g["val0"], g["val1"])
+    assert np.array_equal(got, S[:, 3]) and len(set(S[:, 3])) == 2
+
+
 @pytest.mark.parametrize("name", ["CUB", "FCC", "BCC"])
 def test_product_coarse_mesh_equals_reference_code(bloch, name):
     """Topology-only handle (no GPU): element geometry and H1 vertex numbering of the unrefined cell."""
