@@ -45,6 +45,9 @@ int main() {
       {"FCC", FACE_CENTERED_CUBIC, 1.0, 1.0, 1.0},
       {"BCC", BODY_CENTERED_CUBIC, 1.0, 1.0, 1.0},
       {"HEX", PRIMITIVE_HEXAGONAL_PRISM, 1.0, 1.0, 1.0},
+      {"FCC_a2", FACE_CENTERED_CUBIC, 2.0, 2.0, 2.0},                 // scaled cells
+      {"BCC_a0.5", BODY_CENTERED_CUBIC, 0.5, 0.5, 0.5},
+      {"HEX_c1.5", PRIMITIVE_HEXAGONAL_PRISM, 1.0, 1.0, 1.5},
   };
   BravaisLatticeFactory fact;
   std::printf("{\n");

@@ -136,6 +136,31 @@ def test_plane_wave_phase_convention_equals_reference_code(bloch, name):
         assert abs(z.real - r["re"]) < 1e-14 and abs(z.imag - r["im"]) < 1e-14
 
 
+@pytest.mark.parametrize("tag,name,kw", [("FCC_a2", "FCC", dict(a=2.0)), ("BCC_a0.5", "BCC", dict(a=0.5)),
+                                         ("HEX_c1.5", "HEX", dict(a=1.0, c=1.5))])
+def test_scaled_lattices_equal_reference_code(bloch, tag, name, kw):
+    """Lattice parameters other than 1 (the factory's parameter handling, lib/bravais.cpp:8662-8778)."""
+    g, L = GOLD[tag], bloch.BravaisLattice(name, **kw)
+    assert np.allclose(L.GetLatticeVectors(), g["lattice_vectors"], atol=1e-15)
+    assert np.allclose(L.GetReciprocalLatticeVectors(), g["reciprocal_vectors"], atol=1e-15)
+    assert abs(L.GetUnitCellVolume() - g["cell_volume"]) < 1e-14
+    assert np.allclose(L.GetTranslationVectors(), g["translation_vectors"], atol=1e-15)
+    assert np.allclose(L.GetFaceRadii(), g["face_radii"], atol=1e-15)
+    for i, s in enumerate(g["symmetry_points"]):
+        assert L.GetSymmetryPointLabel(i) == s["label"] and np.allclose(L.GetSymmetryPoint(i), s["kappa"], atol=1e-13)
+    for p, gp in enumerate(g["paths"]):
+        for s, seg in enumerate(gp):
+            assert np.allclose(L.GetIntermediatePoint(p, s), seg["mid"], atol=1e-13)
+    if name != "HEX":        # coarse hex cell of the scaled lattice through the topology-only handle
+        eq = bloch.MaxwellBlochWaveEquation(L, 1, 1, device=-2)
+        x0, cls, J = eq.element_geometry()
+        V = np.array(g["ws_mesh"]["vertices"])
+        ref = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], float)
+        for e, el in enumerate(g["ws_mesh"]["elements"]):
+            P = x0[e] + ref @ J[cls[e]].T
+            assert {tuple(np.round(p, 12) + 0.0) for p in P} == {tuple(np.round(V[v], 12) + 0.0) for v in el["v"]}
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_lattice_coefficient_equals_reference_code(bloch, name):
     g = GOLD[name]["lattice_coefficient"]
