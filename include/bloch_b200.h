@@ -99,6 +99,17 @@ int bloch_set_eps(bloch_handle h, const double *eps_per_elem);
 int bloch_set_muinv(bloch_handle h, const double *muinv_per_elem);
 /* SetKappa (maxwell_bloch.hpp:152; beta = |kappa|, zeta = kappa/beta, .cpp:200-210) */
 int bloch_set_kappa(bloch_handle h, const double kappa[3]);
+/* k-point batch: nk Bloch vectors kappa[3*nk] are set at once and the next bloch_solve iterates their nk
+ * INDEPENDENT eigenproblems together - same mesh, maps and coefficients, one set of kernel launches on block
+ * vectors of nk * block columns (the k-loop of maxwell_dispersion.cpp:475-531 run nk points at a time; results are
+ * those of nk separate GetEigenvalues calls).  Needs an even n_sub (multigrid projector).  bloch_set_kappa is the
+ * batch of one.  bloch_select_kpoint chooses which k-point of the batch the getters below (eigenvalues,
+ * eigenvectors, stats, field averages) refer to; bloch_solve resets the selection to 0.  Operator applies on a
+ * batched handle take nvec = nk * c vectors, vector v using kappa[v / c]. */
+#define BLOCH_MAX_BATCH 16
+int bloch_set_kappa_batch(bloch_handle h, int nk, const double *kappa /* [nk][3] */);
+int bloch_batch_size(bloch_handle h);
+int bloch_select_kpoint(bloch_handle h, int k);
 /* SetNumEigs counts REAL modes in the reference (2 per complex band); this takes complex bands */
 int bloch_set_num_bands(bloch_handle h, int n_complex_bands);
 /* SetAbsoluteTolerance (default 1e-6, .cpp:53) and lobpcg_->SetMaxIter(2000) (.cpp:543) */
@@ -128,6 +139,14 @@ typedef struct {
   int64_t kernel_launches; /* kernels launched by this handle since creation */
 } bloch_stats;
 int bloch_get_stats(bloch_handle h, bloch_stats *st);                   /* GetSolverStats */
+
+/* Measurement hook (GetSolverStats has only wall times, maxwell_bloch.hpp:232-234): with profiling on, the next
+ * bloch_solve brackets its phases with CUDA events on the handle's stream.  ms[0] whole solve, [1] ND operator-apply
+ * kernels outside the preconditioner (incl. clearing y), [2] divergence projector (S0 solves + G / G^H M applies),
+ * [3] Chebyshev preconditioner (its ND applies are [7]), [4] Gram + Rayleigh-Ritz rotation kernels, [5] host
+ * Rayleigh-Ritz incl. the copies around it (wall clock), [6] extra work of the lifted operator (V-cycle, G, G^H M, M). */
+int bloch_set_profile(bloch_handle h, int on);
+int bloch_get_profile(bloch_handle h, double *ms, int n /* <= 8 */);
 
 /* GetAOperator()/GetMOperator()->Mult (maxwell_bloch.hpp:199-200) on nvec vectors of length
  * 2N [re;im], HOST pointers (copies inside) */

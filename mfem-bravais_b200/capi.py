@@ -59,6 +59,11 @@ SIGNATURES = {
     "bloch_set_eps": (C.c_int, [_vp, _dp]),
     "bloch_set_muinv": (C.c_int, [_vp, _dp]),
     "bloch_set_kappa": (C.c_int, [_vp, _dp]),
+    "bloch_set_kappa_batch": (C.c_int, [_vp, C.c_int, _dp]),
+    "bloch_batch_size": (C.c_int, [_vp]),
+    "bloch_select_kpoint": (C.c_int, [_vp, C.c_int]),
+    "bloch_set_profile": (C.c_int, [_vp, C.c_int]),
+    "bloch_get_profile": (C.c_int, [_vp, _dp, C.c_int]),
     "bloch_set_num_bands": (C.c_int, [_vp, C.c_int]),
     "bloch_set_tol": (C.c_int, [_vp, C.c_double, C.c_int]),
     "bloch_setup": (C.c_int, [_vp]),

@@ -164,59 +164,67 @@ static void probe_diagonals(bloch_handle_s *h, std::vector<double> &dA, std::vec
   const int nc = h->mesh.n_class, Ln = h->L_nd, Lh = h->L_h1;
   cudaStream_t s = h->stream;
   auto run = [&](int L, bool h1space, std::vector<double> *outA, std::vector<double> *outM) {
-    const int ne = nc * L;
+    const int ne = nc * L, nk = h->nk;
     bloch_handle_s::ProbeWork &pw = h1space ? h->probe_h1 : h->probe_nd;
-    if (!pw.built) {
+    if (!pw.built || pw.built_nk != nk) {
       std::vector<int32_t> map((size_t)ne * L);
       std::vector<int> cls(ne);
       std::vector<double> one(ne, 1.0);
-      std::vector<D2> x((size_t)ne * L, make_double2(0.0, 0.0));
+      std::vector<D2> x((size_t)ne * L * nk, make_double2(0.0, 0.0));
       for (int c = 0; c < nc; c++)
         for (int k = 0; k < L; k++) {
           const int e = c * L + k;
           cls[e] = c;
           for (int l = 0; l < L; l++) map[(size_t)e * L + l] = (int32_t)((size_t)e * L + l + 1);
-          x[(size_t)e * L + k].x = 1.0;
+          for (int kk = 0; kk < nk; kk++) x[((size_t)e * L + k) * nk + kk].x = 1.0;
         }
       pw.map.upload(map, s); pw.cls.upload(cls, s); pw.one.upload(one, s); pw.x.upload(x, s);
       pw.y.alloc(x.size());
       pw.hy.resize(x.size());
       BLOCH_CUDA(cudaStreamSynchronize(s));
       pw.built = true;
+      pw.built_nk = nk;
     }
     DevBuf<int32_t> &dmap = pw.map; DevBuf<int> &dcls = pw.cls; DevBuf<double> &done = pw.one;
     DevBuf<D2> &dx = pw.x, &dy = pw.y;
-    const size_t xsize = (size_t)ne * L;
+    const size_t xsize = (size_t)ne * L * nk;
     ElemData E = h->E;
     E.n_elem = ne; E.cls = dcls.p; E.eps = done.p; E.muinv = done.p;
     if (h1space) E.map_h1 = dmap.p; else E.map_nd = dmap.p;
     std::vector<D2> &y = pw.hy;
-    auto fetch = [&](std::vector<double> *out) {
-      BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * y.size(), cudaMemcpyDeviceToHost, s));
+    auto fetch = [&](std::vector<double> *out) {   // out[(k * nc + c) * L + l]: element-local diagonals per k-point
+      BLOCH_CUDA(cudaMemcpyAsync(y.data(), dy.p, sizeof(D2) * xsize, cudaMemcpyDeviceToHost, s));
       BLOCH_CUDA(cudaStreamSynchronize(s));
-      out->resize((size_t)nc * L);
-      for (int c = 0; c < nc; c++)
-        for (int k = 0; k < L; k++) (*out)[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
+      out->resize((size_t)nk * nc * L);
+      for (int kk = 0; kk < nk; kk++)
+        for (int c = 0; c < nc; c++)
+          for (int k = 0; k < L; k++) (*out)[((size_t)kk * nc + c) * L + k] = y[(((size_t)(c * L + k)) * L + k) * nk + kk].x;
       double *bound = h1space ? lmax_bound_h1 : lmax_bound;
-      if (bound)   // lambda_max(D^-1 (a A + b M)) <= max_class max(mu_A, mu_M)
-        for (int c = 0; c < nc; c++) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
+      if (bound) {  // lambda_max(D^-1 (a A + b M)) <= max_class max(mu_A, mu_M)
+        std::vector<D2> loc((size_t)L * L);
+        for (int kk = 0; kk < nk; kk++)
+          for (int c = 0; c < nc; c++) {
+            for (size_t t = 0; t < (size_t)L * L; t++) loc[t] = y[((size_t)c * L * L + t) * nk + kk];
+            *bound = std::max(*bound, local_scaled_lmax(L, loc.data()));
+          }
+      }
     };
     if (h1space) {
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
-      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 1.0, 0.0));
+      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, nk, dy.p, nk, nk, s, 1.0, 0.0));
       h->count_launch();
       fetch(outA);
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
-      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, 1, dy.p, 1, 1, s, 0.0, 1.0));
+      BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, dx.p, nk, dy.p, nk, nk, s, 0.0, 1.0));
       h->count_launch();
       fetch(outM);
     } else {
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
-      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 1.0, 0.0, s));
+      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, nk, dy.p, nk, nk, 1.0, 0.0, s));
       h->count_launch();
       fetch(outA);
       BLOCH_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(D2) * xsize, s));
-      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, 1, dy.p, 1, 1, 0.0, 1.0, s));
+      BLOCH_CUDA(launch_nd_apply(h->p, h->tabs, E, dx.p, nk, dy.p, nk, nk, 0.0, 1.0, s));
       h->count_launch();
       fetch(outM);
     }
@@ -234,6 +242,7 @@ void bloch_handle_s::setup() {
   }
   E.n_elem = mesh.n_elem;
   E.n_class = mesh.n_class;
+  E.nk = nk;
   E.cls = d_cls.p;
   E.eps = d_eps.p;
   E.muinv = d_muinv.p;
@@ -241,10 +250,23 @@ void bloch_handle_s::setup() {
   E.map_h1 = d_map_h1.p;
   E.map_rt = d_map_rt.p;
   if (dirty_kappa) {
-    std::vector<double> cp((size_t)mesh.n_class * kClassParDoubles);
-    for (int c = 0; c < mesh.n_class; c++) class_params(&mesh.J[9 * c], kappa, &cp[(size_t)c * kClassParDoubles]);
+    std::vector<double> cp((size_t)nk * mesh.n_class * kClassParDoubles);
+    std::vector<int> gf(nk, 0);
+    betas.assign(nk, 0.0);
+    any_gamma = false;
+    for (int k = 0; k < nk; k++) {
+      const double *kp = &kappas[3 * k];
+      for (int c = 0; c < mesh.n_class; c++)
+        class_params(&mesh.J[9 * c], kp, &cp[((size_t)k * mesh.n_class + c) * kClassParDoubles]);
+      betas[k] = std::sqrt(kp[0] * kp[0] + kp[1] * kp[1] + kp[2] * kp[2]);
+      gf[k] = betas[k] == 0.0 ? 1 : 0;
+      any_gamma = any_gamma || gf[k];
+    }
     d_cpar.upload(cp, stream);
-    beta = std::sqrt(kappa[0] * kappa[0] + kappa[1] * kappa[1] + kappa[2] * kappa[2]);
+    d_gflag.upload(gf, stream);
+    BLOCH_CUDA(cudaStreamSynchronize(stream));   // cp / gf are stack temporaries
+    for (int d = 0; d < 3; d++) kappa[d] = kappas[d];
+    beta = betas[0];
   }
   E.cpar = d_cpar.p;
   if (dirty_kappa || dirty_coef) {
@@ -256,24 +278,26 @@ void bloch_handle_s::setup() {
     if (lmax_local <= 0.0) lmax_local = bound;
     if (lmax_local_h1 <= 0.0) lmax_local_h1 = bound_h1;
     DevBuf<double> &dl = d_dloc;
-    d_diagA.alloc(N); d_diagM.alloc(N); d_diagS0.alloc(N0); d_diagM0.alloc(N0);
-    BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N, stream));
-    BLOCH_CUDA(cudaMemsetAsync(d_diagM.p, 0, sizeof(double) * N, stream));
-    BLOCH_CUDA(cudaMemsetAsync(d_diagS0.p, 0, sizeof(double) * N0, stream));
-    BLOCH_CUDA(cudaMemsetAsync(d_diagM0.p, 0, sizeof(double) * N0, stream));
+    // Jacobi diagonals are [n][nk]: one value per (dof, k-point)
+    const int nc = mesh.n_class;
+    d_diagA.alloc((size_t)N * nk); d_diagM.alloc((size_t)N * nk); d_diagS0.alloc((size_t)N0 * nk); d_diagM0.alloc((size_t)N0 * nk);
+    BLOCH_CUDA(cudaMemsetAsync(d_diagA.p, 0, sizeof(double) * N * nk, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagM.p, 0, sizeof(double) * N * nk, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagS0.p, 0, sizeof(double) * N0 * nk, stream));
+    BLOCH_CUDA(cudaMemsetAsync(d_diagM0.p, 0, sizeof(double) * N0 * nk, stream));
     if (p <= 3) {
       dl.upload(dA, stream);
-      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagA.p, stream));
+      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagA.p, stream, nk, nc));
       BLOCH_CUDA(cudaStreamSynchronize(stream));
       dl.upload(dM, stream);
-      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagM.p, stream));
+      BLOCH_CUDA(launch_scatter_diag(d_map_nd.p, L_nd, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagM.p, stream, nk, nc));
       BLOCH_CUDA(cudaStreamSynchronize(stream));
     }
     dl.upload(dM0, stream);
-    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagM0.p, stream));
+    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_muinv.p, dl.p, mesh.n_elem, d_diagM0.p, stream, nk, nc));
     BLOCH_CUDA(cudaStreamSynchronize(stream));
     dl.upload(dS0, stream);
-    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagS0.p, stream));
+    BLOCH_CUDA(launch_scatter_diag(d_map_h1.p, L_h1, d_cls.p, d_eps.p, dl.p, mesh.n_elem, d_diagS0.p, stream, nk, nc));
     BLOCH_CUDA(cudaStreamSynchronize(stream));
     count_launch(3);
   }
@@ -290,6 +314,7 @@ void bloch_handle_s::setup() {
 // global rows are then merged on the host.  Debug / interchange path, not used by the solver.
 void bloch_handle_s::assemble(int which) {
   if (p > 3) throw std::invalid_argument("order not supported");
+  if (nk != 1) throw std::invalid_argument("matrix export needs a single-kappa handle (bloch_set_kappa)");
   if (dirty_coef || dirty_kappa) setup();
   cudaStream_t s = stream;
   const int L = L_nd, nc = mesh.n_class;
@@ -373,16 +398,18 @@ void bloch_handle_s::field_averages(int i, double out24[24]) {
   if (dirty_coef || dirty_kappa) setup();
   d_fa_e.alloc(N); d_fa_b.alloc(Nrt);
   d_fa_part.alloc((size_t)mesh.n_elem * 12); d_fa_out.alloc(12);
-  BLOCH_CUDA(cudaMemcpy2DAsync(d_fa_e.p, sizeof(D2), d_X.p + i, sizeof(D2) * block, sizeof(D2), N, cudaMemcpyDeviceToDevice, s));
-  apply_curl(d_fa_e.p, d_fa_b.p, 1);
-  BLOCH_CUDA(launch_field_avg(p, avg_tabs, E, d_x0.p, d_geom.p, kappa, d_fa_e.p, 1, d_fa_b.p, 1, 1, d_fa_part.p, d_fa_out.p, s));
+  BLOCH_CUDA(cudaMemcpy2DAsync(d_fa_e.p, sizeof(D2), d_X.p + (size_t)sel * block + i, sizeof(D2) * nk * block, sizeof(D2), N,
+                               cudaMemcpyDeviceToDevice, s));
+  const ElemData Ek = elem_of_k(sel);
+  BLOCH_CUDA(launch_curl(p, tabs, Ek, d_fa_e.p, 1, d_fa_b.p, 1, 1, s));
+  BLOCH_CUDA(launch_field_avg(p, avg_tabs, Ek, d_x0.p, d_geom.p, &kappas[3 * sel], d_fa_e.p, 1, d_fa_b.p, 1, 1, d_fa_part.p, d_fa_out.p, s));
   count_launch(2);
   D2 o[12];
   BLOCH_CUDA(cudaMemcpyAsync(o, d_fa_out.p, sizeof(o), cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
   // B = i C E / sqrt|lambda| (Bi = Re(C E), Br = -Im(C E), maxwell_bloch.cpp:1432-1457); output order of
   // the reference's argument list: Er, Ei, Br, Bi, Dr, Di, Hr, Hi
-  const double lam = std::fabs(eigenvalues[i]);
+  const double lam = std::fabs(eigenvalues[(size_t)sel * nbands + i]);
   const double sc = lam > 0 ? 1.0 / std::sqrt(lam) : 1.0;
   for (int k = 0; k < 3; k++) {
     out24[k] = o[k].x;            out24[3 + k] = o[k].y;
@@ -390,6 +417,20 @@ void bloch_handle_s::field_averages(int i, double out24[24]) {
     out24[12 + k] = o[6 + k].x;   out24[15 + k] = o[6 + k].y;
     out24[18 + k] = -sc * o[9 + k].y; out24[21 + k] = sc * o[9 + k].x;
   }
+}
+
+void bloch_handle_s::set_kappas(int n, const double *k3) {
+  if (n != nk) {   // the block layout [N][nk * block] changes: no warm start across a change of the batch size
+    have_vectors = 0;
+    have_vectors_s = 0;
+    eigenvalues.clear();
+    eigenvalues_s.clear();
+  }
+  nk = n;
+  kappas.assign(k3, k3 + 3 * (size_t)n);
+  for (int d = 0; d < 3; d++) kappa[d] = kappas[d];
+  sel = 0;
+  dirty_kappa = true;
 }
 
 void bloch_handle_s::apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm) {
@@ -400,15 +441,19 @@ void bloch_handle_s::apply_nd(const D2 *x, D2 *y, int nvec, double ca, double cm
 // is the single-pass variant with fp64 atomics, which measured ~15% faster on B200.
 void bloch_handle_s::apply_nd_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
   if (p > 3) throw std::invalid_argument("the Nedelec operators support orders 1..3 (order 4: scalar H1 problem only)");
+  if (nvec % nk != 0) throw std::invalid_argument("the number of vectors must be a multiple of the k-point batch size");
   if (two_pass) {
     d_evec.alloc((size_t)mesh.n_elem * L_nd * nvec);
     BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, stream, d_evec.p));
     BLOCH_CUDA(launch_nd_reduce(d_tp_ptr.p, d_tp_loc.p, d_evec.p, y, N, nvec, ldy, stream));
     count_launch(2);
   } else {
+    const int cat = prof_in_precond ? 7 : 1;
+    prof_begin(cat);
     BLOCH_CUDA(cudaMemset2DAsync(y, sizeof(D2) * ldy, 0, sizeof(D2) * nvec, N, stream));
     BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, stream));
     count_launch();
+    prof_end(cat);
   }
   if (ca != 0.0) stats.applies_A += nvec;
 }
@@ -637,6 +682,7 @@ int bloch_destroy(bloch_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaStream_t own = h->own_stream;
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->mg) mg_destroy(h->mg);
   delete h;
   if (own) cudaStreamDestroy(own);
@@ -712,8 +758,33 @@ int bloch_set_muinv(bloch_handle h, const double *mu) {
 }
 int bloch_set_kappa(bloch_handle h, const double kappa[3]) {
   if (!h || !kappa) return BLOCH_ERR_ARG;
-  for (int i = 0; i < 3; i++) h->kappa[i] = kappa[i];
-  h->dirty_kappa = true;
+  h->set_kappas(1, kappa);
+  return BLOCH_OK;
+}
+int bloch_set_kappa_batch(bloch_handle h, int nk, const double *kappa) {
+  API_BEGIN
+  REQUIRE(h && kappa, "null argument");
+  REQUIRE(nk >= 1 && nk <= BLOCH_MAX_BATCH, "batch size must be in [1, BLOCH_MAX_BATCH]");
+  h->set_kappas(nk, kappa);
+  return BLOCH_OK;
+  API_END
+}
+int bloch_batch_size(bloch_handle h) { return h ? h->nk : BLOCH_ERR_ARG; }
+int bloch_select_kpoint(bloch_handle h, int k) {
+  API_BEGIN
+  REQUIRE(h && k >= 0 && k < h->nk, "k-point index outside the batch");
+  h->sel = k;
+  return BLOCH_OK;
+  API_END
+}
+int bloch_set_profile(bloch_handle h, int on) {
+  if (!h) return BLOCH_ERR_ARG;
+  h->profile = on != 0;
+  return BLOCH_OK;
+}
+int bloch_get_profile(bloch_handle h, double *ms, int n) {
+  if (!h || !ms || n < 1) return BLOCH_ERR_ARG;
+  for (int i = 0; i < n; i++) ms[i] = i < 8 ? h->stats.prof_ms[i] : 0.0;
   return BLOCH_OK;
 }
 int bloch_set_num_bands(bloch_handle h, int n) {
@@ -753,24 +824,27 @@ int bloch_solve(bloch_handle h) {
   REQUIRE(h, "null handle");
   h->setup();
   h->solve();
+  h->sel = 0;
   return h->stats.converged >= h->nbands ? BLOCH_OK : BLOCH_ERR_NOCONV;
   API_END
 }
 int bloch_get_eigenvalues(bloch_handle h, double *lambda, int n) {
   API_BEGIN
   REQUIRE(h && lambda, "null argument");
-  REQUIRE(n >= 0 && n <= (int)h->eigenvalues.size(), "more eigenvalues requested than computed");
-  std::memcpy(lambda, h->eigenvalues.data(), sizeof(double) * n);
+  REQUIRE((int)h->eigenvalues.size() == h->nk * h->nbands, "no eigenvalues (call bloch_solve first)");
+  REQUIRE(n >= 0 && n <= h->nbands, "more eigenvalues requested than computed");
+  std::memcpy(lambda, h->eigenvalues.data() + (size_t)h->sel * h->nbands, sizeof(double) * n);
   return BLOCH_OK;
   API_END
 }
 int bloch_get_stats(bloch_handle h, bloch_stats *st) {
   if (!h || !st) return BLOCH_ERR_ARG;
-  st->iterations = h->stats.iterations;
-  st->converged_bands = h->stats.converged;
+  const bool perk = (int)h->stats.k_iterations.size() == h->nk && h->nk > 1;
+  st->iterations = perk ? h->stats.k_iterations[h->sel] : h->stats.iterations;
+  st->converged_bands = perk ? h->stats.k_converged[h->sel] : h->stats.converged;
   st->inner_iterations = h->stats.inner_iterations;
   st->solve_seconds = h->stats.seconds;
-  st->max_residual = h->stats.max_residual;
+  st->max_residual = perk ? h->stats.k_max_residual[h->sel] : h->stats.max_residual;
   st->applies_A = h->stats.applies_A;
   st->kernel_launches = h->stats.launches;
   return BLOCH_OK;
@@ -816,6 +890,7 @@ int bloch_apply_A_device(bloch_handle h, const double *d_x, double *d_y, int nve
   API_BEGIN
   REQUIRE(h && d_x && d_y && nvec >= 1, "bad argument");
   if (h->device < 0 || h->dirty_coef || h->dirty_kappa) h->setup();
+  BLOCH_CUDA(cudaSetDevice(h->device));
   h->apply_nd((const D2 *)d_x, (D2 *)d_y, nvec, 1.0, 0.0);
   return BLOCH_OK;
   API_END
@@ -824,6 +899,7 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
   API_BEGIN
   REQUIRE(h && d_x && d_y && nvec >= 1, "bad argument");
   if (h->device < 0 || h->dirty_coef || h->dirty_kappa) h->setup();
+  BLOCH_CUDA(cudaSetDevice(h->device));
   h->apply_nd((const D2 *)d_x, (D2 *)d_y, nvec, 0.0, 1.0);
   return BLOCH_OK;
   API_END
@@ -831,6 +907,7 @@ int bloch_apply_M_device(bloch_handle h, const double *d_x, double *d_y, int nve
 int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int nvec) {
   API_BEGIN
   REQUIRE(h && d_reim && d_block && nvec >= 1 && h->device >= 0, "bad argument");
+  BLOCH_CUDA(cudaSetDevice(h->device));
   BLOCH_CUDA(launch_pack(d_reim, (D2 *)d_block, h->N, nvec, h->stream));
   h->count_launch();
   return BLOCH_OK;
@@ -839,6 +916,7 @@ int bloch_pack_device(bloch_handle h, const double *d_reim, double *d_block, int
 int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, int nvec) {
   API_BEGIN
   REQUIRE(h && d_reim && d_block && nvec >= 1 && h->device >= 0, "bad argument");
+  BLOCH_CUDA(cudaSetDevice(h->device));
   BLOCH_CUDA(launch_unpack((const D2 *)d_block, d_reim, h->N, nvec, h->stream));
   h->count_launch();
   return BLOCH_OK;
@@ -924,6 +1002,7 @@ int bloch_prolong_eigenvectors(bloch_handle coarse, bloch_handle fine) {
               coarse->coarse_hex == fine->coarse_hex && coarse->coarse_vert == fine->coarse_vert,
           "fine mesh must be the uniform refinement of the coarse one");
   REQUIRE(coarse->have_vectors > 0, "no coarse eigenvectors (call bloch_solve on the coarse handle first)");
+  REQUIRE(coarse->nk == 1 && fine->nk == 1, "multilevel warm start works on single-kappa handles");
   BLOCH_CUDA(cudaSetDevice(fine->device));
   const int p = fine->p, q = p + 1, mb = coarse->block;
   NdTransfer1D T;
@@ -959,7 +1038,8 @@ int bloch_get_field_averages(bloch_handle h, int i, double out24[24]) {
   API_BEGIN
   REQUIRE(h && out24, "null argument");
   REQUIRE(h->device >= 0, "topology-only handle");
-  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  REQUIRE(i >= 0 && i < h->have_vectors && i < h->nbands && (int)h->eigenvalues.size() == h->nk * h->nbands,
+          "eigenvector index out of range (only the bands of the last bloch_solve are addressable)");
   REQUIRE(h->p <= 3, "order not supported");
   BLOCH_CUDA(cudaSetDevice(h->device));
   h->field_averages(i, out24);
@@ -985,8 +1065,7 @@ int bloch_rb_size(bloch_handle h) { return h ? h->rb_size : BLOCH_ERR_ARG; }
 int bloch_rb_approx(bloch_handle h, const double kappa[3], double *lambda, int n) {
   API_BEGIN
   REQUIRE(h && kappa && lambda && n >= 1, "bad argument");
-  for (int i = 0; i < 3; i++) h->kappa[i] = kappa[i];
-  h->dirty_kappa = true;
+  h->set_kappas(1, kappa);
   auto t0 = std::chrono::steady_clock::now();
   h->setup();
   if (std::getenv("BLOCH_VERBOSE"))
@@ -1025,8 +1104,9 @@ int bloch_scalar_solve(bloch_handle h) {
 }
 int bloch_scalar_get_eigenvalues(bloch_handle h, double *lambda, int n) {
   API_BEGIN
-  REQUIRE(h && lambda && n >= 0 && n <= (int)h->eigenvalues_s.size(), "more eigenvalues requested than computed");
-  std::memcpy(lambda, h->eigenvalues_s.data(), sizeof(double) * n);
+  REQUIRE(h && lambda && n >= 0 && n <= h->nbands_s && (int)h->eigenvalues_s.size() == h->nk * h->nbands_s,
+          "more eigenvalues requested than computed");
+  std::memcpy(lambda, h->eigenvalues_s.data() + (size_t)h->sel * h->nbands_s, sizeof(double) * n);
   return BLOCH_OK;
   API_END
 }
@@ -1061,11 +1141,12 @@ int bloch_debug_fp64_peak(bloch_handle h, double *tflops) {
 int bloch_get_eigenvector_E(bloch_handle h, int i, double *re, double *im) {
   API_BEGIN
   REQUIRE(h && re && im, "null argument");
-  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  REQUIRE(i >= 0 && i < h->have_vectors && i < h->nbands && (int)h->eigenvalues.size() == h->nk * h->nbands,
+          "eigenvector index out of range (only the bands of the last bloch_solve are addressable)");
   BLOCH_CUDA(cudaSetDevice(h->device));
   std::vector<D2> col(h->N);
-  BLOCH_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(D2), h->d_X.p + i, sizeof(D2) * h->block, sizeof(D2), h->N,
-                               cudaMemcpyDeviceToHost, h->stream));
+  BLOCH_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(D2), h->d_X.p + (size_t)h->sel * h->block + i,
+                               sizeof(D2) * h->nk * h->block, sizeof(D2), h->N, cudaMemcpyDeviceToHost, h->stream));
   BLOCH_CUDA(cudaStreamSynchronize(h->stream));
   for (long k = 0; k < h->N; k++) { re[k] = col[k].x; im[k] = col[k].y; }
   return BLOCH_OK;
@@ -1074,20 +1155,22 @@ int bloch_get_eigenvector_E(bloch_handle h, int i, double *re, double *im) {
 int bloch_get_eigenvector_B(bloch_handle h, int i, double *re, double *im) {
   API_BEGIN
   REQUIRE(h && re && im, "null argument");
-  REQUIRE(i >= 0 && i < h->have_vectors, "eigenvector index out of range (call bloch_solve first)");
+  REQUIRE(i >= 0 && i < h->have_vectors && i < h->nbands && (int)h->eigenvalues.size() == h->nk * h->nbands,
+          "eigenvector index out of range (only the bands of the last bloch_solve are addressable)");
   BLOCH_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   DevBuf<D2> e, b;
   e.alloc(h->N); b.alloc(h->Nrt);
-  BLOCH_CUDA(cudaMemcpy2DAsync(e.p, sizeof(D2), h->d_X.p + i, sizeof(D2) * h->block, sizeof(D2), h->N,
-                               cudaMemcpyDeviceToDevice, s));
-  h->apply_curl(e.p, b.p, 1);
+  BLOCH_CUDA(cudaMemcpy2DAsync(e.p, sizeof(D2), h->d_X.p + (size_t)h->sel * h->block + i, sizeof(D2) * h->nk * h->block,
+                               sizeof(D2), h->N, cudaMemcpyDeviceToDevice, s));
+  BLOCH_CUDA(launch_curl(h->p, h->tabs, h->elem_of_k(h->sel), e.p, 1, b.p, 1, 1, s));
+  h->count_launch();
   std::vector<D2> col(h->Nrt);
   BLOCH_CUDA(cudaMemcpyAsync(col.data(), b.p, sizeof(D2) * h->Nrt, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));
   // B = C E / sqrt|lambda| (maxwell_bloch.cpp:1432-1457).  In the reference's real block form
   // C E = [Cr; Ci] and it returns Bi = block 0, Br = -block 1.
-  const double lam = std::fabs(h->eigenvalues[i]);
+  const double lam = std::fabs(h->eigenvalues[(size_t)h->sel * h->nbands + i]);
   const double sc = lam > 0 ? 1.0 / std::sqrt(lam) : 1.0;
   for (long k = 0; k < h->Nrt; k++) { im[k] = sc * col[k].x; re[k] = -sc * col[k].y; }
   return BLOCH_OK;

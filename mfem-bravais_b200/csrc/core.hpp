@@ -9,6 +9,7 @@
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "basis.hpp"
@@ -42,7 +43,8 @@ inline void h_sync(cudaStream_t s) {
     BLOCH_CUDA(cudaStreamSynchronize(s));
     return;
   }
-  static thread_local cudaEvent_t ev = nullptr;
+  static thread_local cudaEvent_t evs[kMaxDevices] = {};   // an event belongs to the device it was created on
+  cudaEvent_t &ev = evs[current_device_slot()];
   if (!ev) BLOCH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
   BLOCH_CUDA(cudaEventRecord(ev, s));
   BLOCH_CUDA(cudaEventSynchronize(ev));
@@ -91,6 +93,14 @@ struct SolverStats {
   int iterations = 0, converged = 0, inner_iterations = 0;
   double seconds = 0, max_residual = 0;
   int64_t applies_A = 0, launches = 0;
+  // per k-point of a batched solve (size nk): outer iterations until that k-point converged, converged bands,
+  // largest residual of its wanted bands
+  std::vector<int> k_iterations, k_converged;
+  std::vector<double> k_max_residual;
+  // phase times of the last solve in ms (only with profiling on, bloch_set_profile): whole solve, operator-apply
+  // kernels (ND A/M applies incl. the clearing of y), projector (inner S0 solves + G, G^H M applies),
+  // Chebyshev vector updates, Gram + rotation kernels, host Rayleigh-Ritz (incl. the copies around it)
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace bloch_b200
@@ -112,9 +122,18 @@ struct bloch_handle_s {
   int L_nd = 0, L_h1 = 0, L_rt = 0;
 
   std::vector<double> eps, muinv;
+  // k-point batch: nk Bloch vectors solved together (independent eigenproblems sharing mesh, maps and
+  // coefficients, maxwell_dispersion.cpp:475-531); kappa / beta alias k-point 0 for the single-kappa entry points
+  int nk = 1;
+  std::vector<double> kappas = {0, 0, 0};   // [nk][3]
+  std::vector<double> betas = {0};          // [nk]
   double kappa[3] = {0, 0, 0};
   double beta = 0;
+  int sel = 0;                              // k-point the getters refer to (bloch_select_kpoint)
+  bloch_b200::DevBuf<int> d_gflag;          // [nk] 1 where kappa == 0 (S0 singular on constants)
+  bool any_gamma = false;
   bool dirty_coef = true, dirty_kappa = true;
+  bool profile = false;
 
   bloch_b200::DevBuf<int> d_cls;
   bloch_b200::DevBuf<double> d_eps, d_muinv, d_cpar;
@@ -134,9 +153,9 @@ struct bloch_handle_s {
   int cheb_degree = 8;
   double lmaxA = 0;                 // bound of lambda_max(D^-1 (A + sigma M)) used by Chebyshev
   double lmax_local = 0;            // max over classes of lambda_max(diag(X_e)^-1 X_e), X = A, M
-  std::vector<double> eigenvalues;  // ascending
-  bloch_b200::DevBuf<D2> d_X;       // eigenvectors, block layout [N][block]
-  int have_vectors = 0;             // number of valid columns in d_X
+  std::vector<double> eigenvalues;  // ascending, [nk][nbands]
+  bloch_b200::DevBuf<D2> d_X;       // eigenvectors, block layout [N][nk * block] (column k * block + j)
+  int have_vectors = 0;             // number of valid columns per k-point in d_X
   std::vector<double> init_vecs;    // user supplied [m][2N]
   int n_init = 0;
   bloch_b200::SolverStats stats;
@@ -175,16 +194,24 @@ struct bloch_handle_s {
     bloch_b200::DevBuf<int32_t> map;
     bloch_b200::DevBuf<int> cls;
     bloch_b200::DevBuf<double> one;
-    bloch_b200::DevBuf<D2> x, y;
+    bloch_b200::DevBuf<D2> x, y;     // [n_class * L * L][nk]: the unit vectors replicated per k-point
     std::vector<D2> hy;
     bool built = false;
+    int built_nk = 0;
   } probe_nd, probe_h1;
   bloch_b200::DevBuf<double> d_dloc;
 
   struct LobpcgWork {
     bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM, Lu, Lphi, Lg;
-    bloch_b200::DevBuf<double> dlam, drn;
+    bloch_b200::DevBuf<double> dlam, drn, dtau;
   } lw;
+
+  // workspace of the divergence projector (inner S0 solve); owned by the handle so that it is released by
+  // bloch_destroy and always lives on the handle's device
+  struct ProjWork {
+    bloch_b200::DevBuf<D2> rhs, phi, z, p, q, g;
+    bloch_b200::DevBuf<double> scal;
+  } pw;
 
   // scratch for host-pointer entry points
   bloch_b200::DevBuf<double> d_io_a, d_io_b;
@@ -196,10 +223,26 @@ struct bloch_handle_s {
   void apply_h1(int mode, const D2 *x, D2 *y, int nvec);               // zeroes y for modes 0, 2
   void apply_curl(const D2 *x, D2 *y, int nvec);
   void project(D2 *x, int nvec, double rel_tol, int *iters);           // in place x <- P x
+  bloch_b200::ElemData elem_of_k(int k) const {                         // single-kappa view of k-point k's class table
+    bloch_b200::ElemData K = E;
+    K.nk = 1;
+    K.cpar = E.cpar + (size_t)k * E.n_class * bloch_b200::kClassParDoubles;
+    return K;
+  }
+  void set_kappas(int n, const double *k3);
   void solve();
   void solve_scalar();
   void lobpcg(bloch_b200::EigProblem &prob);
   void apply_scalar_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm);
   void setup_scalar();
   void count_launch(int n = 1) { stats.launches += n; }
+
+  // phase timing (bloch_set_profile / bloch_get_profile); categories: see SolverStats::prof_ms
+  std::vector<cudaEvent_t> prof_pool;
+  std::pair<cudaEvent_t, cudaEvent_t> prof_open[8] = {};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_done[8];
+  bool prof_in_precond = false;
+  void prof_begin(int cat);
+  void prof_end(int cat);
+  void prof_collect();
 };

@@ -8,6 +8,11 @@ namespace dev {
 
 __device__ __forceinline__ double2 ld2(const double2 *p) { return *p; }
 
+// row of the (k-point, class) parameter table used by column v of an element of class cls (kernels.hpp: ElemData)
+__device__ __forceinline__ int vclass(const ElemData &E, int cls, int v) { return cls + E.n_class * (v / E.cpk); }
+// number of doubles of the whole table
+__device__ __forceinline__ int cpar_doubles(const ElemData &E) { return E.nk * E.n_class * kClassParDoubles; }
+
 #define CFMA(acc, a, z)            \
   {                                \
     (acc).x = fma((a), (z).x, (acc).x); \

@@ -155,7 +155,8 @@ cudaError_t field_avg_t(const AvgTabs &A, const ElemData &E, const double *x0, c
                         cudaStream_t s) {
   using D = Dim<P>;
   const size_t smem = (size_t)(D::LND + D::LRT + FA_WARPS * 6) * 32 * sizeof(double2);
-  static bool attr_set = false;
+  static bool attr_set_of[kMaxDevices] = {};
+  bool &attr_set = attr_set_of[current_device_slot()];
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(k_field_avg<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;

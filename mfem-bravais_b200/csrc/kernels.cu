@@ -167,7 +167,7 @@ k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__re
   double2 *sRT = sBuf1 + D::LND * 32;
   double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  for (int i = threadIdx.x; i < cpar_doubles(E); i += NW * 32) sCP[i] = E.cpar[i];
   constexpr int KG = (D::LND + NW - 1) / NW;
   const long ntiles = (n_items + 31) / 32;
   const double2 zero2 = make_double2(0.0, 0.0);
@@ -176,7 +176,7 @@ k_nd_apply(const __grid_constant__ Tabs T, const ElemData E, const double2 *__re
     const long item = tile * 32 + lane;
     const bool act = tile < ntiles && item < n_items;
     const int e = act ? (int)(item / m) : 0;
-    cls_ = act ? __ldg(E.cls + e) : 0;
+    cls_ = act ? vclass(E, __ldg(E.cls + e), (int)(item - (long)e * m)) : 0;
     eps_ = act ? __ldg(E.eps + e) : 0.0;
     mui_ = act ? __ldg(E.muinv + e) : 0.0;
     const int32_t *mp = E.map_nd + (long)e * D::LND;
@@ -293,7 +293,7 @@ k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restr
   double2 *sH = sND + D::LND * 32;
   double *sCP = reinterpret_cast<double *>(sH + D::LH1 * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  for (int i = threadIdx.x; i < cpar_doubles(E); i += NW * 32) sCP[i] = E.cpar[i];
   const long item = (long)blockIdx.x * 32 + lane;
   const bool active = item < n_items;
   const int e = active ? (int)(item / m) : 0;
@@ -319,7 +319,7 @@ k_h1_op(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restr
     }
   }
   __syncthreads();
-  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
+  const double *cp = sCP + kClassParDoubles * (active ? vclass(E, E.cls[e], v) : 0);
   const double eps = active ? E.eps[e] : 0.0;
   if (MODE == 2) {
     nd_transform_all<P, NW, 0>(sND, T, warp, lane);
@@ -434,7 +434,7 @@ k_curl(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restri
   double2 *sRT = sND + D::LND * 32;
   double *sCP = reinterpret_cast<double *>(sRT + D::LRT * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NW * 32) sCP[i] = E.cpar[i];
+  for (int i = threadIdx.x; i < cpar_doubles(E); i += NW * 32) sCP[i] = E.cpar[i];
   const long item = (long)blockIdx.x * 32 + lane;
   const bool active = item < n_items;
   const int e = active ? (int)(item / m) : 0;
@@ -451,7 +451,7 @@ k_curl(const __grid_constant__ Tabs T, const ElemData E, const double2 *__restri
     sND[j * 32 + lane] = val;
   }
   __syncthreads();
-  const double *cp = sCP + kClassParDoubles * (active ? E.cls[e] : 0);
+  const double *cp = sCP + kClassParDoubles * (active ? vclass(E, E.cls[e], v) : 0);
   nd_transform_all<P, NW, 0>(sND, T, warp, lane);
   __syncthreads();
   for (int t = warp; t < 3 * Q; t += NW) {
@@ -517,8 +517,9 @@ cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int l
                        int nvec, double ca, double cm, double2 *z, cudaStream_t s) {
   using D = Dim<P>;
   const size_t smem = (size_t)(2 * D::LND + D::LRT) * 32 * sizeof(double2) +
-                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
-  static int max_ctas = 0;
+                      (size_t)E.nk * E.n_class * kClassParDoubles * sizeof(double);
+  static int max_ctas_of[kMaxDevices] = {};
+  int &max_ctas = max_ctas_of[current_device_slot()];
   if (max_ctas == 0) {
     cudaError_t err = cudaFuncSetAttribute(k_nd_apply<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;
@@ -533,7 +534,7 @@ cudaError_t nd_apply_t(const Tabs &T, const ElemData &E, const double2 *x, int l
   const long n_items = (long)E.n_elem * nvec;
   const long ntiles = (n_items + 31) / 32;
   const unsigned grid = (unsigned)(ntiles < max_ctas ? ntiles : max_ctas);
-  k_nd_apply<P, NW><<<grid, NW * 32, smem, s>>>(T, E, x, y, z, nvec, ldx, ldy, n_items, ca, cm);
+  k_nd_apply<P, NW><<<grid, NW * 32, smem, s>>>(T, with_cpk(E, nvec), x, y, z, nvec, ldx, ldy, n_items, ca, cm);
   return cudaGetLastError();
 }
 
@@ -551,9 +552,13 @@ k_h1_dense(const ElemData E, const double2 *__restrict__ S, const double2 *__res
   constexpr int RPW = (L + NWD - 1) / NWD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *sX = reinterpret_cast<double2 *>(smem_raw);      // [L][32] gathered inputs
-  double2 *sS = sX + L * 32;                                  // [n_class][L][L] class matrices
+  double2 *sS = sX + L * 32;                                  // [n_class][L][L] class matrices (single kappa only)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < E.n_class * L * L; i += NWD * 32) sS[i] = S[i];
+  // batched k-points: nk * n_class matrices do not fit in shared memory; they are read through L1 instead (a tile
+  // of 32 items spans at most a few (k-point, class) pairs, so the loads stay nearly warp-uniform)
+  const bool staged = E.nk == 1;
+  if (staged)
+    for (int i = threadIdx.x; i < E.n_class * L * L; i += NWD * 32) sS[i] = S[i];
   const long item = (long)blockIdx.x * 32 + lane;
   const bool active = item < n_items;
   const int e = active ? (int)(item / m) : 0;
@@ -563,7 +568,7 @@ k_h1_dense(const ElemData E, const double2 *__restrict__ S, const double2 *__res
     sX[k * 32 + lane] = active ? X[(long)(__ldg(mh + k) - 1) * ldx + v] : make_double2(0.0, 0.0);
   __syncthreads();
   if (!active) return;
-  const double2 *Sc = sS + E.cls[e] * L * L;
+  const double2 *Sc = staged ? sS + E.cls[e] * L * L : S + (size_t)vclass(E, E.cls[e], v) * L * L;
   const int row0 = warp * RPW;
   double2 acc[RPW];
 #pragma unroll
@@ -606,7 +611,7 @@ k_h1_s0_item(const __grid_constant__ Tabs T, const ElemData E, const double2 *__
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *scol = reinterpret_cast<double2 *>(smem_raw) + threadIdx.x;
   double *sCP = reinterpret_cast<double *>(reinterpret_cast<double2 *>(smem_raw) + D::LH1 * NT);
-  for (int i = threadIdx.x; i < E.n_class * kClassParDoubles; i += NT) sCP[i] = E.cpar[i];
+  for (int i = threadIdx.x; i < cpar_doubles(E); i += NT) sCP[i] = E.cpar[i];
   __syncthreads();
   const long item = (long)blockIdx.x * NT + threadIdx.x;
   if (item >= n_items) return;
@@ -616,7 +621,7 @@ k_h1_s0_item(const __grid_constant__ Tabs T, const ElemData E, const double2 *__
 #pragma unroll
   for (int k = 0; k < D::LH1; k++) scol[k * NT] = X[(long)(__ldg(mh + k) - 1) * ldx + v];
   double2 out[D::LH1];
-  s0_item<P, NT>(T, sCP + kClassParDoubles * E.cls[e], ca * E.eps[e], scol, out);
+  s0_item<P, NT>(T, sCP + kClassParDoubles * vclass(E, E.cls[e], v), ca * E.eps[e], scol, out);
   if (EVEC) {
 #pragma unroll
     for (int k = 0; k < D::LH1; k++) Y[((long)e * D::LH1 + k) * m + v] = out[k];
@@ -653,8 +658,9 @@ cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x
                     int ldy, int nvec, double ca, double cm, cudaStream_t s) {
   using D = Dim<P>;
   const size_t smem = (size_t)(D::LND + D::LH1) * 32 * sizeof(double2) +
-                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
-  static bool attr_set = false;
+                      (size_t)E.nk * E.n_class * kClassParDoubles * sizeof(double);
+  static bool attr_set_of[kMaxDevices] = {};
+  bool &attr_set = attr_set_of[current_device_slot()];
   if (!attr_set) {
     cudaError_t err;
     if constexpr (P <= 3) {
@@ -671,13 +677,15 @@ cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x
   }
   const long n_items = (long)E.n_elem * nvec;
   const unsigned grid = (unsigned)((n_items + 31) / 32);
+  const ElemData Ek = with_cpk(E, nvec);
   if constexpr (P <= 2) {
     static const int item_kernel = [] { const char *e = std::getenv("BLOCH_H1_ITEM"); return e ? std::atoi(e) : 1; }();
     const bool mode_evec = mode == 4;
     if ((mode == 3 || mode == 4) && cm == 0.0 && item_kernel) {
       constexpr int NT = 64;
-      const size_t sm = (size_t)D::LH1 * NT * sizeof(double2) + (size_t)E.n_class * kClassParDoubles * sizeof(double);
-      static bool attr2 = false;
+      const size_t sm = (size_t)D::LH1 * NT * sizeof(double2) + (size_t)E.nk * E.n_class * kClassParDoubles * sizeof(double);
+      static bool attr2_of[kMaxDevices] = {};
+      bool &attr2 = attr2_of[current_device_slot()];
       if (!attr2) {
         cudaError_t err = cudaFuncSetAttribute(k_h1_s0_item<P, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (err != cudaSuccess) return err;
@@ -686,21 +694,21 @@ cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x
         attr2 = true;
       }
       if (mode_evec)
-        k_h1_s0_item<P, NT, true><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca);
+        k_h1_s0_item<P, NT, true><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, ca);
       else
-        k_h1_s0_item<P, NT, false><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca);
+        k_h1_s0_item<P, NT, false><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, ca);
       return cudaGetLastError();
     }
   }
   if (mode == 4) return cudaErrorInvalidValue;   // E-vector variant exists for the item kernel only
   if (mode == 3) {
-    k_h1_op<P, NW, 3><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, ca, cm);
+    k_h1_op<P, NW, 3><<<grid, NW * 32, smem, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, ca, cm);
     return cudaGetLastError();
   }
   if constexpr (P <= 3) {
-    if (mode == 0) k_h1_op<P, NW, 0><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
-    else if (mode == 1) k_h1_op<P, NW, 1><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
-    else k_h1_op<P, NW, 2><<<grid, NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    if (mode == 0) k_h1_op<P, NW, 0><<<grid, NW * 32, smem, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    else if (mode == 1) k_h1_op<P, NW, 1><<<grid, NW * 32, smem, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
+    else k_h1_op<P, NW, 2><<<grid, NW * 32, smem, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, 1.0, 0.0);
     return cudaGetLastError();
   }
   return cudaErrorInvalidValue;
@@ -711,15 +719,16 @@ cudaError_t curl_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, 
                    int nvec, cudaStream_t s) {
   using D = Dim<P>;
   const size_t smem = (size_t)(D::LND + D::LRT) * 32 * sizeof(double2) +
-                      (size_t)E.n_class * kClassParDoubles * sizeof(double);
-  static bool attr_set = false;
+                      (size_t)E.nk * E.n_class * kClassParDoubles * sizeof(double);
+  static bool attr_set_of[kMaxDevices] = {};
+  bool &attr_set = attr_set_of[current_device_slot()];
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(k_curl<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
   const long n_items = (long)E.n_elem * nvec;
-  k_curl<P, NW><<<(unsigned)((n_items + 31) / 32), NW * 32, smem, s>>>(T, E, x, y, nvec, ldx, ldy, n_items);
+  k_curl<P, NW><<<(unsigned)((n_items + 31) / 32), NW * 32, smem, s>>>(T, with_cpk(E, nvec), x, y, nvec, ldx, ldy, n_items);
   return cudaGetLastError();
 }
 
@@ -780,9 +789,10 @@ cudaError_t launch_h1_dense(int p, const ElemData &E, const double2 *S, const do
   const long n_items = (long)E.n_elem * nvec;
   const unsigned grid = (unsigned)((n_items + 31) / 32);
   const int L = (p + 1) * (p + 1) * (p + 1);
-  const size_t smem = ((size_t)L * 32 + (size_t)E.n_class * L * L) * sizeof(double2);
+  const size_t smem = ((size_t)L * 32 + (E.nk == 1 ? (size_t)E.n_class * L * L : 0)) * sizeof(double2);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
+  static bool attr_set_of[kMaxDevices] = {};
+  bool &attr_set = attr_set_of[current_device_slot()];
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(k_h1_dense<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (err != cudaSuccess) return err;
@@ -791,8 +801,8 @@ cudaError_t launch_h1_dense(int p, const ElemData &E, const double2 *S, const do
     attr_set = true;
   }
   switch (p) {
-    case 1: k_h1_dense<1, 4><<<grid, 4 * 32, smem, s>>>(E, S, x, y, nvec, ldx, ldy, n_items, ca); break;
-    case 2: k_h1_dense<2, 9><<<grid, 9 * 32, smem, s>>>(E, S, x, y, nvec, ldx, ldy, n_items, ca); break;
+    case 1: k_h1_dense<1, 4><<<grid, 4 * 32, smem, s>>>(with_cpk(E, nvec), S, x, y, nvec, ldx, ldy, n_items, ca); break;
+    case 2: k_h1_dense<2, 9><<<grid, 9 * 32, smem, s>>>(with_cpk(E, nvec), S, x, y, nvec, ldx, ldy, n_items, ca); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -1001,13 +1011,13 @@ __global__ void k_scalar_div(const double *num, const double *den, double *out, 
 }
 __global__ void k_scatter_diag(const int32_t *__restrict__ map, int L, const int *__restrict__ cls,
                                const double *__restrict__ coef, const double *__restrict__ dloc,
-                               int n_elem, double *__restrict__ d) {
+                               int n_elem, double *__restrict__ d, int nk, int n_class) {
   const long total = (long)n_elem * L;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const int e = (int)(t / L), l = (int)(t - (long)e * L);
     const int s = map[t];
     const long g = (s < 0 ? -s : s) - 1;
-    atomicAdd(d + g, coef[e] * dloc[(long)cls[e] * L + l]);
+    for (int k = 0; k < nk; k++) atomicAdd(d + g * nk + k, coef[e] * dloc[((long)k * n_class + cls[e]) * L + l]);
   }
 }
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
@@ -1094,8 +1104,8 @@ cudaError_t launch_scalar_div(const double *num, const double *den, double *out,
   return cudaGetLastError();
 }
 cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const double *coef,
-                                const double *dloc, int n_elem, double *d, cudaStream_t s) {
-  k_scatter_diag<<<grid_for((long)n_elem * L, 256), 256, 0, s>>>(map, L, cls, coef, dloc, n_elem, d);
+                                const double *dloc, int n_elem, double *d, cudaStream_t s, int nk, int n_class) {
+  k_scatter_diag<<<grid_for((long)n_elem * L, 256), 256, 0, s>>>(map, L, cls, coef, dloc, n_elem, d, nk, n_class);
   return cudaGetLastError();
 }
 cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s) {

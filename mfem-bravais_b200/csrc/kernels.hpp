@@ -10,6 +10,14 @@
 namespace bloch_b200 {
 
 constexpr int kMaxP = 4;
+constexpr int kMaxDevices = 64;
+// index of the current device for per-device one-time launcher state (cudaFuncSetAttribute and occupancy
+// results are per device; a process may hold handles on several devices)
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
 constexpr int kMaxClasses = 64;
 constexpr int kClassParDoubles = 22;   // kh[3], G[3][3], H[3][3], det J
 
@@ -36,15 +44,27 @@ struct NdTransfer1D {
 };
 
 struct ElemData {            // device pointers, element order = mesh order
-  int n_elem, n_class;
-  const int *cls;            // [n_elem]
-  const double *eps;         // [n_elem]
-  const double *muinv;       // [n_elem]
-  const double *cpar;        // [n_class][21]   (kappa dependent)
-  const int32_t *map_nd;     // [n_elem][L_nd]  kernel ("cyclic") local order, signed 1-based
-  const int32_t *map_h1;     // [n_elem][L_h1]  kernel local order, 1-based
-  const int32_t *map_rt;     // [n_elem][L_rt]  kernel local order, signed 1-based
+  int n_elem = 0, n_class = 0;
+  // k-point batching: a handle may carry nk Bloch vectors at once.  Every block vector then has nvec = nk * cpk
+  // columns, column v belongs to k-point v / cpk and uses the class table cpar[v / cpk][class]; the launchers fill
+  // in cpk = nvec / nk (with_cpk below), nk == 1 gives the plain single-kappa behaviour.
+  int nk = 1, cpk = 1 << 30;
+  const int *cls = nullptr;            // [n_elem]
+  const double *eps = nullptr;         // [n_elem]
+  const double *muinv = nullptr;       // [n_elem]
+  const double *cpar = nullptr;        // [nk][n_class][22]   (kappa dependent)
+  const int32_t *map_nd = nullptr;     // [n_elem][L_nd]  kernel ("cyclic") local order, signed 1-based
+  const int32_t *map_h1 = nullptr;     // [n_elem][L_h1]  kernel local order, 1-based
+  const int32_t *map_rt = nullptr;     // [n_elem][L_rt]  kernel local order, signed 1-based
 };
+// copy of E with the columns-per-k-point of an nvec-column block vector filled in
+inline ElemData with_cpk(const ElemData &E, int nvec) {
+  ElemData K = E;
+  if (K.nk < 1) K.nk = 1;
+  K.cpk = nvec / K.nk;
+  if (K.cpk < 1) K.cpk = 1;
+  return K;
+}
 
 // y = ca * A x + cm * M x   (ND -> ND), A = (C - i Z_kappa)^H M2(muinv) (C - i Z_kappa), M = M1(eps)
 // z == nullptr: signed scatter-ADD into y with fp64 atomics (y must be zero-initialised).
@@ -125,9 +145,10 @@ cudaError_t launch_col_dot(const double2 *A, const double2 *B, long n, int m, do
 // tiny helpers on per-column scalars (device side, avoids host round trips in CG)
 //   out[j] = (den[j] != 0) ? num[j]/den[j] : 0
 cudaError_t launch_scalar_div(const double *num, const double *den, double *out, int m, cudaStream_t s);
-// diagonal accumulation: d[gid] += coef_e * dloc[cls][l] over elements (real)
+// diagonal accumulation: d[gid][k] += coef_e * dloc[k][cls][l] over elements (real); d is [n][nk], k = k-point
 cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const double *coef,
-                                const double *dloc, int n_elem, double *d, cudaStream_t s);
+                                const double *dloc, int n_elem, double *d, cudaStream_t s, int nk = 1,
+                                int n_class = 0);
 // Whole block Jacobi-PCG solve of S0 phi = r0 in ONE cooperative launch (proj_cg.cu).  On entry
 // phi = 0, r = right-hand side, scal (8*m doubles) = 0; info[0] = iterations, info[1] = converged.
 cudaError_t launch_proj_cg(int p, const Tabs &T, const ElemData &E, const double *jac, double2 *phi,

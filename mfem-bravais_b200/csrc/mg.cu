@@ -123,11 +123,13 @@ __global__ void k_invert(double *x, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
     x[t] = x[t] > 0 ? 1.0 / x[t] : 0.0;
 }
-// x[r][v] = sum_c inv[r][c] b[c][v]   (small dense coarse solve)
-__global__ void k_dense_apply(const D2 *__restrict__ inv, const D2 *__restrict__ b, D2 *__restrict__ x, int n, int m) {
+// x[r][v] = sum_c inv_k[r][c] b[c][v], k = v / cpk   (small dense coarse solve; one inverse per k-point)
+__global__ void k_dense_apply(const D2 *__restrict__ inv_all, const D2 *__restrict__ b, D2 *__restrict__ x, int n, int m,
+                              int cpk) {
   const int total = n * m;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int r = t / m, v = t - r * m;
+    const D2 *inv = inv_all + (size_t)(v / cpk) * n * n;
     D2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
     int c = 0;
     for (; c + 8 <= n; c += 8) {               // 8 independent load pairs in flight per step
@@ -167,11 +169,12 @@ __global__ void k_add(D2 *__restrict__ x, const D2 *__restrict__ y, long total) 
 // (all Chebyshev coefficients are read from device memory - coef[0] = 1/theta, coef[2k-1], coef[2k] for step
 // k - so that the captured CUDA graphs stay valid when Setup() changes them with kappa)
 __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ d,
-                             D2 *__restrict__ x, const double *__restrict__ coef, long n, int m, int accumulate) {
+                             D2 *__restrict__ x, const double *__restrict__ coef, long n, int m, int accumulate, int nk,
+                             int cpk) {
   const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = c0 * jac[t / m];
+    const double s = c0 * jac[(t / m) * nk + (int)(t % m) / cpk];
     const D2 v = r[t];
     const D2 o = make_double2(s * v.x, s * v.y);
     d[t] = o;
@@ -181,11 +184,11 @@ __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restric
 // r -= q ; d = a d + b jac r ; x += d
 __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict__ q, D2 *__restrict__ r,
                             D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, int step, long n,
-                            int m) {
+                            int m, int nk, int cpk) {
   const double a = coef[2 * step - 1], b = coef[2 * step];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = b * jac[t / m];
+    const double s = b * jac[(t / m) * nk + (int)(t % m) / cpk];
     const D2 qq = q[t];
     D2 rr = r[t];
     rr.x -= qq.x; rr.y -= qq.y;
@@ -211,10 +214,12 @@ __global__ void k_col_sum(const D2 *__restrict__ X, long n, int m, double *__res
     atomicAdd(sums + 2 * (t % m) + 1, v.y);
   }
 }
-__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums) {
+__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums,
+                            const int *__restrict__ gflag, int cpk) {
   const long total = n * m;
   const double inv = 1.0 / (double)n;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    if (!gflag[(int)(t % m) / cpk]) continue;
     D2 v = X[t];
     v.x -= sums[2 * (t % m)] * inv; v.y -= sums[2 * (t % m) + 1] * inv;
     X[t] = v;
@@ -230,11 +235,12 @@ __global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__r
 
 // pre-smoothing from a zero guess: r = b ; d = c0 jac b ; x = d
 __global__ void k_cheb_first_b(const double *__restrict__ jac, const D2 *__restrict__ b, D2 *__restrict__ r,
-                               D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, long n, int m) {
+                               D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, long n, int m,
+                               int nk, int cpk) {
   const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = c0 * jac[t / m];
+    const double s = c0 * jac[(t / m) * nk + (int)(t % m) / cpk];
     const D2 v = b[t];
     const D2 o = make_double2(s * v.x, s * v.y);
     r[t] = v; d[t] = o; x[t] = o;
@@ -243,11 +249,11 @@ __global__ void k_cheb_first_b(const double *__restrict__ jac, const D2 *__restr
 // r -= q ; q = 0 ; d = a d + b jac r ; x += d
 __global__ void k_cheb_step_z(const double *__restrict__ jac, D2 *__restrict__ q, D2 *__restrict__ r,
                               D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, int step, long n,
-                              int m) {
+                              int m, int nk, int cpk) {
   const double a = coef[2 * step - 1], b = coef[2 * step];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = b * jac[t / m];
+    const double s = b * jac[(t / m) * nk + (int)(t % m) / cpk];
     const D2 qq = q[t];
     q[t] = make_double2(0.0, 0.0);
     D2 rr = r[t];
@@ -272,11 +278,11 @@ __global__ void k_resid_z(const D2 *__restrict__ b, D2 *__restrict__ q, D2 *__re
 // post-smoothing start: r = b - q ; q = 0 ; (b = 0) ; d = c0 jac r ; x += d
 __global__ void k_resid_cheb_first(const double *__restrict__ jac, D2 *__restrict__ b, D2 *__restrict__ q,
                                    D2 *__restrict__ r, D2 *__restrict__ d, D2 *__restrict__ x,
-                                   const double *__restrict__ coef, long n, int m, int clear_b) {
+                                   const double *__restrict__ coef, long n, int m, int clear_b, int nk, int cpk) {
   const double c0 = coef[0];
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = c0 * jac[t / m];
+    const double s = c0 * jac[(t / m) * nk + (int)(t % m) / cpk];
     const D2 bb = b[t], qq = q[t];
     q[t] = make_double2(0.0, 0.0);
     if (clear_b) b[t] = make_double2(0.0, 0.0);
@@ -495,7 +501,9 @@ struct H1Multigrid {
   // Chebyshev coefficients are kernel arguments captured by value)
   cudaGraphExec_t gA = nullptr, gB = nullptr;
   const void *g_rhs = nullptr, *g_phi = nullptr;
-  int g_m = 0;
+  int g_m = 0, g_nk = 0;
+  int nodes_A = 0, nodes_B = 0;       // kernels inside each graph (added to the launch counter per graph launch)
+  int nk_built = 0;
   void drop_graphs() {
     if (gA) cudaGraphExecDestroy(gA);
     if (gB) cudaGraphExecDestroy(gB);
@@ -642,13 +650,17 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
       L.eps.upload(L.eps_h, s);
     }
     // kappa-dependent class tables with this level's Jacobians
-    std::vector<double> cp((size_t)mesh.n_class * kClassParDoubles);
-    for (int c = 0; c < mesh.n_class; c++) class_params(&mesh.J[9 * c], h->kappa, &cp[(size_t)c * kClassParDoubles]);
+    const int nk = h->nk;
+    std::vector<double> cp((size_t)nk * mesh.n_class * kClassParDoubles);
+    for (int k = 0; k < nk; k++)
+      for (int c = 0; c < mesh.n_class; c++)
+        class_params(&mesh.J[9 * c], &h->kappas[3 * k], &cp[((size_t)k * mesh.n_class + c) * kClassParDoubles]);
     L.cpar.upload(cp, s);
     ElemData &E = L.E;
     E = h->E;
     E.n_elem = mesh.n_elem;
     E.n_class = mesh.n_class;
+    E.nk = nk;
     E.cpar = L.cpar.p;
     if (l > 0) {
       E.cls = L.cls.p;
@@ -671,63 +683,73 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     if (l == nl - 1) L.cheb40.upload(cheb_coefs(L.lmax, 2000.0, 40), s);
     DevBuf<double> &dl = L.dloc;
     dl.upload(dloc, s);
-    L.diag.alloc(L.N0); L.jac.alloc(L.N0);
-    BLOCH_CUDA(cudaMemsetAsync(L.diag.p, 0, sizeof(double) * L.N0, s));
-    BLOCH_CUDA(launch_scatter_diag(E.map_h1, h->L_h1, E.cls, E.eps, dl.p, E.n_elem, L.diag.p, s));
-    k_jacobi<<<grid_for(L.N0), TPB, 0, s>>>(L.diag.p, L.jac.p, L.N0);
+    L.diag.alloc((size_t)L.N0 * nk); L.jac.alloc((size_t)L.N0 * nk);     // [N0][nk]
+    BLOCH_CUDA(cudaMemsetAsync(L.diag.p, 0, sizeof(double) * L.N0 * nk, s));
+    BLOCH_CUDA(launch_scatter_diag(E.map_h1, h->L_h1, E.cls, E.eps, dl.p, E.n_elem, L.diag.p, s, nk, E.n_class));
+    k_jacobi<<<grid_for(L.N0 * nk), TPB, 0, s>>>(L.diag.p, L.jac.p, L.N0 * nk);
     h_sync(s);
   }
-  // coarsest level: dense inverse from one block apply to the identity
+  // coarsest level: dense inverse per k-point from one block apply to the identity (columns k * n + j = e_j)
   H1Level &C = mg->lev[nl - 1];
   C.dense = C.N0 <= 512;
   if (C.dense) {
-    const int n = (int)C.N0;
-    std::vector<D2> I((size_t)n * n, make_double2(0.0, 0.0));
-    for (int i = 0; i < n; i++) I[(size_t)i * n + i].x = 1.0;
+    const int n = (int)C.N0, nk = h->nk, w = nk * n;
     DevBuf<D2> &dI = C.dI, &dA = C.dA;
-    if (dI.n < (size_t)n * n) dI.upload(I, s);
-    dA.alloc((size_t)n * n);
-    BLOCH_CUDA(cudaMemsetAsync(dA.p, 0, sizeof(D2) * n * n, s));
-    BLOCH_CUDA(launch_h1_op(p, 3, h->tabs, C.E, dI.p, n, dA.p, n, n, s, 1.0, 0.0));
-    std::vector<D2> A((size_t)n * n);
-    BLOCH_CUDA(cudaMemcpyAsync(A.data(), dA.p, sizeof(D2) * n * n, cudaMemcpyDeviceToHost, s));
+    if (dI.n < (size_t)n * w || mg->nk_built != nk) {
+      std::vector<D2> I((size_t)n * w, make_double2(0.0, 0.0));
+      for (int k = 0; k < nk; k++)
+        for (int i = 0; i < n; i++) I[(size_t)i * w + k * n + i].x = 1.0;
+      dI.upload(I, s);
+      h_sync(s);
+    }
+    dA.alloc((size_t)n * w);
+    BLOCH_CUDA(cudaMemsetAsync(dA.p, 0, sizeof(D2) * n * w, s));
+    BLOCH_CUDA(launch_h1_op(p, 3, h->tabs, C.E, dI.p, w, dA.p, w, w, s, 1.0, 0.0));
+    std::vector<D2> A((size_t)n * w);
+    BLOCH_CUDA(cudaMemcpyAsync(A.data(), dA.p, sizeof(D2) * n * w, cudaMemcpyDeviceToHost, s));
     h_sync(s);
-    dense::Mat Am((size_t)n * n);
-    double tr = 0;
-    for (int i = 0; i < n; i++) tr += A[(size_t)i * n + i].x;
-    for (int i = 0; i < n; i++)
-      for (int j = 0; j < n; j++) {
-        const D2 a = A[(size_t)i * n + j], at = A[(size_t)j * n + i];
-        Am[(size_t)i * n + j] = 0.5 * dense::cplx(a.x + at.x, a.y - at.y);
-      }
-    if (h->beta == 0.0)   // singular on constants: lift that single mode
+    std::vector<D2> inv((size_t)nk * n * n);
+    for (int k = 0; k < nk && C.dense; k++) {
+      dense::Mat Am((size_t)n * n);
+      double tr = 0;
+      for (int i = 0; i < n; i++) tr += A[(size_t)i * w + k * n + i].x;
       for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += tr / ((double)n * n);
-    dense::Mat Lc = Am;
-    if (!dense::cholesky(n, Lc, 1e-14)) {
-      C.dense = false;
-    } else {
+        for (int j = 0; j < n; j++) {
+          const D2 a = A[(size_t)i * w + k * n + j], at = A[(size_t)j * w + k * n + i];
+          Am[(size_t)i * n + j] = 0.5 * dense::cplx(a.x + at.x, a.y - at.y);
+        }
+      if (h->betas[k] == 0.0)   // singular on constants: lift that single mode
+        for (int i = 0; i < n; i++)
+          for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += tr / ((double)n * n);
+      dense::Mat Lc = Am;
+      if (!dense::cholesky(n, Lc, 1e-14)) {
+        C.dense = false;
+        break;
+      }
       // inverse = L^-H L^-1: solve for the identity
       dense::Mat X((size_t)n * n, dense::cplx(0));
       for (int c = 0; c < n; c++) {
         std::vector<dense::cplx> y(n, dense::cplx(0));
         for (int i = 0; i < n; i++) {           // L y = e_c
           dense::cplx sacc = (i == c) ? 1.0 : 0.0;
-          for (int k = 0; k < i; k++) sacc -= Lc[(size_t)i * n + k] * y[k];
+          for (int kk = 0; kk < i; kk++) sacc -= Lc[(size_t)i * n + kk] * y[kk];
           y[i] = sacc / Lc[(size_t)i * n + i].real();
         }
         for (int i = n - 1; i >= 0; i--) {      // L^H x = y
           dense::cplx sacc = y[i];
-          for (int k = i + 1; k < n; k++) sacc -= std::conj(Lc[(size_t)k * n + i]) * X[(size_t)k * n + c];
+          for (int kk = i + 1; kk < n; kk++) sacc -= std::conj(Lc[(size_t)kk * n + i]) * X[(size_t)kk * n + c];
           X[(size_t)i * n + c] = sacc / Lc[(size_t)i * n + i].real();
         }
       }
-      std::vector<D2> inv((size_t)n * n);
-      for (size_t i = 0; i < inv.size(); i++) inv[i] = make_double2(X[i].real(), X[i].imag());
+      for (size_t i = 0; i < (size_t)n * n; i++) inv[(size_t)k * n * n + i] = make_double2(X[i].real(), X[i].imag());
+    }
+    if (C.dense) {
       C.inv.upload(inv, s);
       h_sync(s);
     }
   }
+  if (mg->nk_built != h->nk) { mg->drop_graphs(); mg->m_alloc = 0; mg->zero_valid = false; }
+  mg->nk_built = h->nk;
   if (C.dense != was_dense) mg->drop_graphs();   // the coarse solve is a different node list
   h_sync(s);                                      // host-side tables uploaded above are stack temporaries
 }
@@ -736,29 +758,37 @@ static void probe_level(bloch_handle_s *h, const ElemData &Elev, std::vector<dou
                         std::vector<D2> *Sloc) {
   // same probe problem as Setup() (core.cu): one private element per local unit vector; the probe
   // buffers were built there and are reused (no allocation per k-point)
-  const int nc = Elev.n_class, L = h->L_h1;
+  const int nc = Elev.n_class, L = h->L_h1, nk = h->nk;
   cudaStream_t s = h->stream;
   const int ne = nc * L;
   bloch_handle_s::ProbeWork &pw = h->probe_h1;
-  if (!pw.built) throw std::runtime_error("multigrid setup before Setup()");
+  if (!pw.built || pw.built_nk != nk) throw std::runtime_error("multigrid setup before Setup()");
   ElemData E = Elev;
   E.n_elem = ne; E.cls = pw.cls.p; E.eps = pw.one.p; E.muinv = pw.one.p; E.map_h1 = pw.map.p;
-  const size_t xs = (size_t)ne * L;
+  const size_t xs = (size_t)ne * L * nk;
   BLOCH_CUDA(cudaMemsetAsync(pw.y.p, 0, sizeof(D2) * xs, s));
-  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, pw.x.p, 1, pw.y.p, 1, 1, s, 1.0, 0.0));
+  BLOCH_CUDA(launch_h1_op(h->p, 3, h->tabs, E, pw.x.p, nk, pw.y.p, nk, nk, s, 1.0, 0.0));
   std::vector<D2> &y = pw.hy;
   BLOCH_CUDA(cudaMemcpyAsync(y.data(), pw.y.p, sizeof(D2) * xs, cudaMemcpyDeviceToHost, s));
   h_sync(s);
-  dloc.resize((size_t)nc * L);
-  for (int c = 0; c < nc; c++) {
-    for (int k = 0; k < L; k++) dloc[(size_t)c * L + k] = y[((size_t)(c * L + k)) * L + k].x;
-    if (bound) *bound = std::max(*bound, local_scaled_lmax(L, y.data() + (size_t)c * L * L));
-  }
-  if (Sloc) {   // y[(c*L + k)*L + l] = S_c[l][k]  ->  row-major S_c[l][k]
-    Sloc->resize((size_t)nc * L * L);
-    for (int c = 0; c < nc; c++)
-      for (int k = 0; k < L; k++)
-        for (int l = 0; l < L; l++) (*Sloc)[((size_t)c * L + l) * L + k] = y[((size_t)(c * L + k)) * L + l];
+  // y[((c*L + k)*L + l)*nk + kk] = S_{kk,c}[l][k]
+  dloc.resize((size_t)nk * nc * L);
+  std::vector<D2> loc((size_t)L * L);
+  for (int kk = 0; kk < nk; kk++)
+    for (int c = 0; c < nc; c++) {
+      for (int k = 0; k < L; k++) dloc[((size_t)kk * nc + c) * L + k] = y[(((size_t)(c * L + k)) * L + k) * nk + kk].x;
+      if (bound) {
+        for (size_t t = 0; t < (size_t)L * L; t++) loc[t] = y[((size_t)c * L * L + t) * nk + kk];
+        *bound = std::max(*bound, local_scaled_lmax(L, loc.data()));
+      }
+    }
+  if (Sloc) {   // row-major S_{kk,c}[l][k], matrices ordered [kk][c]
+    Sloc->resize((size_t)nk * nc * L * L);
+    for (int kk = 0; kk < nk; kk++)
+      for (int c = 0; c < nc; c++)
+        for (int k = 0; k < L; k++)
+          for (int l = 0; l < L; l++)
+            (*Sloc)[(((size_t)kk * nc + c) * L + l) * L + k] = y[(((size_t)(c * L + k)) * L + l) * nk + kk];
   }
 }
 
@@ -788,11 +818,11 @@ static std::vector<double> cheb_coefs(double lmax, double ratio, int degree) {
 static void chebyshev(bloch_handle_s *h, H1Level &L, D2 *x, int m, int degree, const double *cf, bool accumulate) {
   cudaStream_t s = h->stream;
   const unsigned g = grid_for(L.N0 * m);
-  k_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, L.r.p, L.d.p, x, cf, L.N0, m, accumulate ? 1 : 0);
+  k_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, L.r.p, L.d.p, x, cf, L.N0, m, accumulate ? 1 : 0, h->nk, m / h->nk);
   h->count_launch();
   for (int k = 1; k < degree; k++) {
     level_apply(h, L, L.d.p, L.q.p, m);
-    k_cheb_step<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, cf, k, L.N0, m);
+    k_cheb_step<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, cf, k, L.N0, m, h->nk, m / h->nk);
     h->count_launch();
   }
 }
@@ -805,7 +835,7 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   const long tot = L.N0 * m;
   if (l == nl - 1) {
     if (L.dense) {
-      k_dense_apply<<<grid_for(tot), TPB, 0, s>>>(L.inv.p, L.b.p, L.x.p, (int)L.N0, m);
+      k_dense_apply<<<grid_for(tot), TPB, 0, s>>>(L.inv.p, L.b.p, L.x.p, (int)L.N0, m, m / h->nk);
       h->count_launch();
     } else {
       BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
@@ -867,7 +897,7 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
   const unsigned g = grid_for(tot);
   if (l == nl - 1) {
     if (L.dense) {
-      k_dense_apply<<<g, TPB, 0, s>>>(L.inv.p, b, x, (int)L.N0, m);
+      k_dense_apply<<<g, TPB, 0, s>>>(L.inv.p, b, x, (int)L.N0, m, m / h->nk);
       h->count_launch();
     } else {   // rare: coarsest level too large for a dense inverse
       BLOCH_CUDA(cudaMemcpyAsync(L.r.p, b, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
@@ -882,12 +912,12 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
   auto cheb_tail = [&]() {   // steps 1 .. deg-1 of the Chebyshev recurrence on (r, d, x)
     for (int k = 1; k < deg; k++) {
       apply_nz(h, L, L.d.p, L.q.p, m);
-      k_cheb_step_z<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, L.cheb.p, k, L.N0, m);
+      k_cheb_step_z<<<g, TPB, 0, s>>>(L.jac.p, L.q.p, L.r.p, L.d.p, x, L.cheb.p, k, L.N0, m, h->nk, m / h->nk);
       h->count_launch();
     }
   };
   // pre-smoothing from a zero guess
-  k_cheb_first_b<<<g, TPB, 0, s>>>(L.jac.p, b, L.r.p, L.d.p, x, L.cheb.p, L.N0, m);
+  k_cheb_first_b<<<g, TPB, 0, s>>>(L.jac.p, b, L.r.p, L.d.p, x, L.cheb.p, L.N0, m, h->nk, m / h->nk);
   cheb_tail();
   // residual, restriction (coarse b is zero on entry)
   apply_nz(h, L, x, L.q.p, m);
@@ -912,7 +942,7 @@ static void vcycle_fused(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int d
   }
   // post-smoothing; levels >= 1 clear their right-hand side for the next cycle's restriction
   apply_nz(h, L, x, L.q.p, m);
-  k_resid_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, b, L.q.p, L.r.p, L.d.p, x, L.cheb.p, L.N0, m, l > 0 ? 1 : 0);
+  k_resid_cheb_first<<<g, TPB, 0, s>>>(L.jac.p, b, L.q.p, L.r.p, L.d.p, x, L.cheb.p, L.N0, m, l > 0 ? 1 : 0, h->nk, m / h->nk);
   h->count_launch(2);
   cheb_tail();
 }
@@ -929,7 +959,7 @@ static void ensure_zero_buffers(H1Multigrid *mg, bloch_handle_s *h, int m) {
   mg->zero_m = m;
 }
 
-static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, const double *rel_tol_k, int max_it) {
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
   H1Level &F = mg->lev[0];
@@ -940,10 +970,10 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
   double *part_rz = mg->part.p, *part_pq = part_rz + PCG_BLOCKS * m, *part_rr = part_pq + PCG_BLOCKS * m;
   double *rz_saved = part_rr + PCG_BLOCKS * m;
   double *sums = mg->scal.p + 6 * m;
-  if (h->beta == 0.0) {
+  if (h->any_gamma) {
     BLOCH_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * m, s));
     k_col_sum<<<grid_for(tot), TPB, 0, s>>>(rhs, N0, m, sums);
-    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(rhs, N0, m, sums);
+    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(rhs, N0, m, sums, h->d_gflag.p, m / h->nk);
     h->count_launch(2);
   }
   BLOCH_CUDA(cudaMemsetAsync(phi, 0, sizeof(D2) * tot, s));
@@ -1000,27 +1030,36 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
   auto w0 = std::chrono::steady_clock::now();
   int it = 0;
   for (it = 1; it <= max_it; it++) {
-    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m;
+    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m && mg->g_nk == h->nk;
     if (use_graph && !graphs_ok && it == 2) {
       mg->drop_graphs();
-      if (capture(&mg->gA, half_a) && capture(&mg->gB, half_b)) {
-        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m;
+      const int64_t l0 = h->stats.launches;
+      const bool okA = capture(&mg->gA, half_a);
+      const int64_t l1 = h->stats.launches;
+      const bool okB = okA && capture(&mg->gB, half_b);
+      const int64_t l2 = h->stats.launches;
+      h->stats.launches = l0;                      // captured, not launched: counted per graph launch below
+      if (okA && okB) {
+        mg->nodes_A = (int)(l1 - l0); mg->nodes_B = (int)(l2 - l1);
+        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m; mg->g_nk = h->nk;
         graphs_ok = true;
       } else {
         mg->drop_graphs();
       }
     }
     if (timing) cudaEventRecord(e0, s);
-    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); else half_a();
+    if (graphs_ok) { BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); h->count_launch(mg->nodes_A); } else half_a();
     if (timing) cudaEventRecord(e1, s);
     fetch_rr(rrh);
     if (timing && it > 2) { float ms; cudaEventElapsedTime(&ms, e0, e1); tA += ms; nA++; }
     bool done = true;
-    for (int j = 0; j < m; j++)
+    for (int j = 0; j < m; j++) {
+      const double rel_tol = rel_tol_k[j / (m / h->nk)];
       if (rrh[j] > rel_tol * rel_tol * rr0[j]) done = false;
+    }
     if (done) break;
     if (timing) cudaEventRecord(e1, s);
-    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); else half_b();
+    if (graphs_ok) { BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); h->count_launch(mg->nodes_B); } else half_b();
     if (timing) {
       cudaEventRecord(e2, s);
       cudaEventSynchronize(e2);
@@ -1056,7 +1095,7 @@ void mg_vcycle(H1Multigrid *mg, bloch_handle_s *h, const D2 *b, D2 *x, int m) {
 }
 
 // block PCG on the fine level, one V-cycle as preconditioner; rhs is overwritten by the residual
-int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double rel_tol, int max_it) {
+int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, const double *rel_tol_k, int max_it) {
   // Two schedules of the same iteration.  The fused one (fewer graph nodes, consume-and-clear buffers,
   // atomic-free fine-level apply) wins while the fine level is a few hundred thousand entries and every
   // node sits at its latency floor; once the level vectors outgrow L2 the plain schedule is faster
@@ -1064,7 +1103,8 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
   // crossover at ~0.8 M entries (FCC p2: n_sub 12).
   static const double fused_max = env_double("BLOCH_MG_FUSED_MAX_ENTRIES", 8.0e5);
   static const bool fused = env_double("BLOCH_MG_FUSED", 1.0) != 0.0;
-  if (fused && (double)mg->lev[0].N0 * m <= fused_max) return mg_solve_fused(mg, h, rhs, phi, m, rel_tol, max_it);
+  if (m % h->nk != 0) throw std::invalid_argument("block width must be a multiple of the k-point batch size");
+  if (fused && (double)mg->lev[0].N0 * m <= fused_max) return mg_solve_fused(mg, h, rhs, phi, m, rel_tol_k, max_it);
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
   mg->zero_valid = false;   // this schedule leaves the operator-output buffers dirty
@@ -1075,10 +1115,10 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
   double *rz = mg->scal.p, *pq = rz + m, *rzn = pq + m, *rr = rzn + m, *alpha = rr + m, *beta = alpha + m;
   double *sums = beta + m;
   auto remove_mean = [&](D2 *v) {
-    if (h->beta != 0.0) return;
+    if (!h->any_gamma) return;
     BLOCH_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * m, s));
     k_col_sum<<<grid_for(tot), TPB, 0, s>>>(v, N0, m, sums);
-    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(v, N0, m, sums);
+    k_col_shift<<<grid_for(tot), TPB, 0, s>>>(v, N0, m, sums, h->d_gflag.p, m / h->nk);
     h->count_launch(2);
   };
   auto precond = [&](const D2 *r, D2 *z) {
@@ -1129,25 +1169,34 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, double
   };
   int it = 0;
   for (it = 1; it <= max_it; it++) {
-    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m;
+    bool graphs_ok = use_graph && mg->gA && mg->gB && mg->g_rhs == rhs && mg->g_phi == phi && mg->g_m == m && mg->g_nk == h->nk;
     if (use_graph && !graphs_ok && it == 2) {
       // iteration 1 ran eagerly (kernel attributes set, buffers allocated): capture now
       mg->drop_graphs();
-      if (capture(&mg->gA, half_a) && capture(&mg->gB, half_b)) {
-        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m;
+      const int64_t l0 = h->stats.launches;
+      const bool okA = capture(&mg->gA, half_a);
+      const int64_t l1 = h->stats.launches;
+      const bool okB = okA && capture(&mg->gB, half_b);
+      const int64_t l2 = h->stats.launches;
+      h->stats.launches = l0;                      // captured, not launched: counted per graph launch below
+      if (okA && okB) {
+        mg->nodes_A = (int)(l1 - l0); mg->nodes_B = (int)(l2 - l1);
+        mg->g_rhs = rhs; mg->g_phi = phi; mg->g_m = m; mg->g_nk = h->nk;
         graphs_ok = true;
       } else {
         mg->drop_graphs();
       }
     }
-    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); else half_a();
+    if (graphs_ok) { BLOCH_CUDA(cudaGraphLaunch(mg->gA, s)); h->count_launch(mg->nodes_A); } else half_a();
     BLOCH_CUDA(cudaMemcpyAsync(rrh.data(), rr, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
     h_sync(s);
     bool done = true;
-    for (int j = 0; j < m; j++)
+    for (int j = 0; j < m; j++) {
+      const double rel_tol = rel_tol_k[j / (m / h->nk)];
       if (rrh[j] > rel_tol * rel_tol * rr0[j]) done = false;
+    }
     if (done) break;
-    if (graphs_ok) BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); else half_b();
+    if (graphs_ok) { BLOCH_CUDA(cudaGraphLaunch(mg->gB, s)); h->count_launch(mg->nodes_B); } else half_b();
   }
   return it > max_it ? max_it : it;
 }

@@ -11,8 +11,10 @@ H1Multigrid *mg_create(bloch_handle_s *h);
 void mg_destroy(H1Multigrid *mg);
 // per (kappa, coefficients): class tables, restricted coefficients, Jacobi diagonals, coarse inverse
 void mg_setup(H1Multigrid *mg, bloch_handle_s *h);
-// rhs (N0 x m contiguous) is overwritten by the final residual; returns the PCG iteration count
-int mg_solve(H1Multigrid *mg, bloch_handle_s *h, double2 *rhs, double2 *phi, int m, double rel_tol, int max_it);
+// rhs (N0 x m contiguous) is overwritten by the final residual; returns the PCG iteration count.
+// rel_tol_k: relative residual tolerance per k-point of the handle's batch (host array, h->nk entries; column j of
+// the block belongs to k-point j / (m / nk))
+int mg_solve(H1Multigrid *mg, bloch_handle_s *h, double2 *rhs, double2 *phi, int m, const double *rel_tol_k, int max_it);
 // x = B b: ONE V-cycle (a fixed symmetric positive definite linear operator, spectrally equivalent to S0^-1);
 // b (N0 x m contiguous) is preserved
 void mg_vcycle(H1Multigrid *mg, bloch_handle_s *h, const double2 *b, double2 *x, int m);

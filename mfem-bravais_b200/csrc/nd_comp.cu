@@ -103,7 +103,7 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
   double *sCP = reinterpret_cast<double *>(smem_raw);
   const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-  const int ncp = E.n_class * kClassParDoubles;
+  const int ncp = cpar_doubles(E);
   for (int i = threadIdx.x; i < ncp; i += blockDim.x) sCP[i] = E.cpar[i];
   __syncthreads();
   // lane roles: lane = base(slot) + 2 c + part; spare lanes shadow the lane 6 below them and never write
@@ -135,7 +135,7 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
     const int e = small ? (int)((unsigned)item / (unsigned)m) : (int)(item / m);
     const int v = (int)(item - (long)e * m);
     const int32_t *mp = E.map_nd + (long)e * D::LND + c * NB;
-    const double *cp = sCP + kClassParDoubles * __ldg(E.cls + e);
+    const double *cp = sCP + kClassParDoubles * vclass(E, __ldg(E.cls + e), v);
     // 32-bit offsets in doubles (the launcher checks 2 * n_dofs * ld < 2^32):  (|s| - 1) * 2 ld + 2 v + part
     const unsigned xoff = 2u * (unsigned)v + (unsigned)part - xstep, yoff = 2u * (unsigned)v + (unsigned)part - ystep;
 
@@ -324,7 +324,7 @@ cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
   constexpr int kMaxDev = 64;
   static int sms_of[kMaxDev] = {};
   static size_t cap_of[kMaxDev] = {};
-  const size_t cp_bytes = (size_t)((E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
+  const size_t cp_bytes = (size_t)((E.nk * E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
   const size_t per_warp = (size_t)((HAS_A && !HAS_M) ? (D::NB > D::RB ? D::NB : D::RB) : D::NB + (HAS_A ? D::RB : 0)) * 32 * sizeof(double);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -357,7 +357,7 @@ cudaError_t nd_comp_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
   }
   const size_t smem = cp_bytes + per_warp * nw;
   k_nd_comp<P, HAS_A, HAS_M, NT, IPW><<<(unsigned)blocks, nw * 32, smem, s>>>(
-      comp_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items,
+      comp_tabs(T, P), with_cpk(E, nvec), reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items,
       ca, cm);
   return cudaGetLastError();
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void nd_item_body(const ItemTabs &T, const ElemData &
   double *sCP = reinterpret_cast<double *>(smem_raw);
   const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: no divergent-path code
-  const int ncp = E.n_class * kClassParDoubles;
+  const int ncp = cpar_doubles(E);
   for (int i = threadIdx.x; i < ncp; i += blockDim.x) sCP[i] = E.cpar[i];
   __syncthreads();
   double *col = sCP + ((ncp + 1) & ~1) + (size_t)warp * (D::LND * 32) + lane;   // own column
@@ -131,7 +131,7 @@ __device__ __forceinline__ void nd_item_body(const ItemTabs &T, const ElemData &
     int e, v;
     const bool active = locate(tile, e, v);
     const int32_t *mp = E.map_nd + (long)e * D::LND;
-    const double *cp = sCP + kClassParDoubles * __ldg(E.cls + e);
+    const double *cp = sCP + kClassParDoubles * vclass(E, __ldg(E.cls + e), v);
     const unsigned xoff = 2u * (unsigned)v + (unsigned)part - xstep, yoff = 2u * (unsigned)v + (unsigned)part - ystep;
 
     // ---- signed gather + nodal -> mode in the closed directions, one component at a time ----
@@ -335,7 +335,7 @@ cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
   constexpr int kMaxDev = 64;
   static int sms_of[kMaxDev] = {};
   static size_t cap_of[kMaxDev] = {};
-  const size_t cp_bytes = (size_t)((E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
+  const size_t cp_bytes = (size_t)((E.nk * E.n_class * kClassParDoubles + 1) & ~1) * sizeof(double);
   const size_t per_warp = (size_t)D::LND * 32 * sizeof(double);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -369,7 +369,7 @@ cudaError_t nd_item_t(const Tabs &T, const ElemData &E, const double2 *x, int ld
   }
   const size_t smem = cp_bytes + per_warp * nw;
   kern<<<(unsigned)blocks, nw * 32, smem, s>>>(
-      item_tabs(T, P), E, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca, cm);
+      item_tabs(T, P), with_cpk(E, nvec), reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca, cm);
   return cudaGetLastError();
 }
 

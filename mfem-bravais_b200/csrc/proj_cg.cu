@@ -287,7 +287,8 @@ cudaError_t proj_cg_t(const Tabs &T, const ElemData &E, const double *jac, doubl
   const size_t elem_d2 = (P <= 2) ? (size_t)D::LH1 * NW * 32 : (size_t)(D::LND + D::LH1) * 32;
   const size_t smem = elem_d2 * sizeof(double2) +
                       (size_t)(E.n_class * kClassParDoubles + 2 * m) * sizeof(double);
-  static int max_blocks = 0;
+  static int max_blocks_of[kMaxDevices] = {};
+  int &max_blocks = max_blocks_of[current_device_slot()];
   cudaError_t err;
   if (max_blocks == 0) {
     err = cudaFuncSetAttribute(k_proj_cg<P, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));

@@ -10,10 +10,12 @@
 //     Jacobi-PCG on S0 = G^H M G whose per-column scalars live on the device.
 // On the affine WS meshes (C - iZ)(G - iZ0) = 0 holds exactly, so the projected residual equals
 // the plain residual and the convergence test is || A x - lambda M x ||_2 <= atol like hypre's.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "core.hpp"
 #include "dense.hpp"
@@ -58,18 +60,26 @@ __global__ void k_resid_norm(const D2 *__restrict__ AS, const D2 *__restrict__ M
   for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(rn2 + j, sred[j]);
 }
 
-// Rayleigh-Ritz rotation, in place on the basis arrays (pitch ld = 3m):
-//   P_new = sum_{i>=m} S_i C[i][:],  X_new = sum_{i<m} S_i C[i][:] + P_new
+// Basis layout with nk k-points batched: S = [X | W | P] is ONE array [N][3 * gs], gs = nk * m; each of the three
+// groups holds the m columns of every k-point (column k * m + j), so the X (or W) block of ALL k-points is a
+// contiguous column range - the operator / vector kernels see one block vector of nk * m columns - while the basis
+// of k-point b is the strided set col(b, i) = (i / m) * gs + b * m + i % m, i < 3 m.
+__device__ __forceinline__ int basis_col(int i, int m, int gs, int b) { return (i / m) * gs + b * m + (i % m); }
+
+// Rayleigh-Ritz rotation, in place on the basis arrays (pitch ld = 3 gs), k-point b = blockIdx.y:
+//   P_new = sum_{i>=m} S_i C[i][:],  X_new = sum_{i<m} S_i C[i][:] + P_new        (C = C[b], k x m)
 // A CTA stages RP rows of one array in shared memory (coalesced), then thread (row, column) forms its two
 // sums; CW = 16 or 32 column slots per row (m <= 21), k = number of active basis columns (m, 2m or 3m).
 template <int CW>
 __global__ void __launch_bounds__(256)
-k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k, int m,
-            const D2 *__restrict__ C, long n) {
+k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k, int m, int gs,
+            const D2 *__restrict__ Call, long n) {
   constexpr int RP = 256 / CW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   D2 *sC = reinterpret_cast<D2 *>(smem_raw);     // [k][m]
   D2 *sT = sC + k * m;                           // [RP][k]
+  const int b = blockIdx.y;
+  const D2 *C = Call + (size_t)b * k * m;
   for (int t = threadIdx.x; t < k * m; t += 256) sC[t] = C[t];
   const int rr = threadIdx.x / CW, j = threadIdx.x % CW;
   const long ntiles = (n + RP - 1) / RP;
@@ -80,7 +90,7 @@ k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld
     for (int a = 0; a < 3; a++) {
       D2 *base = (a == 0 ? S : (a == 1 ? AS : MS)) + r0 * ld;
       __syncthreads();
-      for (int t = threadIdx.x; t < nr * k; t += 256) sT[t] = base[(long)(t / k) * ld + t % k];
+      for (int t = threadIdx.x; t < nr * k; t += 256) sT[t] = base[(long)(t / k) * ld + basis_col(t % k, m, gs, b)];
       __syncthreads();
       if (rr < nr && j < m) {
         const D2 *row = sT + rr * k;
@@ -95,20 +105,79 @@ k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld
           pn.x = fma(s.x, c.x, pn.x); pn.x = fma(-s.y, c.y, pn.x);
           pn.y = fma(s.x, c.y, pn.y); pn.y = fma(s.y, c.x, pn.y);
         }
-        D2 *out = base + (long)rr * ld;
+        D2 *out = base + (long)rr * ld + b * m;
         out[j] = make_double2(x.x + pn.x, x.y + pn.y);
-        out[2 * m + j] = pn;
+        out[2 * gs + j] = pn;
       }
     }
   }
 }
 
+// Gram matrices of every k-point's basis: C[b][i][j] = sum_r conj(A[r][col(b,i)]) B[r][col(b,j)], i, j < k (<= 64).
+// Same register tiling as k_gram (kernels.cu): 16 x 16 threads, 4 x 4 outputs each; blockIdx.y = k-point.
+constexpr int GB_ROWS = 16;
+__global__ void __launch_bounds__(256)
+k_gram_basis(const D2 *__restrict__ A, const D2 *__restrict__ B, int ld, int k, int m, int gs, long n,
+             D2 *__restrict__ Call, long rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  D2 *sA = reinterpret_cast<D2 *>(smem_raw);   // [GB_ROWS][64] (zero padded)
+  D2 *sB = sA + GB_ROWS * 64;
+  const int b = blockIdx.y;
+  const long r0 = blockIdx.x * rows_per_cta;
+  const long r1 = min(n, r0 + rows_per_cta);
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  D2 acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[a][c] = make_double2(0.0, 0.0);
+  for (long r = r0; r < r1; r += GB_ROWS) {
+    const int nr = (int)min((long)GB_ROWS, r1 - r);
+    for (int t = threadIdx.x; t < GB_ROWS * 64; t += 256) {
+      const int q = t >> 6, c = t & 63;
+      const bool in = q < nr && c < k;
+      const long off = in ? (r + q) * ld + basis_col(c, m, gs, b) : 0;
+      sA[t] = in ? A[off] : make_double2(0.0, 0.0);
+      sB[t] = in ? B[off] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < GB_ROWS; q++) {
+      D2 x[4], y[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) { x[a] = sA[q * 64 + ti + 16 * a]; y[a] = sB[q * 64 + tj + 16 * a]; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          acc[a][c].x = fma(x[a].x, y[c].x, acc[a][c].x); acc[a][c].x = fma(x[a].y, y[c].y, acc[a][c].x);
+          acc[a][c].y = fma(x[a].x, y[c].y, acc[a][c].y); acc[a][c].y = fma(-x[a].y, y[c].x, acc[a][c].y);
+        }
+    }
+    __syncthreads();
+  }
+  double *Cd = reinterpret_cast<double *>(Call + (size_t)b * k * k);
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int i = ti + 16 * a, j = tj + 16 * c;
+      if (i < k && j < k) {
+        atomicAdd(Cd + 2 * (i * k + j), acc[a][c].x);
+        atomicAdd(Cd + 2 * (i * k + j) + 1, acc[a][c].y);
+      }
+    }
+}
+
+// Jacobi diagonals are [n][nk] (one value per dof and k-point); column j of an m-column block vector belongs to
+// k-point j / cpk, cpk = m / nk.
 // Chebyshev: d = c0 * jac .* r ; x = d
 __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ d,
-                             D2 *__restrict__ x, double c0, long n, int m) {
+                             D2 *__restrict__ x, double c0, long n, int m, int nk, int cpk) {
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = c0 * jac[t / m];
+    const long row = t / m;
+    const double s = c0 * jac[row * nk + (int)(t - row * m) / cpk];
     const D2 v = r[t];
     const D2 o = make_double2(s * v.x, s * v.y);
     d[t] = o;
@@ -117,10 +186,11 @@ __global__ void k_cheb_first(const double *__restrict__ jac, const D2 *__restric
 }
 // r -= q ; d = a*d + b * jac .* r ; x += d
 __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict__ q, D2 *__restrict__ r,
-                            D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m) {
+                            D2 *__restrict__ d, D2 *__restrict__ x, double a, double b, long n, int m, int nk, int cpk) {
   const long total = n * m;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const double s = b * jac[t / m];
+    const long row = t / m;
+    const double s = b * jac[row * nk + (int)(t - row * m) / cpk];
     const D2 qq = q[t];
     D2 rr = r[t];
     rr.x -= qq.x; rr.y -= qq.y;
@@ -135,7 +205,7 @@ __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict
   }
 }
 
-// jac[i] = 1 / (dA[i] + sigma * dM[i])
+// jac[i] = 1 / (dA[i] + sigma * dM[i])   (elementwise over the [n][nk] tables)
 __global__ void k_make_jacobi(const double *dA, const double *dM, double sigma, double *jac, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
     const double d = dA[t] + sigma * dM[t];
@@ -160,12 +230,14 @@ __global__ void k_col_sum(const D2 *__restrict__ X, long n, int m, double *__res
   __syncthreads();
   for (int j = threadIdx.x; j < 2 * m; j += blockDim.x) atomicAdd(sums + j, sred[j]);
 }
-// X[r][j] -= sums[j] / n
-__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums) {
+// X[r][j] -= sums[j] / n for the columns of the k-points flagged in gflag (kappa == 0: S0 singular on constants)
+__global__ void k_col_shift(D2 *__restrict__ X, long n, int m, const double *__restrict__ sums,
+                            const int *__restrict__ gflag, int cpk) {
   const long total = n * m;
   const double inv = 1.0 / (double)n;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const int j = (int)(t % m);
+    if (!gflag[j / cpk]) continue;
     D2 v = X[t];
     v.x -= sums[2 * j] * inv; v.y -= sums[2 * j + 1] * inv;
     X[t] = v;
@@ -183,6 +255,16 @@ __global__ void k_sub_strided(D2 *__restrict__ X, int ld, const D2 *__restrict__
     X[r * ld + j] = x;
   }
 }
+// X[r][j] *= sc[j / cpk]   (per-k-point real factor, e.g. the lift parameter tau)
+__global__ void k_col_scale_k(D2 *__restrict__ X, long n, int m, const double *__restrict__ sc, int cpk) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double f = sc[(int)(t % m) / cpk];
+    D2 v = X[t];
+    v.x *= f; v.y *= f;
+    X[t] = v;
+  }
+}
 
 double env_double(const char *name, double dflt) {
   const char *s = std::getenv(name);
@@ -192,23 +274,66 @@ double env_double(const char *name, double dflt) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// x (n x nvec, pitch ldx) <- x - G S0^-1 G^H M x      (maxwell_bloch.cpp:2280-2290)
+// phase timing (bloch_set_profile): CUDA event pairs on the handle's stream, summed per category at the end of
+// the solve.  Off by default - the events themselves are cheap but the bookkeeping is not free.
 // ------------------------------------------------------------------------------------------
-struct ProjWork {
-  DevBuf<D2> rhs, phi, z, p, q, g;
-  DevBuf<double> scal;
-};
-static ProjWork &proj_work(bloch_handle_s *h) {
-  static thread_local std::vector<std::pair<bloch_handle_s *, ProjWork *>> pool;
-  for (auto &e : pool) if (e.first == h) return *e.second;
-  pool.emplace_back(h, new ProjWork());
-  return *pool.back().second;
+void bloch_handle_s::prof_begin(int cat) {
+  if (!profile) return;
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (prof_pool.size() >= 2) {
+    a = prof_pool.back(); prof_pool.pop_back();
+    b = prof_pool.back(); prof_pool.pop_back();
+  } else {
+    BLOCH_CUDA(cudaEventCreate(&a));
+    BLOCH_CUDA(cudaEventCreate(&b));
+  }
+  BLOCH_CUDA(cudaEventRecord(a, stream));
+  prof_open[cat] = {a, b};
+}
+void bloch_handle_s::prof_end(int cat) {
+  if (!profile || !prof_open[cat].first) return;
+  BLOCH_CUDA(cudaEventRecord(prof_open[cat].second, stream));
+  prof_done[cat].push_back(prof_open[cat]);
+  prof_open[cat] = {nullptr, nullptr};
+}
+void bloch_handle_s::prof_collect() {
+  for (int c = 0; c < 8; c++) {
+    double tot = 0.0;
+    for (auto &pr : prof_done[c]) {
+      float ms = 0.f;
+      cudaEventSynchronize(pr.second);
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) tot += ms;
+      prof_pool.push_back(pr.first);
+      prof_pool.push_back(pr.second);
+    }
+    prof_done[c].clear();
+    if (profile) stats.prof_ms[c] = tot;
+  }
 }
 
-static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_tol, int max_it, int *iters) {
+// ------------------------------------------------------------------------------------------
+// x (n x nvec, pitch ldx) <- x - G S0^-1 G^H M x      (maxwell_bloch.cpp:2280-2290)
+// rel_tol_k: relative tolerance of the inner S0 solve per k-point (host array of h->nk entries)
+// ------------------------------------------------------------------------------------------
+using ProjWork = bloch_handle_s::ProjWork;
+static ProjWork &proj_work(bloch_handle_s *h) { return h->pw; }
+
+static void remove_gamma_means(bloch_handle_s *h, D2 *v, long n, int m, double *scratch /* >= 2 m doubles */) {
+  if (!h->any_gamma) return;
+  cudaStream_t s = h->stream;
+  BLOCH_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * m, s));
+  const unsigned g1 = std::min<unsigned>(grid_for(n * m), 148);
+  k_col_sum<<<g1, TPB, sizeof(double) * 2 * m, s>>>(v, n, m, scratch);
+  k_col_shift<<<grid_for(n * m), TPB, 0, s>>>(v, n, m, scratch, h->d_gflag.p, std::max(1, m / h->nk));
+  h->count_launch(2);
+}
+
+static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, const double *rel_tol_k, int max_it, int *iters) {
   cudaStream_t s = h->stream;
   const long N = h->N, N0 = h->N0;
   const int m = nvec;
+  if (m % h->nk != 0) throw std::invalid_argument("block width must be a multiple of the k-point batch size");
+  h->prof_begin(2);
   ProjWork &w = proj_work(h);
   w.rhs.alloc((size_t)N0 * m); w.phi.alloc((size_t)N0 * m); w.z.alloc((size_t)N0 * m);
   w.p.alloc((size_t)N0 * m); w.q.alloc((size_t)N0 * m); w.g.alloc((size_t)N * m);
@@ -220,42 +345,47 @@ static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_t
   BLOCH_CUDA(launch_h1_op(h->p, 2, h->tabs, h->E, x, ldx, w.rhs.p, m, m, s));
   BLOCH_CUDA(cudaMemsetAsync(w.phi.p, 0, sizeof(D2) * N0 * m, s));
   BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * (8 * m + 2), s));
-  if (h->beta == 0.0) {
+  if (h->any_gamma) {
     // Gamma point: S0 = G^T M G is singular (constants).  The exact right-hand side is orthogonal
     // to the constants; rounding is not, and CG amplifies that component without bound - remove it.
-    const unsigned g1 = std::min<unsigned>(grid_for(N0 * m), 148);
-    k_col_sum<<<g1, TPB, sizeof(double) * 2 * m, s>>>(w.rhs.p, N0, m, w.scal.p);
-    k_col_shift<<<grid_for(N0 * m), TPB, 0, s>>>(w.rhs.p, N0, m, w.scal.p);
+    remove_gamma_means(h, w.rhs.p, N0, m, w.scal.p);
     BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * (8 * m + 2), s));
-    h->count_launch(2);
   }
   if (dbg) { int magic = 12345; BLOCH_CUDA(cudaMemcpyAsync(d_info + 2, &magic, sizeof(int), cudaMemcpyHostToDevice, s)); }
   int mg_its = -1;
   if (h->mg && h->use_mg) {
     // V-cycle preconditioned block PCG (mesh-independent iteration count)
-    mg_its = mg_solve(h->mg, h, w.rhs.p, w.phi.p, m, rel_tol, 200);
+    mg_its = mg_solve(h->mg, h, w.rhs.p, w.phi.p, m, rel_tol_k, 200);
   } else {
+    if (h->nk != 1)
+      throw std::invalid_argument("batched k-points need the multigrid projector (even n_sub, BLOCH_MG != 0)");
     // Jacobi-PCG, the whole block solve in one cooperative launch
     BLOCH_CUDA(launch_proj_cg(h->p, h->tabs, h->E, h->d_jac0.p, w.phi.p, w.rhs.p, w.z.p, w.p.p, w.q.p,
-                              w.scal.p, m, N0, max_it, rel_tol, d_info, s));
+                              w.scal.p, m, N0, max_it, rel_tol_k[0], d_info, s));
   }
   // x -= G phi
   BLOCH_CUDA(launch_h1_op(h->p, 1, h->tabs, h->E, w.phi.p, m, w.g.p, m, m, s));
   k_sub_strided<<<grid_for(N * m), TPB, 0, s>>>(x, ldx, w.g.p, N, m);
   h->count_launch(4);
   int info[2] = {0, 0};
-  BLOCH_CUDA(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, s));
-  h_sync(s);
-  if (mg_its >= 0) info[0] = mg_its;
+  if (mg_its < 0) {
+    BLOCH_CUDA(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, s));
+    h_sync(s);
+  } else {
+    info[0] = mg_its;
+  }
   h->stats.inner_iterations += info[0];
   if (iters) *iters = info[0];
+  h->prof_end(2);
+}
+static void project_ld(bloch_handle_s *h, D2 *x, int ldx, int nvec, double rel_tol, int max_it, int *iters) {
+  std::vector<double> tol(h->nk, rel_tol);
+  project_ld(h, x, ldx, nvec, tol.data(), max_it, iters);
 }
 
 void bloch_handle_s::project(D2 *x, int nvec, double rel_tol, int *iters) {
-  if (d_jac0.n < (size_t)N0) {
-    d_jac0.alloc(N0);
-  }
-  k_make_jacobi<<<grid_for(N0), TPB, 0, stream>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
+  d_jac0.alloc((size_t)N0 * nk);
+  k_make_jacobi<<<grid_for(N0 * nk), TPB, 0, stream>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0 * nk);
   count_launch();
   project_ld(this, x, nvec, nvec, rel_tol, 3000, iters);
 }
@@ -302,12 +432,18 @@ void bloch_handle_s::solve_scalar() {
   lobpcg(prob);
 }
 
+// All nk k-points of the handle are iterated TOGETHER: they share mesh, maps and coefficients, so every kernel of
+// the iteration (operator applies, preconditioner, projector multigrid, Gram, rotation) runs once on block vectors
+// of nk * mb columns; only the class tables, Jacobi diagonals, Ritz values and Rayleigh-Ritz rotations are per
+// k-point.  The eigenproblems stay independent (maxwell_dispersion.cpp:475-531): per-k Gram matrices, per-k
+// Rayleigh-Ritz, per-k convergence; a k-point that has converged is frozen (its W / P columns leave the basis).
 void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   using dense::cplx;
   using dense::Mat;
   cudaStream_t s = stream;
   const long N = prob.n;
   const int nb = prob.nbands;
+  const int K = nk;
   int &block = *prob.blk;
   int &have_vectors = *prob.have;
   bloch_b200::DevBuf<D2> &d_X = *prob.X;
@@ -318,13 +454,15 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   if (3L * mb > N) mb = (int)(N / 3);
   if (nb > mb) throw std::invalid_argument("problem too small for the requested number of bands");
   if (block != mb) { have_vectors = 0; block = mb; }
-  const int ld = 3 * mb;
+  const int gs = K * mb;          // columns of one basis group (X, W or P) over all k-points
+  const int ld = 3 * gs;
   const long Nl = N;
 
   cudaEvent_t ev0, ev1;
   BLOCH_CUDA(cudaEventCreate(&ev0));
   BLOCH_CUDA(cudaEventCreate(&ev1));
   BLOCH_CUDA(cudaEventRecord(ev0, s));
+  prof_begin(0);
   stats.iterations = 0;
   stats.converged = 0;
   stats.inner_iterations = 0;
@@ -337,12 +475,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   const double proj_tol = env_double("BLOCH_PROJ_TOL_FACTOR", 1e-2) * tol;
   const bool warm = env_double("BLOCH_WARM_START", 1.0) != 0.0;
   const int refresh_every = (int)env_double("BLOCH_REFRESH_EVERY", 1.0);
-  const double proj_adapt = env_double("BLOCH_PROJ_ADAPT", 0.0);
   const bool verbose = env_double("BLOCH_VERBOSE", 0.0) != 0.0;
-  d_jac.alloc(Nl);
-  d_jac0.alloc(N0);
-  k_make_jacobi<<<grid_for(Nl), TPB, 0, s>>>(prob.diagA, prob.diagM, sigma, d_jac.p, Nl);
-  if (prob.constrained) k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0);
+  d_jac.alloc((size_t)Nl * K);
+  d_jac0.alloc((size_t)N0 * K);
+  k_make_jacobi<<<grid_for(Nl * K), TPB, 0, s>>>(prob.diagA, prob.diagM, sigma, d_jac.p, Nl * K);
+  if (prob.constrained) k_make_jacobi<<<grid_for(N0 * K), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, d_jac0.p, N0 * K);
   count_launch(2);
 
   // workspace lives in the handle and only grows: cudaMalloc/cudaFree per solve cost random
@@ -351,10 +488,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   DevBuf<D2> &dC = lw.dC, &dGA = lw.dGA, &dGM = lw.dGM;
   DevBuf<double> &dlam = lw.dlam, &drn = lw.drn;
   S.alloc((size_t)Nl * ld); AS.alloc((size_t)Nl * ld); MS.alloc((size_t)Nl * ld);
-  R.alloc((size_t)Nl * mb); Wc.alloc((size_t)Nl * mb); Dd.alloc((size_t)Nl * mb);
-  Tq.alloc((size_t)Nl * mb); Qb.alloc((size_t)Nl * mb);
-  dC.alloc((size_t)ld * mb); dGA.alloc((size_t)ld * ld); dGM.alloc((size_t)ld * ld);
-  dlam.alloc(mb); drn.alloc(mb);
+  R.alloc((size_t)Nl * gs); Wc.alloc((size_t)Nl * gs); Dd.alloc((size_t)Nl * gs);
+  Tq.alloc((size_t)Nl * gs); Qb.alloc((size_t)Nl * gs);
+  const int kmax = 3 * mb;
+  dC.alloc((size_t)K * kmax * mb); dGA.alloc((size_t)K * kmax * kmax); dGM.alloc((size_t)K * kmax * kmax);
+  dlam.alloc(gs); drn.alloc(gs); lw.dtau.alloc(K);
 
   auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
     prob.apply(x, ldx, y, ldy, nvec, ca, cm);
@@ -368,34 +506,33 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   // projection (relative 1e-2, a few PCG iterations) instead of one to 1e-2 * tol (16 iterations) per outer
   // iteration; the price is one V-cycle per lifted operator application.
   // (only with a warm start: tau must sit a modest factor above the wanted bands, and the Ritz values of a
-  // random block say nothing about them)
-  const bool warm_block = warm && !(prob.use_init && n_init > 0) && have_vectors == mb && d_X.n >= (size_t)Nl * mb;
+  // random block say nothing about them).  tau is per k-point; a k-point that is not lifted yet has tau = 0.
+  const bool warm_block = warm && !(prob.use_init && n_init > 0) && have_vectors == mb && d_X.n >= (size_t)Nl * gs;
   const bool lift_allowed = prob.constrained && mg && use_mg && !two_pass && env_double("BLOCH_LIFT", 1.0) != 0.0;
-  bool lift = false;            // switched on right after the initial Rayleigh-Ritz (warm start) or, from a cold
-                                // start, once the exactly projected iteration has settled the Ritz values
+  std::vector<char> lift(K, 0);
+  std::vector<double> tau(K, 0.0);
+  bool any_lift = false;
   const double lift_factor = env_double("BLOCH_LIFT_TAU", 8.0);
   const double lift_ptol = env_double("BLOCH_LIFT_PROJ_TOL", 1e-1);
   const double lift_xtol = env_double("BLOCH_LIFT_X_TOL", 1e-1);
-  double tau = 0.0;
-  if (lift_allowed) { lw.Lu.alloc((size_t)N0 * mb); lw.Lphi.alloc((size_t)N0 * mb); lw.Lg.alloc((size_t)Nl * mb); }
-  auto opA = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec) {   // y = A_tau x
+  if (lift_allowed) { lw.Lu.alloc((size_t)N0 * gs); lw.Lphi.alloc((size_t)N0 * gs); lw.Lg.alloc((size_t)Nl * gs); }
+  auto opA = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec) {   // y = A_tau x   (nvec = gs)
     op(x, ldx, y, ldy, nvec, 1.0, 0.0);
-    if (!lift || tau <= 0.0) return;
+    if (!any_lift) return;
+    prof_begin(6);
     BLOCH_CUDA(cudaMemsetAsync(lw.Lu.p, 0, sizeof(D2) * N0 * nvec, s));
     BLOCH_CUDA(launch_h1_op(p, 2, tabs, E, x, ldx, lw.Lu.p, nvec, nvec, s));           // u = G^H M x
-    if (beta == 0.0) {   // S0 singular on constants at Gamma: u is orthogonal to them up to rounding
+    if (any_gamma) {   // S0 singular on constants at Gamma: u is orthogonal to them up to rounding
       ProjWork &w = proj_work(this);
       w.scal.alloc(8 * nvec + 2);
-      BLOCH_CUDA(cudaMemsetAsync(w.scal.p, 0, sizeof(double) * 2 * nvec, s));
-      const unsigned g1 = std::min<unsigned>(grid_for(N0 * nvec), 148);
-      k_col_sum<<<g1, TPB, sizeof(double) * 2 * nvec, s>>>(lw.Lu.p, N0, nvec, w.scal.p);
-      k_col_shift<<<grid_for(N0 * nvec), TPB, 0, s>>>(lw.Lu.p, N0, nvec, w.scal.p);
-      count_launch(2);
+      remove_gamma_means(this, lw.Lu.p, N0, nvec, w.scal.p);
     }
     mg_vcycle(mg, this, lw.Lu.p, lw.Lphi.p, nvec);                                      // phi = B u
+    k_col_scale_k<<<grid_for(N0 * nvec), TPB, 0, s>>>(lw.Lphi.p, N0, nvec, lw.dtau.p, nvec / K);   // phi *= tau_k
     BLOCH_CUDA(launch_h1_op(p, 1, tabs, E, lw.Lphi.p, nvec, lw.Lg.p, nvec, nvec, s));  // g = G phi
-    BLOCH_CUDA(launch_nd_apply(p, tabs, E, lw.Lg.p, nvec, y, ldy, nvec, 0.0, tau, s));  // y += tau M g
-    count_launch(3);
+    BLOCH_CUDA(launch_nd_apply(p, tabs, E, lw.Lg.p, nvec, y, ldy, nvec, 0.0, 1.0, s));  // y += M g
+    count_launch(4);
+    prof_end(6);
   };
 
   // lambda_max(D^-1 (A + sigma M)) <= max over element classes of the local scaled spectra
@@ -404,65 +541,64 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   // operator UNDER-estimates the clustered top of the spectrum and makes the Chebyshev
   // preconditioner indefinite.
   lmaxA = env_double("BLOCH_LMAX_SCALE", 1.05) * lmax_local;
-  if (verbose) std::printf("[lobpcg] lambda_max bound %.4f sigma %.3f cheb degree %d ratio %.0f\n", lmaxA, sigma, cheb_degree, cheb_ratio);
+  if (verbose) std::printf("[lobpcg] lambda_max bound %.4f sigma %.3f cheb degree %d ratio %.0f, %d k-point(s)\n", lmaxA, sigma, cheb_degree, cheb_ratio, K);
   const double lmax = lmaxA, lmin = lmaxA / cheb_ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
 
-  // out = T r_in (both contiguous N x mb, r_in preserved): Chebyshev iteration on A + sigma M
+  // out = T r_in (both contiguous N x gs, r_in preserved): Chebyshev iteration on A + sigma M
   auto precondition = [&](const D2 *r_in, D2 *out) {
-    BLOCH_CUDA(cudaMemcpyAsync(Tq.p, r_in, sizeof(D2) * Nl * mb, cudaMemcpyDeviceToDevice, s));
-    const unsigned g = grid_for(Nl * mb);
-    k_cheb_first<<<g, TPB, 0, s>>>(d_jac.p, Tq.p, Dd.p, out, 1.0 / theta, Nl, mb);
+    prof_begin(3);
+    prof_in_precond = true;
+    BLOCH_CUDA(cudaMemcpyAsync(Tq.p, r_in, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
+    const unsigned g = grid_for(Nl * gs);
+    k_cheb_first<<<g, TPB, 0, s>>>(d_jac.p, Tq.p, Dd.p, out, 1.0 / theta, Nl, gs, K, mb);
     count_launch();
     double rho = 1.0 / sigma1;
     for (int k = 1; k < cheb_degree; k++) {
-      op(Dd.p, mb, Qb.p, mb, mb, 1.0, sigma);
+      op(Dd.p, gs, Qb.p, gs, gs, 1.0, sigma);
       const double rho_n = 1.0 / (2.0 * sigma1 - rho);
-      k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / delta, Nl, mb);
+      k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / delta, Nl, gs, K, mb);
       count_launch();
       rho = rho_n;
     }
+    prof_in_precond = false;
+    prof_end(3);
   };
 
-  // Rayleigh-Ritz on the first k basis columns; returns false if the Gram matrix is not PD
-  std::vector<D2> hGA((size_t)ld * ld), hGM((size_t)ld * ld);
-  std::vector<double> lam(mb, 0.0), rn(mb, 0.0);
-  std::vector<char> active(mb, 1);
-  bool need_refresh = false;
-  auto rayleigh_ritz = [&](int k) -> bool {
-    BLOCH_CUDA(launch_gram(S.p, k, ld, AS.p, k, ld, Nl, dGA.p, s));
-    BLOCH_CUDA(launch_gram(S.p, k, ld, MS.p, k, ld, Nl, dGM.p, s));
-    count_launch(2);
-    BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
-    BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * k * k, cudaMemcpyDeviceToHost, s));
-    h_sync(s);
+  // ---- Rayleigh-Ritz of every k-point on its first kc basis columns ----
+  std::vector<D2> hGA((size_t)K * kmax * kmax), hGM((size_t)K * kmax * kmax), hC((size_t)K * kmax * mb);
+  std::vector<double> lam((size_t)gs, 0.0), rn((size_t)gs, 0.0);
+  std::vector<char> active((size_t)gs, 1);          // column still iterating (soft locking)
+  std::vector<char> use_p(K, 0), frozen(K, 0), refresh_k(K, 0);
+  double t_host_rr = 0.0;
+  // one k-point: false if even the X block alone is not positive definite
+  auto rr_one = [&](int b, int kc, bool &dropped) -> bool {
+    const D2 *gA = hGA.data() + (size_t)b * kc * kc, *gM = hGM.data() + (size_t)b * kc * kc;
     // basis columns that take part: all of X; W_j / P_j only for unconverged j (soft locking) and
     // only if they are not numerically zero (X is M-orthonormal, so diag(GM) of X is ~1)
     std::vector<int> keep;
-    for (int i = 0; i < k; i++) {
-      const int j = i % mb;
-      const bool is_x = i < mb;
-      const double dii = hGM[i * k + i].x;
-      if (is_x || (active[j] && dii > 1e-26)) keep.push_back(i);
+    for (int i = 0; i < kc; i++) {
+      const int j = i % mb, grp = i / mb;
+      const double dii = gM[i * kc + i].x;
+      if (grp == 0 || (active[(size_t)b * mb + j] && dii > 1e-26 && !(grp == 2 && !use_p[b]))) keep.push_back(i);
     }
     int kk = (int)keep.size();
-    bool dropped = false;
     std::vector<double> l;
     Mat C;
     bool ok = false;
     while (!ok) {
       Mat GA((size_t)kk * kk), GM((size_t)kk * kk), Cs;
       for (int a = 0; a < kk; a++)
-        for (int b = 0; b < kk; b++) {
+        for (int c = 0; c < kk; c++) {
           // Hermitian part (the two triangles are computed independently on the device)
-          const int i = keep[a], j = keep[b];
-          const D2 x = hGA[i * k + j], xt = hGA[j * k + i], y = hGM[i * k + j], yt = hGM[j * k + i];
-          GA[a * kk + b] = 0.5 * cplx(x.x + xt.x, x.y - xt.y);
-          GM[a * kk + b] = 0.5 * cplx(y.x + yt.x, y.y - yt.y);
+          const int i = keep[a], j = keep[c];
+          const D2 x = gA[i * kc + j], xt = gA[j * kc + i], y = gM[i * kc + j], yt = gM[j * kc + i];
+          GA[a * kk + c] = 0.5 * cplx(x.x + xt.x, x.y - xt.y);
+          GM[a * kk + c] = 0.5 * cplx(y.x + yt.x, y.y - yt.y);
         }
       ok = dense::hegv_lowest(kk, mb, GA, GM, l, Cs);
       if (ok) {
-        C.assign((size_t)k * mb, cplx(0));
+        C.assign((size_t)kc * mb, cplx(0));
         for (int a = 0; a < kk; a++)
           for (int j = 0; j < mb; j++) C[(size_t)keep[a] * mb + j] = Cs[(size_t)a * mb + j];
       } else {
@@ -479,26 +615,65 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
         dropped = true;
       }
     }
-    std::vector<D2> hC((size_t)k * mb);
-    for (size_t i = 0; i < hC.size(); i++) hC[i] = make_double2(C[i].real(), C[i].imag());
-    lam = l;
-    BLOCH_CUDA(cudaMemcpyAsync(dC.p, hC.data(), sizeof(D2) * hC.size(), cudaMemcpyHostToDevice, s));
-    BLOCH_CUDA(cudaMemcpyAsync(dlam.p, lam.data(), sizeof(double) * mb, cudaMemcpyHostToDevice, s));
-    if (mb <= 16) {
-      const unsigned g = (unsigned)std::min<long>((Nl + 15) / 16, 148L * 4);
-      k_rr_update<16><<<g, 256, sizeof(D2) * (k * mb + 16 * k), s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+    D2 *hc = hC.data() + (size_t)b * kc * mb;
+    for (size_t i = 0; i < (size_t)kc * mb; i++) hc[i] = make_double2(C[i].real(), C[i].imag());
+    for (int j = 0; j < mb; j++) lam[(size_t)b * mb + j] = l[j];
+    return true;
+  };
+  auto rayleigh_ritz = [&](int kc) {
+    prof_begin(4);
+    BLOCH_CUDA(cudaMemsetAsync(dGA.p, 0, sizeof(D2) * K * kc * kc, s));
+    BLOCH_CUDA(cudaMemsetAsync(dGM.p, 0, sizeof(D2) * K * kc * kc, s));
+    long ctas = std::max(1L, 148L * 2 / K);
+    long rows = (Nl + ctas - 1) / ctas;
+    rows = ((rows + GB_ROWS - 1) / GB_ROWS) * GB_ROWS;
+    ctas = (Nl + rows - 1) / rows;
+    const size_t gsm = (size_t)GB_ROWS * 128 * sizeof(D2);
+    k_gram_basis<<<dim3((unsigned)ctas, K), 256, gsm, s>>>(S.p, AS.p, ld, kc, mb, gs, Nl, dGA.p, rows);
+    k_gram_basis<<<dim3((unsigned)ctas, K), 256, gsm, s>>>(S.p, MS.p, ld, kc, mb, gs, Nl, dGM.p, rows);
+    count_launch(2);
+    prof_end(4);
+    auto th0 = std::chrono::steady_clock::now();
+    BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
+    h_sync(s);
+    // the K dense problems are independent: spread them over host threads when there are several
+    std::vector<char> okk(K, 1), dropped(K, 0);
+    auto work = [&](int b0, int b1) {
+      for (int b = b0; b < b1; b++) { bool d = false; okk[b] = rr_one(b, kc, d) ? 1 : 0; dropped[b] = d ? 1 : 0; }
+    };
+    static const int rr_threads = std::max(1, (int)env_double("BLOCH_RR_THREADS", 4.0));
+    const int nt = std::min(K, rr_threads);
+    if (nt <= 1) {
+      work(0, K);
     } else {
-      const unsigned g = (unsigned)std::min<long>((Nl + 7) / 8, 148L * 4);
-      k_rr_update<32><<<g, 256, sizeof(D2) * (k * mb + 8 * k), s>>>(S.p, AS.p, MS.p, ld, k, mb, dC.p, Nl);
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++) th.emplace_back(work, (int)((long)K * t / nt), (int)((long)K * (t + 1) / nt));
+      for (auto &t : th) t.join();
+    }
+    for (int b = 0; b < K; b++) {
+      if (!okk[b]) throw std::runtime_error("Rayleigh-Ritz failed (basis numerically rank deficient)");
+      if (dropped[b]) refresh_k[b] = 1;
+    }
+    BLOCH_CUDA(cudaMemcpyAsync(dC.p, hC.data(), sizeof(D2) * K * kc * mb, cudaMemcpyHostToDevice, s));
+    BLOCH_CUDA(cudaMemcpyAsync(dlam.p, lam.data(), sizeof(double) * gs, cudaMemcpyHostToDevice, s));
+    t_host_rr += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count();
+    prof_begin(4);
+    if (mb <= 16) {
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 4 / K));
+      k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 16 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+    } else {
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 4 / K));
+      k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 8 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
     }
     count_launch();
-    h_sync(s);   // hC / lam are stack-lifetime host buffers
-    if (dropped) need_refresh = true;
-    return true;
+    prof_end(4);
+    h_sync(s);   // hC / lam are reused by the next call
   };
 
   // ---- initial block ----
   if (prob.use_init && n_init > 0) {
+    if (K != 1) throw std::invalid_argument("user initial vectors are supported for single-kappa solves only");
     const int mi = std::min(n_init, mb);
     DevBuf<double> tmp;
     tmp.alloc((size_t)2 * Nl * mi);
@@ -508,33 +683,44 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     BLOCH_CUDA(cudaMemcpy2DAsync(Wc.p, sizeof(D2) * mb, Dd.p, sizeof(D2) * mi, sizeof(D2) * mi, Nl, cudaMemcpyDeviceToDevice, s));
     h_sync(s);
     count_launch(2);
-  } else if (warm && have_vectors == mb && d_X.n >= (size_t)Nl * mb) {
-    BLOCH_CUDA(cudaMemcpyAsync(Wc.p, d_X.p, sizeof(D2) * Nl * mb, cudaMemcpyDeviceToDevice, s));
+  } else if (warm_block) {
+    BLOCH_CUDA(cudaMemcpyAsync(Wc.p, d_X.p, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
   } else {
-    BLOCH_CUDA(launch_fill_random(Wc.p, Nl * mb, 0xB10C4ULL, s));
+    BLOCH_CUDA(launch_fill_random(Wc.p, Nl * gs, 0xB10C4ULL, s));
     count_launch();
   }
   {
     int its = 0;
-    if (prob.constrained) project_ld(this, Wc.p, mb, mb, std::min(proj_tol, 1e-10), 3000, &its);
-    BLOCH_CUDA(cudaMemcpy2DAsync(S.p, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
-    op(S.p, ld, AS.p, ld, mb, 1.0, 0.0);    // X is divergence-free to 1e-10 here: A_tau X = A X
-    op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
-    if (!rayleigh_ritz(mb)) throw std::runtime_error("initial block is rank deficient");
+    if (prob.constrained) project_ld(this, Wc.p, gs, gs, std::min(proj_tol, 1e-10), 3000, &its);
+    BLOCH_CUDA(cudaMemcpy2DAsync(S.p, sizeof(D2) * ld, Wc.p, sizeof(D2) * gs, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
+    op(S.p, ld, AS.p, ld, gs, 1.0, 0.0);    // X is divergence-free to 1e-10 here: A_tau X = A X
+    op(S.p, ld, MS.p, ld, gs, 0.0, 1.0);
+    try {
+      rayleigh_ritz(mb);
+    } catch (const std::runtime_error &) {
+      throw std::runtime_error("initial block is rank deficient");
+    }
+    std::fill(refresh_k.begin(), refresh_k.end(), 0);
   }
-  double top_prev = 0.0;
-  auto top_ritz = [&]() {
+  std::vector<double> top_prev(K, 0.0);
+  auto top_ritz = [&](int b) {
     double top = 0.0;
-    for (int j = 0; j < mb; j++) top = std::max(top, std::fabs(lam[j]));
+    for (int j = 0; j < mb; j++) top = std::max(top, std::fabs(lam[(size_t)b * mb + j]));
     return top;
   };
-  auto enable_lift = [&]() {   // X (and P) are exactly projected at this point: A_tau = A on them
-    lift = true;
-    tau = lift_factor * std::max(top_ritz(), 1e-3 / vol23);
-    if (verbose) std::printf("[lobpcg] gradient lift on, tau = %.4g (%.1f x top Ritz value)\n", tau, lift_factor);
+  auto enable_lift = [&](int b) {   // X (and P) of k-point b are exactly projected at this point: A_tau = A on them
+    lift[b] = 1;
+    any_lift = true;
+    tau[b] = lift_factor * std::max(top_ritz(b), 1e-3 / vol23);
+    BLOCH_CUDA(cudaMemcpyAsync(lw.dtau.p, tau.data(), sizeof(double) * K, cudaMemcpyHostToDevice, s));
+    h_sync(s);
+    if (verbose) std::printf("[lobpcg] k %d: gradient lift on, tau = %.4g (%.1f x top Ritz value)\n", b, tau[b], lift_factor);
   };
-  if (lift_allowed && warm_block) enable_lift();
-  top_prev = top_ritz();
+  BLOCH_CUDA(cudaMemsetAsync(lw.dtau.p, 0, sizeof(double) * K, s));
+  for (int b = 0; b < K; b++) {
+    if (lift_allowed && warm_block) enable_lift(b);
+    top_prev[b] = top_ritz(b);
+  }
 
   double t_pre = 0, t_proj = 0, t_op = 0, t_rr = 0, t_res = 0;
   auto tick = [&]() {
@@ -546,31 +732,46 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
   bool have_P = false;
-  int it = 0, nconv = 0;
-  double maxres = 0;
+  int it = 0;
+  std::vector<int> nconv(K, 0), its_k(K, 0);
+  std::vector<double> maxres(K, 0.0);
+  std::vector<double> ptol(K, proj_tol), xtol(K, 1e30);
   for (it = 0; it < max_iter; it++) {
     // residuals and their norms
     auto t0 = tick();
-    BLOCH_CUDA(cudaMemsetAsync(drn.p, 0, sizeof(double) * mb, s));
-    k_resid_norm<<<grid_for(Nl * mb), TPB, sizeof(double) * mb, s>>>(AS.p, MS.p, ld, dlam.p, R.p, Nl, mb, drn.p);
+    BLOCH_CUDA(cudaMemsetAsync(drn.p, 0, sizeof(double) * gs, s));
+    k_resid_norm<<<grid_for(Nl * gs), TPB, sizeof(double) * gs, s>>>(AS.p, MS.p, ld, dlam.p, R.p, Nl, gs, drn.p);
     count_launch();
-    BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * mb, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * gs, cudaMemcpyDeviceToHost, s));
     h_sync(s);
     t_res += since(t0);
-    for (int j = 0; j < mb; j++) active[j] = std::sqrt(rn[j]) > 0.1 * tol;
-    nconv = 0;
-    maxres = 0;
-    for (int j = 0; j < nb; j++) {
-      const double r = std::sqrt(rn[j]);
-      maxres = std::max(maxres, r);
-      if (r <= tol) nconv++;
+    bool all_done = true;
+    for (int b = 0; b < K; b++) {
+      if (frozen[b]) continue;
+      nconv[b] = 0;
+      maxres[b] = 0;
+      for (int j = 0; j < mb; j++) active[(size_t)b * mb + j] = std::sqrt(rn[(size_t)b * mb + j]) > 0.1 * tol;
+      for (int j = 0; j < nb; j++) {
+        const double r = std::sqrt(rn[(size_t)b * mb + j]);
+        maxres[b] = std::max(maxres[b], r);
+        if (r <= tol) nconv[b]++;
+      }
+      its_k[b] = it;
+      if (nconv[b] == nb) {   // this k-point is done: freeze it (its W / P columns leave the basis)
+        frozen[b] = 1;
+        for (int j = 0; j < mb; j++) active[(size_t)b * mb + j] = 0;
+      } else {
+        all_done = false;
+      }
     }
     if (verbose) {
-      std::printf("[lobpcg] it %3d conv %2d maxres %.3e lam:", it, nconv, maxres);
-      for (int j = 0; j < std::min(nb, 6); j++) std::printf(" %.8f", lam[j]);
-      std::printf("\n");
+      for (int b = 0; b < K; b++) {
+        std::printf("[lobpcg] it %3d k %d conv %2d maxres %.3e lam:", it, b, nconv[b], maxres[b]);
+        for (int j = 0; j < std::min(nb, 6); j++) std::printf(" %.8f", lam[(size_t)b * mb + j]);
+        std::printf("\n");
+      }
     }
-    if (nconv == nb) break;
+    if (all_done) break;
     // W = P_proj T R
     t0 = tick();
     precondition(R.p, Wc.p);
@@ -579,38 +780,41 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     int its = 0;
     // inexact inner solves: the gradient content left in W only has to stay well below the
     // current eigen-residual level (it enters X scaled by the size of the update)
-    double ptol = lift ? lift_ptol : proj_tol;
-    if (!lift && proj_adapt > 0.0) {
-      const double scale = std::max(1.0, std::fabs(lam[nb - 1]));
-      ptol = std::min(1e-4, std::max(proj_tol, proj_adapt * maxres / scale));
+    for (int b = 0; b < K; b++) {
+      ptol[b] = frozen[b] ? 1e30 : (lift[b] ? lift_ptol : proj_tol);
+      xtol[b] = (lift[b] && !frozen[b]) ? lift_xtol : 1e30;
     }
-    if (prob.constrained) project_ld(this, Wc.p, mb, mb, ptol, 3000, &its);
+    if (prob.constrained) project_ld(this, Wc.p, gs, gs, ptol.data(), 3000, &its);
     t_proj += since(t0);
     t0 = tick();
-    BLOCH_CUDA(cudaMemcpy2DAsync(S.p + mb, sizeof(D2) * ld, Wc.p, sizeof(D2) * mb, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
-    opA(S.p + mb, ld, AS.p + mb, ld, mb);
-    op(S.p + mb, ld, MS.p + mb, ld, mb, 0.0, 1.0);
+    BLOCH_CUDA(cudaMemcpy2DAsync(S.p + gs, sizeof(D2) * ld, Wc.p, sizeof(D2) * gs, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
+    opA(S.p + gs, ld, AS.p + gs, ld, gs);
+    op(S.p + gs, ld, MS.p + gs, ld, gs, 0.0, 1.0);
     t_op += since(t0);
     t0 = tick();
-    bool ok = rayleigh_ritz(have_P ? 3 * mb : 2 * mb);
-    if (!ok && have_P) ok = rayleigh_ritz(2 * mb);   // restart without P
-    if (!ok) throw std::runtime_error("Rayleigh-Ritz failed (basis numerically rank deficient)");
+    rayleigh_ritz(have_P ? 3 * mb : 2 * mb);
     have_P = true;
-    if (need_refresh || refresh_every <= 1 || (it % refresh_every) == refresh_every - 1) {
-      // recompute A X and M X from X instead of carrying them by recurrence; after a degenerate
-      // Rayleigh-Ritz the search direction block is discarded as well
+    bool any_refresh = false;
+    for (int b = 0; b < K; b++) {
+      use_p[b] = refresh_k[b] ? 0 : 1;       // after a degenerate Rayleigh-Ritz the search directions are discarded
+      any_refresh = any_refresh || refresh_k[b];
+      refresh_k[b] = 0;
+    }
+    if (any_refresh || refresh_every <= 1 || (it % refresh_every) == refresh_every - 1) {
+      // recompute A X and M X from X instead of carrying them by recurrence
       // lifted mode: the gradient content X picked up from the roughly projected W / P is removed here
       // (relative to its own small size), before A_tau X and M X are rebuilt from X
-      if (lift) { int its2 = 0; project_ld(this, S.p, ld, mb, lift_xtol, 3000, &its2); }
-      opA(S.p, ld, AS.p, ld, mb);
-      op(S.p, ld, MS.p, ld, mb, 0.0, 1.0);
-      if (need_refresh) have_P = false;
-      need_refresh = false;
+      if (any_lift) { int its2 = 0; project_ld(this, S.p, ld, gs, xtol.data(), 3000, &its2); }
+      opA(S.p, ld, AS.p, ld, gs);
+      op(S.p, ld, MS.p, ld, gs, 0.0, 1.0);
     }
-    if (lift_allowed && !lift) {
-      const double top = top_ritz();
-      if (it >= 1 && std::fabs(top - top_prev) <= 0.1 * top) enable_lift();
-      top_prev = top;
+    if (lift_allowed) {
+      for (int b = 0; b < K; b++) {
+        if (lift[b] || frozen[b]) continue;
+        const double top = top_ritz(b);
+        if (it >= 1 && std::fabs(top - top_prev[b]) <= 0.1 * top) enable_lift(b);
+        top_prev[b] = top;
+      }
     }
     t_rr += since(t0);
   }
@@ -618,12 +822,18 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     std::printf("[lobpcg] %d its; ms: precond %.2f project %.2f (%d cg its) AW/MW %.2f RR %.2f resid %.2f\n", it, t_pre,
                 t_proj, stats.inner_iterations, t_op, t_rr, t_res);
   stats.iterations = it;
-  stats.converged = nconv;
-  stats.max_residual = maxres;
-  eigenvalues.assign(lam.begin(), lam.begin() + nb);
-  d_X.alloc((size_t)Nl * mb);
-  BLOCH_CUDA(cudaMemcpy2DAsync(d_X.p, sizeof(D2) * mb, S.p, sizeof(D2) * ld, sizeof(D2) * mb, Nl, cudaMemcpyDeviceToDevice, s));
+  stats.k_iterations = its_k;
+  stats.k_converged = nconv;
+  stats.k_max_residual = maxres;
+  stats.converged = *std::min_element(nconv.begin(), nconv.end());
+  stats.max_residual = *std::max_element(maxres.begin(), maxres.end());
+  eigenvalues.assign((size_t)K * nb, 0.0);
+  for (int b = 0; b < K; b++)
+    for (int j = 0; j < nb; j++) eigenvalues[(size_t)b * nb + j] = lam[(size_t)b * mb + j];
+  d_X.alloc((size_t)Nl * gs);
+  BLOCH_CUDA(cudaMemcpy2DAsync(d_X.p, sizeof(D2) * gs, S.p, sizeof(D2) * ld, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
   have_vectors = mb;
+  prof_end(0);
   BLOCH_CUDA(cudaEventRecord(ev1, s));
   BLOCH_CUDA(cudaEventSynchronize(ev1));
   float ms = 0;
@@ -631,6 +841,8 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   stats.seconds = 1e-3 * ms;
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  prof_collect();
+  if (profile) stats.prof_ms[5] = t_host_rr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -642,6 +854,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
 // ------------------------------------------------------------------------------------------
 void bloch_handle_s::rb_append() {
   if (have_vectors <= 0) throw std::invalid_argument("no eigenvectors to append (call bloch_solve first)");
+  if (nk != 1) throw std::invalid_argument("the reduced-basis sweep works on single-kappa handles");
   const int nb = nbands;
   if (rb_size + nb > rb_cap) {
     const int ncap = std::max(2 * rb_cap, rb_size + nb + 64);
@@ -677,7 +890,7 @@ void bloch_handle_s::rb_approx(double *lambda, int n) {
     std::printf("[rb] %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
     t0 = t1;
   };
-  k_make_jacobi<<<grid_for(N0), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, (d_jac0.alloc(N0), d_jac0.p), N0);
+  k_make_jacobi<<<grid_for(N0 * nk), TPB, 0, s>>>(d_diagS0.p, d_diagS0.p, 0.0, (d_jac0.alloc((size_t)N0 * nk), d_jac0.p), N0 * nk);
   d_rb_p.alloc((size_t)N * K); d_rb_ap.alloc((size_t)N * K); d_rb_mp.alloc((size_t)N * K);
   static const int CH = std::getenv("BLOCH_RB_CHUNK") ? std::max(1, std::atoi(std::getenv("BLOCH_RB_CHUNK"))) : 64;
   d_rb_tmp.alloc((size_t)N * CH);

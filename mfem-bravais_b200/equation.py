@@ -175,6 +175,43 @@ class MaxwellBlochWaveEquation:
         k = np.ascontiguousarray(kappa, float)
         check(self._L.bloch_set_kappa(self._h, dptr(k)), "bloch_set_kappa")
 
+    # ---- k-point batch: several Bloch vectors iterated together (independent eigenproblems, one set of kernel
+    # launches; the k-loop of maxwell_dispersion.cpp:475-531 taken nk points at a time) ----
+    def SetKappaBatch(self, kappas):
+        k = np.ascontiguousarray(kappas, float).reshape(-1, 3)
+        check(self._L.bloch_set_kappa_batch(self._h, k.shape[0], dptr(k)), "bloch_set_kappa_batch")
+
+    def BatchSize(self):
+        return int(self._L.bloch_batch_size(self._h))
+
+    def SelectKPoint(self, k):
+        """the getters (band_eigenvalues, GetEigenvector*, GetSolverStats, GetFieldAverages) refer to k-point k"""
+        check(self._L.bloch_select_kpoint(self._h, int(k)), "bloch_select_kpoint")
+
+    def SolveBatch(self, kappas):
+        """SetKappaBatch + Setup + Solve; returns (eigenvalues[nk, n_bands], stats per k-point)"""
+        self.SetKappaBatch(kappas)
+        self.Setup()
+        self.Solve()
+        lam, stats = [], []
+        for k in range(self.BatchSize()):
+            self.SelectKPoint(k)
+            lam.append(self.band_eigenvalues())
+            stats.append(self.GetSolverStats())
+        self.SelectKPoint(0)
+        return np.array(lam), stats
+
+    def SetProfile(self, on):
+        check(self._L.bloch_set_profile(self._h, 1 if on else 0))
+
+    def GetProfile(self):
+        """phase times (ms) of the last Solve() with profiling on, see bloch_get_profile in include/bloch_b200.h"""
+        ms = np.zeros(8)
+        check(self._L.bloch_get_profile(self._h, dptr(ms), 8))
+        names = ["solve", "nd_apply_outside_precond", "projector", "precond", "gram_rotation", "host_rr", "lift_extra",
+                 "nd_apply_in_precond"]
+        return dict(zip(names, ms.tolist()))
+
     def SetNumEigs(self, nev):
         """nev counts REAL modes like the reference (2 per complex band)."""
         self.nev = int(nev)
