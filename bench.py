@@ -2,19 +2,22 @@
 """bench.py - headline benchmark of the Bloch Maxwell eigen path (BASELINE.json metric:
 "Bloch curl-curl apply GDOF/s; k-points/sec (10 bands, tol 1e-6)").
 
-A *step* is one k-point eigen-solve (SetKappa + Setup + Solve, 10 complex bands, abs. residual
-tol 1e-6) of configs[1]: FCC lattice, dielectric sphere (eps 10 inside r <= 0.25), ND order 2,
-the 32-point path Gamma-X-W-L-Gamma.  `value` = k-points/sec over all ranks.  The apply kernel
-(Y = A X, the curl-curl operator) is timed separately with CUDA events and reported in
-`roofline` (algorithmic 32 B per complex DOF per vector) and `apply_gdofs`.
+A *step* is one k-point eigen-solve (SetKappa + Setup + Solve, 10 complex bands, abs. residual tol 1e-6) of
+configs[1]: FCC lattice, dielectric sphere (eps 10 inside r <= 0.25), ND order 2, the 32-point path
+Gamma-X-W-L-Gamma.  `value` = k-points/sec over all ranks at n_sub = 8 (N = 49 152 complex DOF, the size the CPU
+arm can solve completely); the same sweep one refinement up (n_sub = 16, N = 393 216) is reported in `n_sub16`.
+Every timed solve is checked (all bands converged; eigenvalues against the committed oracle fixture
+tests/golden/bands_baseline.json) - an unvalidated run exits non-zero.
+`roofline` is the operator-apply kernel Y = A X on configs[2] (BCC order 3, 2.24 M complex DOF, 10 right-hand
+sides; 1/4/16/30 in `study`), timed live with CUDA events, L2 flushed: the "apply GDOF/s" half of the metric.
 
   python bench.py --gpus N --steps K --warmup W            # this framework
-  python bench.py --impl reference ...                     # CPU restatement (oracle port)
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference algorithm (oracle port)
+  python bench.py --sweep hex --gpus N                     # configs[3]: HEX 256-point sweep sharded over N ranks
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -22,17 +25,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm uses every host core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import numpy as np  # noqa: E402
 
 PATH_LABELS = ["Gamma", "X", "W", "L", "Gamma"]
 ALG_BYTES_PER_DOF = 32.0   # read x (16 B) + write y (16 B) per complex DOF per vector
+GOLDEN = os.path.join(ROOT, "tests", "golden", "bands_baseline.json")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lattice", default="FCC")
     ap.add_argument("--order", type=int, default=2)
@@ -40,17 +50,19 @@ def parse():
     ap.add_argument("--bands", type=int, default=10)
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--pts-per-segment", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "4")),
-                    help="concurrent k-point solves per GPU (independent handles on separate streams)")
-    ap.add_argument("--chunk", type=int, default=0,
-                    help="k-points per work unit of the stream pool (0 = steps / (2 * streams))")
-    ap.add_argument("--apply-vectors", type=int, default=10)
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "2")),
+                    help="concurrent handles per GPU (independent streams / host threads)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("BLOCH_BENCH_BATCH", "5")),
+                    help="k-points iterated together inside one handle (bloch_set_kappa_batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the config-3 apply study (quick runs)")
+    ap.add_argument("--no-n16", action="store_true", help="skip the n_sub = 16 leg")
     ap.add_argument("--apply-study", action="store_true",
-                    help="operator-apply roofline study (configs[2]: BCC order 3, ~2.2M complex DOF, 1/4/10/30 RHS)")
-    ap.add_argument("--cpu-sample-nsub", type=int, default=0, help="0 = same mesh as the workload")
-    ap.add_argument("--cpu-sample-iters", type=int, default=1,
-                    help="LOBPCG iterations timed per CPU sample (0 = full solves)")
+                    help="operator-apply roofline study only (CUB p1 / FCC p2 / BCC p3, 1/4/10/16/30 RHS)")
+    ap.add_argument("--sweep", default="", choices=["", "hex"],
+                    help="hex: configs[3], the 256-point HEX dispersion sweep sharded over the ranks (strong scaling)")
+    ap.add_argument("--sweep-np", type=int, default=27, help="points per path segment of --sweep (27 -> 255 rows)")
+    ap.add_argument("--out", default="", help="--sweep: directory for disp.dat")
     return ap.parse_args()
 
 
@@ -65,15 +77,13 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md).  Sampled through NVML from a
-    Python thread (every 100 ms): polling with a `nvidia-smi -lms` child process was measured to slow the timed
-    region by up to 40 % on some hosts (its queries serialise with kernel launches in the driver); nvidia-smi is
-    only the fallback when the NVML binding is missing."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md), sampled through NVML from a
+    Python thread every 100 ms (a polling nvidia-smi child process slowed the timed region on some hosts)."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, "/tmp/bloch_clocks_%d_%d.csv" % (os.getpid(), index)
+        self.index = index
         self.thread, self.stop_flag, self.sm, self.mx, self.reasons = None, threading.Event(), [], [], set()
 
     def _nvml_handle(self):
@@ -108,19 +118,8 @@ class ClockSampler:
             nv, h = self._nvml_handle()
             self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
             self.thread.start()
-            return
         except Exception:
             self.thread = None
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "250"],
-                                         stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -130,40 +129,96 @@ class ClockSampler:
             if self.sm:
                 out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
                        "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
-            return out
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm), "source": "nvidia-smi"}
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
         return out
 
 
-def k_points(m, lat, args):
-    return m.k_path(lat, PATH_LABELS, args.pts_per_segment)
+def workload_config(args, N, nk):
+    """the `config` object, identical for both arms"""
+    return {"workload": "%s dielectric-sphere band structure along Gamma-X-W-L-Gamma, ND order %d, n_sub=%d "
+                        "(N=%d complex DOF), %d-point path, %d bands, tol %g; secondary legs of the b200 arm: the same "
+                        "sweep at n_sub=%d, operator apply on BCC order 3 n_sub=12"
+                        % (args.lattice, args.order, args.n_sub, N, nk, args.bands, args.tol, 2 * args.n_sub),
+            "lattice": args.lattice, "order": args.order, "n_sub": args.n_sub, "bands": args.bands, "tol": args.tol,
+            "k_points_per_rank": args.steps,
+            "l2": "solver working set (basis [N][3 x batch x 16 columns] x3 + temporaries, ~1 GB) exceeds the 126 MB "
+                  "L2; the apply micro-benchmarks flush L2 (256 MiB write) between launches"}
+
+
+def golden_bands(lattice, order, n_sub):
+    """{path index: eigenvalues} of the committed oracle fixture for this mesh (tests/golden/bands_baseline.json)"""
+    out = {}
+    try:
+        for rec in json.load(open(GOLDEN)):
+            if rec["lattice"] == lattice and rec["order"] == order and rec["n_sub"] == n_sub and rec.get("path_index") is not None:
+                out[int(rec["path_index"])] = np.array(rec["eigenvalues"])
+    except Exception:
+        pass
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+def time_apply(m, torch, eq, nv, st, flush, reps=20):
+    """CUDA-event timing of Y = A X (memset of y + apply kernel) on the handle's stream, L2 flushed between launches"""
+    x = torch.rand(eq.N * nv * 2, device="cuda", dtype=torch.float64) * 2 - 1
+    y = torch.empty_like(x)
+    ts = []
+    with torch.cuda.stream(st):
+        for _ in range(5):
+            eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
+        for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
+            e1.record(st)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+    st.synchronize()
+    del x, y
+    return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
+
+
+def apply_entry(eq, name, p, n, nv, t_mean, t_med, t_best, hbm, fp64):
+    Q = p + 1
+    cfma = 12 * p * Q ** 3 + 12 * p * p * Q * Q + 9 * p * p * Q      # complex-by-real FMAs per element-vector
+    flops_per_dof = 4.0 * cfma * eq.n_elem / eq.N
+    gd = eq.N * nv / t_mean / 1e9
+    return {"lattice": name, "order": p, "n_sub": n, "N": eq.N, "vectors": nv, "launch_us_mean": t_mean * 1e6,
+            "launch_us_median": t_med * 1e6, "launch_us_best": t_best * 1e6, "gdofs": gd,
+            "achieved_gbs": ALG_BYTES_PER_DOF * gd, "hbm_frac": ALG_BYTES_PER_DOF * gd / hbm,
+            "flops_per_dof": flops_per_dof, "fp64_tflops": gd * flops_per_dof / 1e3,
+            "fp64_frac": gd * flops_per_dof / 1e3 / fp64 if fp64 else None}
+
+
+def apply_roofline(m, torch, local, cases, vectors):
+    """operator-apply study: list of entries (one per case x vector count)"""
+    hbm, how = peaks()
+    st = torch.cuda.Stream()
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+    out, fp64 = [], None
+    for name, p, n in cases:
+        lat = m.BravaisLattice(name)
+        eq = m.MaxwellBlochWaveEquation(lat, n, p, device=local)
+        eq.SetMassCoef(m.sphere_eps(eq.element_centers()))
+        eq.set_stream(st.cuda_stream)
+        eq.SetKappa(0.5 * lat.GetSymmetryPoint(1))
+        eq.Setup()
+        if fp64 is None:
+            fp64 = eq.fp64_peak_tflops()
+        for nv in vectors:
+            out.append(apply_entry(eq, name, p, n, nv, *time_apply(m, torch, eq, nv, st, flush), hbm, fp64))
+        eq.set_stream(0)
+        del eq
+    return out, hbm, how, fp64
+
+
+def traffic_for(kernel_key):
+    """per-launch DRAM bytes of the roofline kernel from the committed `ncu --set full` capture of this round"""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+        return tr[kernel_key]["dram_bytes_per_launch"], tr[kernel_key].get("source")
+    except Exception:
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -182,69 +237,55 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lat = m.BravaisLattice(args.lattice)
-    ks = k_points(m, lat, args)
+    ks = m.k_path(lat, PATH_LABELS, args.pts_per_segment)
     nk = len(ks)
     cores = os.cpu_count() or 1
     T = max(1, min(args.streams, max(1, cores // max(1, world))))   # solver threads per rank <= cores per rank
+    B = max(1, args.batch)
+    while T * B > args.steps and B > 1:
+        B -= 1
     if T * world * 2 > cores:
         os.environ["BLOCH_BLOCKING_SYNC"] = "1"                    # sleep, do not spin, when threads are scarce
     eqs = [m.MaxwellBlochWaveEquation(lat, args.n_sub, args.order, device=local) for _ in range(T)]
     eps = m.sphere_eps(eqs[0].element_centers())
     for eq in eqs:
         eq.SetMassCoef(eps)
-        eq.SetNumEigs(2 * args.bands)
-        eq.SetAbsoluteTolerance(args.tol, 2000)
     N = eqs[0].N
-
-    iters_seen = []
-
-    def solve_range(eq, idxs, out, e2e):
-        for i in idxs:
-            if e2e:
-                eq.SetMassCoef(eps)          # host -> device copy of this step's coefficient field
-            eq.SetKappa(ks[i % nk])
-            eq.Setup()
-            eq.Solve()
-            out[i] = eq.band_eigenvalues() if e2e else None
-            iters_seen.append(eq.GetSolverStats()["iterations"])
-
-    def sweep(first, count, e2e):
-        """solves k-points first..first+count-1 (mod path length) of this rank on T streams"""
-        out = {}
-        idxs = [first + j for j in range(count)]
-        if T == 1:
-            solve_range(eqs[0], idxs, out, e2e)
-        else:
-            # contiguous chunks (neighbouring k-points warm-start each other) handed out from a shared
-            # queue, so a stream that drew easy k-points takes another chunk instead of idling
-            csz = args.chunk if args.chunk > 0 else max(1, len(idxs) // (2 * T))
-            chunks = [idxs[i:i + csz] for i in range(0, len(idxs), csz)]
-            lock = threading.Lock()
-
-            def worker(eq):
-                while True:
-                    with lock:
-                        if not chunks:
-                            return
-                        mine = chunks.pop(0)
-                    solve_range(eq, mine, out, e2e)
-
-            th = [threading.Thread(target=worker, args=(eqs[t],)) for t in range(T)]
-            [t.start() for t in th]
-            [t.join() for t in th]
-        return out
-
     base = rank * args.steps          # weak scaling: every rank gets its own `steps` k-points
-    sweep(base, max(args.warmup, T), False)
+
+    def kappa_at(pos):
+        """position on the closed path in units of path points (fractional positions interpolate)"""
+        i0 = int(np.floor(pos)) % nk
+        f = pos - np.floor(pos)
+        return ks[i0] if f == 0 else (1 - f) * ks[i0] + f * ks[(i0 + 1) % nk]
+
+    timed_idx = [base + j for j in range(args.steps)]
+    timed_kappas = np.array([kappa_at(i) for i in timed_idx])
+    # warm-up: every slot solves the HALF-STEP predecessor of its first timed k-point - not a member of the timed
+    # set, and as close to it as the previous path point is in the steady state of a long sweep; no timed solve
+    # ever starts from its own eigenvectors
+    chunks = m.slot_chunks(args.steps, T * B)
+    warm_kappas = np.array([kappa_at(timed_idx[c[0]] - 0.5) for c in chunks if len(c) > 0])
+    n_warm = len(warm_kappas)
+
+    def upload_eps(eq):
+        eq.SetMassCoef(eps)          # host -> device copy of this step's coefficient field (end-to-end leg)
+
+    def warm():     # n_warm == T * B points on T * B slots: slot s gets warm_kappas[s], like chunk s of the timed sweep
+        return m.batched_sweep(eqs, warm_kappas, args.bands, B, args.tol)
+
+    def launches():
+        return sum(eq.GetSolverStats()["kernel_launches"] for eq in eqs)
 
     def timed(e2e):
-        l0 = sum(eq.GetSolverStats()["kernel_launches"] for eq in eqs)
+        warm()                         # state before the timed region: slots hold their half-step predecessors
+        l0 = launches()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        out = sweep(base, args.steps, e2e)
+        res = m.batched_sweep(eqs, timed_kappas, args.bands, B, args.tol, per_solve=upload_eps if e2e else None)
         torch.cuda.synchronize()
         ev1.record()
         torch.cuda.synchronize()
@@ -254,101 +295,107 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             dist.barrier()
-        l1 = sum(eq.GetSolverStats()["kernel_launches"] for eq in eqs)
-        return ms, l1 - l0, out
+        return ms, launches() - l0, res
 
+    warm()                             # first touch: kernel attributes, graphs, work space
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches, _ = timed(False)
+    ms, n_launch, res = timed(False)
     clocks = sampler.stop()
-    ms_e2e, _, out = timed(True)
-    its = [eq.GetSolverStats()["iterations"] for eq in eqs]
-    its_all = iters_seen if iters_seen else its
+    ms_e2e, _, res_e2e = timed(True)
 
-    # ---- apply kernel: CUDA events on the handle's stream (= torch's current stream), L2 flushed ----
-    eq = eqs[0]
-    nv = args.apply_vectors
-    st = torch.cuda.Stream()            # a real (non-null) stream shared by the events and the handle
-    eq.set_stream(st.cuda_stream)
-    eq.SetKappa(ks[3]); eq.Setup()
-    g = torch.Generator(device="cuda"); g.manual_seed(12345)
-    x = (torch.rand(N * nv * 2, device="cuda", dtype=torch.float64, generator=g) * 2 - 1)
-    y = torch.empty_like(x)
-    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
-    torch.cuda.synchronize()
-    times = []
-    with torch.cuda.stream(st):
-        for _ in range(5):
-            eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
-        for _ in range(20):
-            flush.fill_(1.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
-            e1.record(st)
-            e1.synchronize()
-            times.append(e0.elapsed_time(e1) * 1e-3)
-    st.synchronize()
-    eq.set_stream(0)
-    t_apply = float(np.mean(times))
-    hbm, how = peaks()
-    achieved = ALG_BYTES_PER_DOF * N * nv / t_apply / 1e9
-    traffic, shares = None, {}
-    try:   # per-launch DRAM traffic of k_nd_apply from the committed ncu --set full capture (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        key = "%s_p%d_n%d" % (args.lattice.lower(), args.order, args.n_sub)
-        if key in tr and tr[key]["vectors"] == nv:
-            traffic = tr[key]["dram_bytes_per_launch"]
-        shares = json.load(open(os.path.join(ROOT, "profiles", "kernel_shares_r1.json")))
-    except Exception:
-        pass
-    nd_kernel = ("k_nd_item<%d> (lane pair per item)" if args.order <= 2 else "k_nd_comp<%d> (six lanes per item)") % args.order
-    nd_share = sum(v["share"] for k, v in shares.items() if k.startswith(("k_nd_item", "k_nd_comp", "k_nd_apply")))
-    roof = {"bound": "hbm", "kernel": nd_kernel + ", y = A x, memset of y included",
-            "achieved": achieved, "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": traffic, "traffic_source": "profiles/ncu_nd_apply_r1.md" if traffic else None,
-            "share_of_step_ncu": nd_share if shares else None,
-            "dominant_kernel_of_step": max(shares.items(), key=lambda kv: kv[1]["share"])[0] if shares else None,
-            "dominant_kernel_share": max((v["share"] for v in shares.values()), default=None),
-            "launch_us_mean": t_apply * 1e6, "launch_us_best": float(np.min(times)) * 1e6,
-            "dofs": N, "vectors": nv, "alg_bytes_per_dof_vector": ALG_BYTES_PER_DOF}
-    # the same kernel in its throughput regime (the bench mesh is in the launch-latency regime): one mesh
-    # refinement up, full 16-column solver block, measured live the same way
+    # ---- validation of what was timed ----
+    def validate(r, what):
+        bad = np.nonzero(r["converged"] != args.bands)[0]
+        if len(bad):
+            raise SystemExit("bench.py: %s: k-point(s) %s did not converge all %d bands" % (what, bad.tolist(), args.bands))
+        gold = golden_bands(args.lattice, args.order, args.n_sub)
+        checked, worst = [], 0.0
+        for j, i in enumerate(timed_idx):
+            if (i % nk) in gold:
+                err = float(np.max(np.abs(r["lam"][j] - gold[i % nk]) / np.abs(gold[i % nk])))
+                checked.append(int(i % nk))
+                worst = max(worst, err)
+        if checked and worst > 1e-6:
+            raise SystemExit("bench.py: %s: eigenvalues deviate from the oracle fixture by %.2e (> 1e-6)" % (what, worst))
+        return {"all_bands_converged": True, "golden_path_indices": checked, "max_rel_err_vs_oracle": worst if checked else None,
+                "tolerance": 1e-6, "fixture": "tests/golden/bands_baseline.json"}
+
+    val = validate(res, "timed sweep")
+    validate(res_e2e, "end-to-end sweep")
+    if np.max(np.abs(res["lam"] - res_e2e["lam"]) / np.maximum(np.abs(res["lam"]), 1e-3)) > 1e-6:
+        raise SystemExit("bench.py: timed and end-to-end sweeps disagree")
+    validated = bool(val["golden_path_indices"]) or rank != 0
+
+    # ---- live phase shares of one batched solve (CUDA events inside the handle, outside the timed region) ----
+    shares = None
     try:
-        del x, y
-        big = m.MaxwellBlochWaveEquation(lat, 2 * args.n_sub, args.order, device=local)
-        big.SetMassCoef(m.sphere_eps(big.element_centers()))
-        big.set_stream(st.cuda_stream)
-        big.SetKappa(ks[3]); big.Setup()
-        nvb = 16
-        xb = torch.rand(big.N * nvb * 2, device="cuda", dtype=torch.float64, generator=g) * 2 - 1
-        yb = torch.empty_like(xb)
-        tb = []
-        with torch.cuda.stream(st):
-            for _ in range(5):
-                big.apply_A_device(xb.data_ptr(), yb.data_ptr(), nvb)
-            for _ in range(20):
-                flush.fill_(1.0)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(st)
-                big.apply_A_device(xb.data_ptr(), yb.data_ptr(), nvb)
-                e1.record(st)
-                e1.synchronize()
-                tb.append(e0.elapsed_time(e1) * 1e-3)
-        st.synchronize()
-        tbm = float(np.mean(tb))
-        Q = args.order + 1
-        cfma = 12 * args.order * Q ** 3 + 12 * args.order ** 2 * Q * Q + 9 * args.order ** 2 * Q
-        flops = 4.0 * cfma * big.n_elem * nvb
-        fp64 = big.fp64_peak_tflops()
-        roof["at_scale"] = {"workload": "%s order %d n_sub=%d, N=%d, %d vectors" % (args.lattice, args.order, 2 * args.n_sub, big.N, nvb),
-                            "achieved": ALG_BYTES_PER_DOF * big.N * nvb / tbm / 1e9, "unit": "GB/s",
-                            "frac": ALG_BYTES_PER_DOF * big.N * nvb / tbm / 1e9 / hbm, "gdofs": big.N * nvb / tbm / 1e9,
-                            "launch_us_mean": tbm * 1e6, "fp64_tflops": flops / tbm / 1e12,
-                            "fp64_peak_tflops_measured": fp64, "fp64_frac": flops / tbm / 1e12 / fp64}
-        del big, xb, yb
-    except Exception as ex:   # informational only
-        roof["at_scale"] = {"error": repr(ex)}
+        eq = eqs[0]
+        eq.SetProfile(True)
+        b = min(B, args.steps)
+        eq.SolveBatch(warm_kappas[:b] if n_warm >= b else timed_kappas[:b])
+        eq.SolveBatch(timed_kappas[:b])
+        pr = eq.GetProfile()
+        eq.SetProfile(False)
+        tot = pr["solve"]
+        nd = pr["nd_apply_outside_precond"] + pr["nd_apply_in_precond"]
+        groups = {"nd_operator_apply": nd, "projector_multigrid": pr["projector"], "lifted_operator_extra": pr["lift_extra"],
+                  "chebyshev_vector_updates": pr["precond"] - pr["nd_apply_in_precond"], "gram_and_rotation": pr["gram_rotation"],
+                  "host_rayleigh_ritz": pr["host_rr"]}
+        shares = {"solve_ms": tot, "batch": b, "share": {k: v / tot for k, v in groups.items()},
+                  "dominant": max(groups.items(), key=lambda kv: kv[1])[0],
+                  "how": "CUDA events around the phases of one batched Solve() (bloch_set_profile), host part by wall clock"}
+    except Exception as ex:   # informational
+        shares = {"error": repr(ex)}
+
+    # ---- secondary leg: the same sweep one refinement up ----
+    n16 = None
+    if not args.no_n16:
+        try:
+            big = m.MaxwellBlochWaveEquation(lat, 2 * args.n_sub, args.order, device=local)
+            big.SetMassCoef(m.sphere_eps(big.element_centers()))
+            b16, k16 = 4, 8
+            c16 = m.slot_chunks(k16, b16)
+            m.batched_sweep([big], np.array([kappa_at(base + c[0] - 0.5) for c in c16]), args.bands, b16, args.tol)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r16 = m.batched_sweep([big], timed_kappas[:k16], args.bands, b16, args.tol)
+            torch.cuda.synchronize()
+            e1.record()
+            torch.cuda.synchronize()
+            ms16 = e0.elapsed_time(e1)
+            n16 = {"n_sub": 2 * args.n_sub, "N": big.N, "k_points": k16, "batch": b16, "value": k16 / (ms16 * 1e-3),
+                   "unit": "k-points/s (this rank)", "ms_per_step": ms16 / k16,
+                   "all_bands_converged": bool(np.all(r16["converged"] == args.bands)),
+                   "lobpcg_iterations_mean": float(np.mean(r16["iterations"])),
+                   "max_rel_dev_from_n_sub_%d" % args.n_sub: float(np.max(np.abs(r16["lam"] - res["lam"][:k16]) / np.abs(res["lam"][:k16])))}
+            del big
+        except Exception as ex:
+            n16 = {"error": repr(ex)}
+
+    # ---- roofline: operator apply on configs[2] (BCC order 3, n_sub 12), FCC order 2 as secondary ----
+    roof, roof_fcc = None, None
+    if not args.no_roofline and rank == 0:
+        try:
+            study, hbm, how, fp64 = apply_roofline(m, torch, local, [("BCC", 3, 12)], [10, 1, 4, 16, 30])
+            head = study[0]
+            traffic, tsrc = traffic_for("bcc_p3_n12_v10")
+            nd_share = shares["share"]["nd_operator_apply"] if shares and "share" in shares else None
+            roof = {"bound": "hbm", "kernel": "k_nd_comp<3> (six lanes per item), y = A x on BCC order 3 n_sub=12 (N=%d), "
+                                              "%d right-hand sides, clearing of y included" % (head["N"], head["vectors"]),
+                    "achieved": head["achieved_gbs"], "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": head["hbm_frac"],
+                    "traffic": traffic, "traffic_source": tsrc, "gdofs": head["gdofs"],
+                    "fp64_tflops": head["fp64_tflops"], "fp64_peak_tflops_measured": fp64, "fp64_frac": head["fp64_frac"],
+                    "launch_us_mean": head["launch_us_mean"], "launch_us_best": head["launch_us_best"], "dofs": head["N"],
+                    "vectors": head["vectors"], "alg_bytes_per_dof_vector": ALG_BYTES_PER_DOF,
+                    "study": [{k: e[k] for k in ("vectors", "gdofs", "hbm_frac", "fp64_frac", "launch_us_mean")} for e in study],
+                    "share_of_headline_step": nd_share, "phase_shares_of_headline_step": shares}
+            sf, _, _, _ = apply_roofline(m, torch, local, [(args.lattice, args.order, args.n_sub), (args.lattice, args.order, 2 * args.n_sub)],
+                                         [16, 16 * B])
+            roof_fcc = [{k: e[k] for k in ("lattice", "order", "n_sub", "N", "vectors", "gdofs", "hbm_frac", "fp64_frac", "launch_us_mean")} for e in sf]
+        except Exception as ex:
+            roof = {"error": repr(ex)}
 
     if rank != 0:
         if dist is not None:
@@ -357,23 +404,24 @@ def run_b200(args):
     total_steps = args.steps * world
     line = {
         "metric": "k-points/sec (10 bands, tol 1e-6)", "value": total_steps / (ms * 1e-3), "unit": "k-points/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, T), "ms_per_step": ms / args.steps,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, n_warm), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s dielectric-sphere band structure along Gamma-X-W-L-Gamma, ND order %d, "
-                               "n_sub=%d (N=%d complex DOF), %d k-points path, %d bands, tol %g"
-                               % (args.lattice, args.order, args.n_sub, N, nk, args.bands, args.tol),
-                   "k_points_per_rank": args.steps, "concurrent_solves_per_gpu": T,
-                   "l2": "solver working set (basis [N][3m] x3 + temporaries) exceeds L2 only for n_sub>=16; "
-                         "apply micro-benchmark flushes L2 (256 MiB write) between launches"},
+        "config": workload_config(args, N, nk),
+        "impl_config": {"handles_per_gpu": T, "k_points_batched_per_handle": B, "slots": T * B,
+                        "padded_solves": int(res["wasted"]), "rounds": int(res["rounds"]),
+                        "warmup_solves": "each of the %d slots solves the half-step predecessor of its first timed "
+                                         "k-point (not in the timed set) before every timed region" % n_warm},
         "e2e": {"value": total_steps / (ms_e2e * 1e-3), "unit": "k-points/s",
                 "h2d_bytes_per_step": int(eps.nbytes + 24), "d2h_bytes_per_step": int(8 * args.bands)},
-        "gpu_launches": int(launches), "lobpcg_iterations_mean": float(np.mean(its_all)),
-        "apply_gdofs": N * nv / t_apply / 1e9,
-        "roofline": roof, "clocks": clocks,
+        "gpu_launches": int(n_launch), "lobpcg_iterations_mean": float(np.mean(res["iterations"])),
+        "validated": validated, "validation": val,
+        "n_sub16": n16, "roofline": roof, "roofline_fcc": roof_fcc, "clocks": clocks,
     }
+    if roof and "gdofs" in roof:
+        line["apply_gdofs"] = roof["gdofs"]
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(args, steps=1, assumed_iterations=int(round(np.mean(its_all))))
+            line["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=1)
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(e)}
     _emit(json.dumps(line))
@@ -382,16 +430,20 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(args, steps, assumed_iterations=20):
-    """CPU restatement of the reference algorithm (oracle port): assembled CSR operators, per
-    k-point RAP-style products, projected block LOBPCG.  Bounded sample of the same workload."""
+def cpu_baseline(args, steps, warmup):
+    """CPU restatement of the reference algorithm (oracle port): assembled CSR operators, per k-point RAP-style
+    products, projected block LOBPCG; FULL converged solves on all host cores (oracle/cpu_solver.py)."""
     from oracle import cpu_solver
-    nsub = args.cpu_sample_nsub or args.n_sub
     t0 = time.time()
-    res = cpu_solver.time_kpoints(args.lattice, nsub, args.order, PATH_LABELS, args.pts_per_segment,
-                                  args.bands, args.tol, steps, first=3, sample_iters=args.cpu_sample_iters,
-                                  assumed_iterations=assumed_iterations)
+    nk = 4 * args.pts_per_segment
+    # untimed k-points first, so that the timed ones are path indices 0 .. steps-1 like rank 0 of the GPU arm
+    res = cpu_solver.time_kpoints(args.lattice, args.n_sub, args.order, PATH_LABELS, args.pts_per_segment,
+                                  args.bands, args.tol, steps, first=(-warmup) % nk, warmup=warmup, nthreads=os.cpu_count())
     res["wall_s"] = time.time() - t0
+    gold = golden_bands(args.lattice, args.order, args.n_sub)
+    last = (steps - 1) % nk
+    if last in gold and res.get("eigenvalues_last"):
+        res["max_rel_err_vs_fixture"] = float(np.max(np.abs(np.array(res["eigenvalues_last"]) - gold[last]) / np.abs(gold[last])))
     return res
 
 
@@ -399,62 +451,92 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
+    import mfem_bravais_b200 as m   # lattice / sizes only (topology handle, no GPU)
+    lat = m.BravaisLattice(args.lattice)
+    nk = len(m.k_path(lat, PATH_LABELS, args.pts_per_segment))
+    topo = m.MaxwellBlochWaveEquation(lat, args.n_sub, args.order, device=-2)
+    res = cpu_baseline(args, steps=args.steps, warmup=args.warmup)
+    if not res["all_converged"]:
+        raise SystemExit("bench.py --impl reference: a CPU solve did not converge")
     line = {"impl": "reference", "metric": "k-points/sec (10 bands, tol 1e-6)", "value": res["value"],
-            "unit": "k-points/s", "n_gpus": 0, "steps": res["steps"], "warmup": 0,
+            "unit": "k-points/s", "n_gpus": 0, "steps": res["steps"], "warmup": res["warmup"],
             "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": res["sample"]}, "cpu_baseline": res,
+            "config": workload_config(args, topo.N, nk), "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "k-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def hex_sweep(args):
+    """configs[3]: the HEX dispersion sweep (Gamma-M-K-Gamma-A-L-H-A, L-M, K-H; 255 rows, symmetry points solved
+    once) sharded over the ranks in contiguous chunks, no collective on the solve path; results gathered, disp.dat
+    written by rank 0.  Strong scaling: total work fixed.  Reports the per-rank times (tail imbalance)."""
+    import torch
+    import mfem_bravais_b200 as m
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lat = m.BravaisLattice("HEX")
+    rows, uk = m.dispersion_path(lat, args.sweep_np)
+    lo, hi = m.shard_kpoints(len(uk), world, rank)
+    T, B = max(1, args.streams), max(1, args.batch)
+    eqs = [m.MaxwellBlochWaveEquation(lat, 8, 2, device=local) for _ in range(T)]
+    eps = m.sphere_eps(eqs[0].element_centers())
+    for eq in eqs:
+        eq.SetMassCoef(eps)
+    m.batched_sweep(eqs, uk[lo:lo + T * B] * 1.0 + 0.01, args.bands, B, args.tol)    # first touch (attributes, graphs)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = m.batched_sweep(eqs, uk[lo:hi], args.bands, B, args.tol)
+    torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    my_ms = e0.elapsed_time(e1)
+    parts = [(lo, res["lam"], my_ms, int(np.sum(res["iterations"])), bool(np.all(res["converged"] == args.bands)))]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, parts[0])
+        parts = gathered
+    if rank == 0:
+        lam = np.zeros((len(uk), args.bands))
+        for plo, block, _, _, _ in parts:
+            lam[plo:plo + len(block)] = block
+        times = [p[2] for p in parts]
+        outdir = args.out or os.path.join(ROOT, "gpurun_out")
+        os.makedirs(outdir, exist_ok=True)
+        path = os.path.join(outdir, "disp_hex_n%d.dat" % world)
+        m.write_dispersion_data(path, rows, lam)
+        np.save(os.path.join(outdir, "disp_hex_n%d.npy" % world), lam)
+        line = {"metric": "HEX 256-point dispersion sweep, wall time (configs[3])", "value": max(times) * 1e-3, "unit": "s",
+                "higher_is_better": False, "scaling": "strong", "n_gpus": world, "rows": len(rows), "unique_k_points": len(uk),
+                "k_points_per_s": len(uk) / (max(times) * 1e-3), "per_rank_s": [t * 1e-3 for t in times],
+                "tail_imbalance_max_over_mean": max(times) / float(np.mean(times)),
+                "per_rank_lobpcg_iterations": [p[3] for p in parts], "all_bands_converged": all(p[4] for p in parts),
+                "config": {"workload": "HEX a=c=1 dielectric sphere, ND order 2, n_sub=8 (N=%d), %d rows / %d unique k-points, "
+                                       "%d bands, tol %g" % (eqs[0].N, len(rows), len(uk), args.bands, args.tol),
+                           "handles_per_gpu": T, "k_points_batched_per_handle": B}, "disp_dat": os.path.relpath(path, ROOT)}
+        _emit(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def apply_study(args):
     """Y = A X throughput (GDOF/s) and fractions of the HBM (32 B/DOF/vector) and fp64 rooflines."""
     import torch
     import mfem_bravais_b200 as m
-    hbm, how = peaks()
-    out = []
-    st = torch.cuda.Stream()
-    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
-    fp64 = None
-    for name, p, n in [("CUB", 1, 48), ("FCC", 2, 16), ("BCC", 3, 12)]:
-        lat = m.BravaisLattice(name)
-        eq = m.MaxwellBlochWaveEquation(lat, n, p)
-        eq.SetMassCoef(m.sphere_eps(eq.element_centers()))
-        eq.set_stream(st.cuda_stream)
-        eq.SetKappa(0.5 * lat.GetSymmetryPoint(1)); eq.Setup()
-        if fp64 is None:
-            fp64 = eq.fp64_peak_tflops()
-        Q = p + 1
-        cfma = 12 * p * Q ** 3 + 12 * p * p * Q * Q + 9 * p * p * Q      # complex-by-real FMAs per element-vector
-        flops_per_dof = 4.0 * cfma * eq.n_elem / eq.N
-        for nv in (1, 4, 10, 30):
-            x = torch.rand(eq.N * nv * 2, device="cuda", dtype=torch.float64) * 2 - 1
-            y = torch.empty_like(x)
-            ts = []
-            with torch.cuda.stream(st):
-                for _ in range(5):
-                    eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
-                for _ in range(20):
-                    flush.fill_(1.0)
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(st)
-                    eq.apply_A_device(x.data_ptr(), y.data_ptr(), nv)
-                    e1.record(st)
-                    e1.synchronize()
-                    ts.append(e0.elapsed_time(e1) * 1e-3)
-            st.synchronize()
-            t = float(np.median(ts))
-            gd = eq.N * nv / t / 1e9
-            out.append({"lattice": name, "order": p, "n_sub": n, "N": eq.N, "vectors": nv, "median_us": t * 1e6,
-                        "best_us": float(np.min(ts)) * 1e6, "gdofs": gd,
-                        "hbm_frac": ALG_BYTES_PER_DOF * gd / hbm, "flops_per_dof": flops_per_dof,
-                        "tflops": gd * flops_per_dof / 1e3, "fp64_frac": gd * flops_per_dof / 1e3 / fp64})
-            del x, y
-        del eq
+    out, hbm, how, fp64 = apply_roofline(m, torch, 0, [("CUB", 1, 48), ("FCC", 2, 16), ("BCC", 3, 12)], [1, 4, 10, 16, 30])
     _emit(json.dumps({"apply_study": out, "hbm_peak_gbs": hbm, "hbm_peak_source": how, "fp64_peak_tflops": fp64,
-                      "note": "timing = cudaMemset of y + k_nd_apply, CUDA events, L2 flushed between launches"}))
+                      "note": "timing = clearing of y + apply kernel, CUDA events, L2 flushed between launches"}))
 
 
 def _emit(line):
@@ -470,6 +552,8 @@ if __name__ == "__main__":
     a = parse()
     if a.apply_study:
         apply_study(a)
+    elif a.sweep == "hex":
+        hex_sweep(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

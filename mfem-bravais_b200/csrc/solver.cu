@@ -113,60 +113,126 @@ k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld
   }
 }
 
-// Gram matrices of every k-point's basis: C[b][i][j] = sum_r conj(A[r][col(b,i)]) B[r][col(b,j)], i, j < k (<= 64).
-// Same register tiling as k_gram (kernels.cu): 16 x 16 threads, 4 x 4 outputs each; blockIdx.y = k-point.
+// Both Gram matrices of every k-point's basis in one pass over the rows:
+//   GA[b][i][j] = sum_r conj(S[r][col(b,i)]) AS[r][col(b,j)],   GM[b] likewise with MS,   i, j < k <= 16 TS.
+// 16 x 16 threads, thread (ti, tj) owns the TS x TS outputs (ti + 16 a, tj + 16 c); both matrices are Hermitian up
+// to rounding, so only the block pairs a <= c are accumulated and mirrored in the epilogue (2/3 of the flops at
+// TS = 3).  Rows are staged 16 at a time with cp.async into a double buffer (the global round trip of the next
+// stage overlaps the current one); the column map of a thread's staging slots is computed once.  blockIdx.y = b.
 constexpr int GB_ROWS = 16;
+template <int TS>
 __global__ void __launch_bounds__(256)
-k_gram_basis(const D2 *__restrict__ A, const D2 *__restrict__ B, int ld, int k, int m, int gs, long n,
-             D2 *__restrict__ Call, long rows_per_cta) {
+k_gram2_basis(const D2 *__restrict__ S, const D2 *__restrict__ AS, const D2 *__restrict__ MS, int ld, int k, int m,
+              int gs, long n, D2 *__restrict__ GAall, D2 *__restrict__ GMall, long rows_per_cta) {
+  constexpr int W = 16 * TS, SLOTS = (GB_ROWS * W) / 256, NP = TS * (TS + 1) / 2;
+  static_assert((GB_ROWS * W) % 256 == 0, "staging slots");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  D2 *sA = reinterpret_cast<D2 *>(smem_raw);   // [GB_ROWS][64] (zero padded)
-  D2 *sB = sA + GB_ROWS * 64;
+  D2 *buf = reinterpret_cast<D2 *>(smem_raw);          // [2 stages][3 arrays][GB_ROWS][W]
   const int b = blockIdx.y;
   const long r0 = blockIdx.x * rows_per_cta;
   const long r1 = min(n, r0 + rows_per_cta);
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-  D2 acc[4][4];
+  // staging slots of this thread: (row q, padded column c) -> global column offset (or -1: zero padding)
+  int sq[SLOTS], sofs[SLOTS];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int u = 0; u < SLOTS; u++) {
+    const int t = threadIdx.x + 256 * u;
+    sq[u] = t / W;
+    const int c = t - sq[u] * W;
+    sofs[u] = c < k ? basis_col(c, m, gs, b) : -1;
+  }
+  auto issue = [&](int stage, long r) {
+    D2 *dst = buf + (size_t)stage * 3 * GB_ROWS * W;
 #pragma unroll
-    for (int c = 0; c < 4; c++) acc[a][c] = make_double2(0.0, 0.0);
-  for (long r = r0; r < r1; r += GB_ROWS) {
-    const int nr = (int)min((long)GB_ROWS, r1 - r);
-    for (int t = threadIdx.x; t < GB_ROWS * 64; t += 256) {
-      const int q = t >> 6, c = t & 63;
-      const bool in = q < nr && c < k;
-      const long off = in ? (r + q) * ld + basis_col(c, m, gs, b) : 0;
-      sA[t] = in ? A[off] : make_double2(0.0, 0.0);
-      sB[t] = in ? B[off] : make_double2(0.0, 0.0);
+    for (int u = 0; u < SLOTS; u++) {
+      const int t = threadIdx.x + 256 * u;
+      const long row = r + sq[u];
+      if (sofs[u] >= 0 && row < r1) {
+        const long off = row * ld + sofs[u];
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + t);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d0), "l"(S + off));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d0 + (unsigned)(GB_ROWS * W * sizeof(D2))), "l"(AS + off));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d0 + (unsigned)(2 * GB_ROWS * W * sizeof(D2))), "l"(MS + off));
+      } else {
+        dst[t] = make_double2(0.0, 0.0);
+        dst[GB_ROWS * W + t] = make_double2(0.0, 0.0);
+        dst[2 * GB_ROWS * W + t] = make_double2(0.0, 0.0);
+      }
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  D2 accA[NP], accM[NP];
+#pragma unroll
+  for (int q = 0; q < NP; q++) { accA[q] = make_double2(0.0, 0.0); accM[q] = make_double2(0.0, 0.0); }
+  int stage = 0;
+  if (r0 < r1) issue(0, r0);
+  for (long r = r0; r < r1; r += GB_ROWS) {
+    const bool more = r + GB_ROWS < r1;
+    if (more) issue(stage ^ 1, r + GB_ROWS);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
+    const D2 *sS = buf + (size_t)stage * 3 * GB_ROWS * W, *sA = sS + GB_ROWS * W, *sM = sA + GB_ROWS * W;
 #pragma unroll 4
     for (int q = 0; q < GB_ROWS; q++) {
-      D2 x[4], y[4];
+      D2 x[TS], ya[TS], ym[TS];
 #pragma unroll
-      for (int a = 0; a < 4; a++) { x[a] = sA[q * 64 + ti + 16 * a]; y[a] = sB[q * 64 + tj + 16 * a]; }
+      for (int a = 0; a < TS; a++) {
+        x[a] = sS[q * W + ti + 16 * a];
+        ya[a] = sA[q * W + tj + 16 * a];
+        ym[a] = sM[q * W + tj + 16 * a];
+      }
+      int pidx = 0;
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int a = 0; a < TS; a++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          acc[a][c].x = fma(x[a].x, y[c].x, acc[a][c].x); acc[a][c].x = fma(x[a].y, y[c].y, acc[a][c].x);
-          acc[a][c].y = fma(x[a].x, y[c].y, acc[a][c].y); acc[a][c].y = fma(-x[a].y, y[c].x, acc[a][c].y);
+        for (int c = a; c < TS; c++) {
+          accA[pidx].x = fma(x[a].x, ya[c].x, accA[pidx].x); accA[pidx].x = fma(x[a].y, ya[c].y, accA[pidx].x);
+          accA[pidx].y = fma(x[a].x, ya[c].y, accA[pidx].y); accA[pidx].y = fma(-x[a].y, ya[c].x, accA[pidx].y);
+          accM[pidx].x = fma(x[a].x, ym[c].x, accM[pidx].x); accM[pidx].x = fma(x[a].y, ym[c].y, accM[pidx].x);
+          accM[pidx].y = fma(x[a].x, ym[c].y, accM[pidx].y); accM[pidx].y = fma(-x[a].y, ym[c].x, accM[pidx].y);
+          pidx++;
         }
     }
     __syncthreads();
+    stage ^= 1;
   }
-  double *Cd = reinterpret_cast<double *>(Call + (size_t)b * k * k);
+  double *GA = reinterpret_cast<double *>(GAall + (size_t)b * k * k);
+  double *GM = reinterpret_cast<double *>(GMall + (size_t)b * k * k);
+  int pidx = 0;
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int a = 0; a < TS; a++)
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
+    for (int c = a; c < TS; c++) {
       const int i = ti + 16 * a, j = tj + 16 * c;
       if (i < k && j < k) {
-        atomicAdd(Cd + 2 * (i * k + j), acc[a][c].x);
-        atomicAdd(Cd + 2 * (i * k + j) + 1, acc[a][c].y);
+        atomicAdd(GA + 2 * (i * k + j), accA[pidx].x); atomicAdd(GA + 2 * (i * k + j) + 1, accA[pidx].y);
+        atomicAdd(GM + 2 * (i * k + j), accM[pidx].x); atomicAdd(GM + 2 * (i * k + j) + 1, accM[pidx].y);
+        if (a != c) {   // mirror block: C[j][i] = conj(C[i][j])
+          atomicAdd(GA + 2 * (j * k + i), accA[pidx].x); atomicAdd(GA + 2 * (j * k + i) + 1, -accA[pidx].y);
+          atomicAdd(GM + 2 * (j * k + i), accM[pidx].x); atomicAdd(GM + 2 * (j * k + i) + 1, -accM[pidx].y);
+        }
       }
+      pidx++;
     }
+}
+
+template <int TS>
+static cudaError_t launch_gram2(const D2 *S, const D2 *AS, const D2 *MS, int ld, int kc, int mb, int gs, long n, int K,
+                                D2 *GA, D2 *GM, cudaStream_t s) {
+  const size_t smem = (size_t)2 * 3 * GB_ROWS * 16 * TS * sizeof(D2);
+  static bool attr_of[kMaxDevices] = {};
+  bool &attr = attr_of[current_device_slot()];
+  if (!attr) {
+    cudaError_t err = cudaFuncSetAttribute(k_gram2_basis<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    attr = true;
+  }
+  long ctas = std::max(1L, 148L * 2 / K);
+  long rows = (n + ctas - 1) / ctas;
+  rows = ((rows + GB_ROWS - 1) / GB_ROWS) * GB_ROWS;
+  ctas = (n + rows - 1) / rows;
+  k_gram2_basis<TS><<<dim3((unsigned)ctas, K), 256, smem, s>>>(S, AS, MS, ld, kc, mb, gs, n, GA, GM, rows);
+  return cudaGetLastError();
 }
 
 // Jacobi diagonals are [n][nk] (one value per dof and k-point); column j of an m-column block vector belongs to
@@ -624,19 +690,15 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     prof_begin(4);
     BLOCH_CUDA(cudaMemsetAsync(dGA.p, 0, sizeof(D2) * K * kc * kc, s));
     BLOCH_CUDA(cudaMemsetAsync(dGM.p, 0, sizeof(D2) * K * kc * kc, s));
-    long ctas = std::max(1L, 148L * 2 / K);
-    long rows = (Nl + ctas - 1) / ctas;
-    rows = ((rows + GB_ROWS - 1) / GB_ROWS) * GB_ROWS;
-    ctas = (Nl + rows - 1) / rows;
-    const size_t gsm = (size_t)GB_ROWS * 128 * sizeof(D2);
-    k_gram_basis<<<dim3((unsigned)ctas, K), 256, gsm, s>>>(S.p, AS.p, ld, kc, mb, gs, Nl, dGA.p, rows);
-    k_gram_basis<<<dim3((unsigned)ctas, K), 256, gsm, s>>>(S.p, MS.p, ld, kc, mb, gs, Nl, dGM.p, rows);
-    count_launch(2);
+    if (kc <= 32) BLOCH_CUDA(launch_gram2<2>(S.p, AS.p, MS.p, ld, kc, mb, gs, Nl, K, dGA.p, dGM.p, s));
+    else if (kc <= 48) BLOCH_CUDA(launch_gram2<3>(S.p, AS.p, MS.p, ld, kc, mb, gs, Nl, K, dGA.p, dGM.p, s));
+    else BLOCH_CUDA(launch_gram2<4>(S.p, AS.p, MS.p, ld, kc, mb, gs, Nl, K, dGA.p, dGM.p, s));
+    count_launch();
     prof_end(4);
-    auto th0 = std::chrono::steady_clock::now();
     BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
     h_sync(s);
+    auto th0 = std::chrono::steady_clock::now();     // the GPU is idle from here until the rotation is launched
     // the K dense problems are independent: spread them over host threads when there are several
     std::vector<char> okk(K, 1), dropped(K, 0);
     auto work = [&](int b0, int b1) {

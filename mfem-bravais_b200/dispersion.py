@@ -93,6 +93,115 @@ def sharded_sweep(solve_fn, kappas, n_bands, dist=None):
     return out
 
 
+def slot_chunks(n_points, n_slots):
+    """Contiguous chunks of the index range [0, n_points) for the slots of a batched sweep (slot = one k-point
+    position of one handle's batch): chunk s = [b[s], b[s+1]); sizes differ by at most one, empty chunks last."""
+    bounds = [n_points * s // n_slots for s in range(n_slots + 1)]
+    return [list(range(bounds[s], bounds[s + 1])) for s in range(n_slots)]
+
+
+def batched_sweep(eqs, kappas, n_bands, batch, tol=1e-6, max_iter=2000, per_solve=None):
+    """Solves every k-point of `kappas` exactly once on len(eqs) handles x `batch` slots per handle
+    (bloch_set_kappa_batch).  The list is cut into len(eqs) * batch contiguous chunks; a handle walks its `batch`
+    chunks in lock step, one batched Solve per round, so that consecutive k-points of a chunk warm-start each other
+    (the reference's k-loop, maxwell_dispersion.cpp:475-531, taken len(eqs) * batch points at a time).  Handles run
+    on their own host threads / streams.  A slot whose chunk is exhausted repeats its last k-point so that the batch
+    size - and with it every captured graph and buffer - stays fixed; those repeats are counted in `wasted`.
+    per_solve(eq): optional hook called before every batched solve (the bench's end-to-end leg re-uploads the
+    coefficient field there).  Returns dict: lam[n, n_bands], iterations[n], converged[n], wasted, rounds."""
+    import threading
+    kappas = np.asarray(kappas, float).reshape(-1, 3)
+    n = len(kappas)
+    T = len(eqs)
+    chunks = slot_chunks(n, T * batch)
+    lam = np.zeros((n, n_bands))
+    its = np.zeros(n, int)
+    conv = np.zeros(n, int)
+    info = {"wasted": 0, "rounds": 0}
+    errors = []
+
+    def worker(t):
+        try:
+            eq = eqs[t]
+            eq.SetNumEigs(2 * n_bands)
+            eq.SetAbsoluteTolerance(tol, max_iter)
+            mine = [c for c in chunks[t * batch:(t + 1) * batch] if len(c) > 0]
+            if not mine:
+                return
+            for r in range(max(len(c) for c in mine)):
+                idx = [c[r] if r < len(c) else c[-1] for c in mine]
+                if per_solve is not None:
+                    per_solve(eq)
+                lm, st = eq.SolveBatch(kappas[idx])
+                for j, (c, i) in enumerate(zip(mine, idx)):
+                    if r < len(c):
+                        lam[i], its[i], conv[i] = lm[j], st[j]["iterations"], st[j]["converged_bands"]
+                    else:
+                        info["wasted"] += 1
+                info["rounds"] = max(info["rounds"], r + 1)
+        except BaseException as e:      # re-raised by the caller: a failed solve must fail the sweep
+            errors.append(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errors:
+        raise errors[0]
+    return {"lam": lam, "iterations": its, "converged": conv, **info}
+
+
+def dispersion_path(lattice, np_per_segment):
+    """The k-points maxwell_dispersion visits, in output order (maxwell_dispersion.cpp:475-531, 596-648): for every
+    path and segment of the lattice the points i = 0..np, kappa = ((np+1-i) kappa0 + i kappa1) / (np+1), plus the
+    closing symmetry point of every path; a blank line separates paths in disp.dat.  Symmetry points are solved
+    once and cached by label (:506, 604-614).  Returns (rows, unique_kappas): rows = list of
+    (label, unique_index, path_index), unique_kappas[unique_index] = kappa to solve."""
+    npt = int(np_per_segment)
+    rows, uniq, by_label = [], [], {}
+
+    def add(label, kappa, p, cache):
+        if cache and label in by_label:
+            u = by_label[label]
+        else:
+            u = len(uniq)
+            uniq.append(np.array(kappa, float))
+            if cache:
+                by_label[label] = u
+        rows.append((label, u, p))
+
+    for p in range(lattice.GetNumberPaths()):
+        ns = lattice.GetNumberPathSegments(p)
+        for sgm in range(ns):
+            e0, e1 = lattice.GetPathSegmentEndPointIndices(p, sgm)
+            k0, k1 = lattice.GetSymmetryPoint(e0), lattice.GetSymmetryPoint(e1)
+            for i in range(npt + 1):
+                kap = ((npt + 1 - i) * k0 + i * k1) / (npt + 1)
+                label = "-"
+                if i == 0:
+                    label = lattice.GetSymmetryPointLabel(e0)
+                elif npt % 2 == 1 and i == (npt + 1) // 2:
+                    label = lattice.GetIntermediatePointLabel(p, sgm)
+                add(label, kap, p, cache=(i == 0))
+            if sgm + 1 == ns:
+                add(lattice.GetSymmetryPointLabel(e1), k1, p, cache=True)
+    return rows, np.array(uniq)
+
+
+def write_dispersion_data(path, rows, lam_unique):
+    """disp.dat exactly as WriteDispersionData prints it (maxwell_dispersion.cpp:1062-1087): counter, label, then
+    omega = sqrt(lambda) (0 for -1e-6 < lambda <= 0, -1 otherwise) of every REAL mode - each complex band twice,
+    like the reference's block form - tab separated, a blank line after every path."""
+    with open(path, "w") as f:
+        last_p = None
+        for c, (label, u, p) in enumerate(rows):
+            if last_p is not None and p != last_p:
+                f.write("\n")
+            last_p = p
+            om = np.repeat(omega_of_lambda(lam_unique[u]), 2)
+            f.write("%d\t%s" % (c, label) + "".join("\t%.10g" % v for v in om) + "\n")
+        f.write("\n")
+
+
 def write_hypre_ij(path, mat, rank=0):
     """Writes a real scipy sparse matrix the way HypreParMatrix::Print does (hypre_ParCSRMatrixPrintIJ:
     file `<path>.<rank as %05d>`, header `ilower iupper jlower jupper`, then `i j value` per entry, %.14e)."""
