@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--pts-per-segment", type=int, default=8)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "2")),
                     help="concurrent handles per GPU (independent streams / host threads)")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("BLOCH_BENCH_BATCH", "5")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("BLOCH_BENCH_BATCH", "10")),
                     help="k-points iterated together inside one handle (bloch_set_kappa_batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the config-3 apply study (quick runs)")
@@ -496,7 +496,7 @@ def hex_sweep(args):
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = m.batched_sweep(eqs, uk[lo:hi], args.bands, B, args.tol)
+    rows, uk, lo, res = m.sharded_dispersion_sweep(eqs, lat, args.sweep_np, args.bands, B, world, rank, args.tol)
     torch.cuda.synchronize()
     e1.record()
     torch.cuda.synchronize()

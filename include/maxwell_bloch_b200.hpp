@@ -109,7 +109,28 @@ public:
     check(bloch_element_centers(h_, xyz.data()), "bloch_element_centers");
   }
 
-  void SetKappa(const std::vector<double> &kappa) { check(bloch_set_kappa(h_, kappa.data()), "SetKappa"); }
+  void SetKappa(const std::vector<double> &kappa) {
+    kappa_.assign(kappa.begin(), kappa.begin() + 3);
+    check(bloch_set_kappa(h_, kappa.data()), "SetKappa");
+  }
+  // k-point batch (bloch_set_kappa_batch): nk Bloch vectors, kappas[3 * nk], iterated together by the next Solve();
+  // SelectKPoint chooses the k-point the getters refer to.  GetEigenvaluesBatch = the 4-argument convenience form of
+  // GetEigenvalues (maxwell_bloch.cpp:1078-1097) for nk k-points at once, eigenvalues[k] as the reference returns them.
+  void SetKappaBatch(const std::vector<double> &kappas) {
+    kappa_.assign(kappas.begin(), kappas.begin() + 3);
+    check(bloch_set_kappa_batch(h_, (int)(kappas.size() / 3), kappas.data()), "SetKappaBatch");
+  }
+  void SelectKPoint(int k) { check(bloch_select_kpoint(h_, k), "SelectKPoint"); }
+  void GetEigenvaluesBatch(int nev, const std::vector<double> &kappas, std::vector<std::vector<double>> &eigenvalues) {
+    SetNumEigs(nev);
+    SetKappaBatch(kappas);
+    Setup();
+    Solve();
+    const int nk = (int)(kappas.size() / 3);
+    eigenvalues.resize(nk);
+    for (int k = 0; k < nk; k++) { SelectKPoint(k); GetEigenvalues(eigenvalues[k]); }
+    SelectKPoint(0);
+  }
   void SetBeta(double beta) { beta_ = beta; push_beta_zeta(); }
   void SetZeta(const std::vector<double> &zeta) { zeta_ = zeta; push_beta_zeta(); }
   void SetAbsoluteTolerance(double atol) { check(bloch_set_tol(h_, atol, 2000), "SetAbsoluteTolerance"); }
@@ -207,6 +228,139 @@ public:
     check(bloch_get_eigenvector_B(h_, i / 2, Br.data(), Bi.data()), "GetEigenvectorB");
     if (i & 1) { for (int64_t k = 0; k < Nrt_; k++) { double t = Br[k]; Br[k] = -Bi[k]; Bi[k] = t; } }
   }
+  // GetEigenvector (maxwell_bloch.hpp:187-190): all four parts of real mode i
+  void GetEigenvector(unsigned i, std::vector<double> &Er, std::vector<double> &Ei, std::vector<double> &Br,
+                      std::vector<double> &Bi) {
+    GetEigenvectorE(i, Er, Ei);
+    GetEigenvectorB(i, Br, Bi);
+  }
+  // DetermineBasis (maxwell_bloch.cpp:1700-1727): right-handed orthonormal frame with e[2] = kappa / |kappa|,
+  // e[1] = the part of v1 orthogonal to kappa, e[0] = e[1] x e[2]; the Cartesian frame when |kappa| < 1e-4.  The
+  // reference's body subtracts (e2.v1) v1 instead of (e2.v1) e2 and assigns e[0][0] twice (e[0][1] stays unset);
+  // this builds the frame those lines are evidently meant to build.
+  void DetermineBasis(const std::vector<double> &v1, std::vector<std::vector<double>> &e) const {
+    e.assign(3, std::vector<double>(3, 0.0));
+    const double kn = kappa_.size() == 3 ? std::sqrt(kappa_[0] * kappa_[0] + kappa_[1] * kappa_[1] + kappa_[2] * kappa_[2]) : 0.0;
+    if (kn < 1.0e-4) { for (int i = 0; i < 3; i++) e[i][i] = 1.0; return; }
+    for (int i = 0; i < 3; i++) e[2][i] = kappa_[i] / kn;
+    const double d = e[2][0] * v1[0] + e[2][1] * v1[1] + e[2][2] * v1[2];
+    double nrm = 0;
+    for (int i = 0; i < 3; i++) { e[1][i] = v1[i] - d * e[2][i]; nrm += e[1][i] * e[1][i]; }
+    nrm = std::sqrt(nrm);
+    for (int i = 0; i < 3; i++) e[1][i] /= nrm;
+    e[0][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
+    e[0][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
+    e[0][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
+  }
+  // empty in the reference as well (maxwell_bloch.cpp:1694-1698)
+  void ComputeHomogenizedCoefs() {}
+
+  // WriteVisitFields (maxwell_bloch.cpp:1730-1822): E_r, E_i, B_r, B_i of every mode, cycle = mode number, time =
+  // omega.  The reference writes an MFEM VisIt data collection; here one legacy-VTK unstructured grid per mode,
+  // <prefix>/<label>_<cycle %06d>.vtk (fields evaluated at the element corners with the covariant / contravariant
+  // Piola maps; per-element corner copies, so the discontinuous parts of the FE fields survive) plus
+  // <prefix>/<label>.visit listing the files and <label>.times with omega - VisIt and ParaView open these directly.
+  void WriteVisitFields(const std::string &prefix, const std::string &label) {
+    const int p = order_, q = p + 1;
+    std::vector<double> g(p), l(q), x0, J;
+    std::vector<int> cls;
+    points01(p, g, l);
+    geometry(x0, cls, J);
+    static const double ref[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    auto lagr = [](const std::vector<double> &nodes, double x, std::vector<double> &v) {
+      v.assign(nodes.size(), 1.0);
+      for (size_t j = 0; j < nodes.size(); j++)
+        for (size_t k = 0; k < nodes.size(); k++)
+          if (k != j) v[j] *= (x - nodes[k]) / (nodes[j] - nodes[k]);
+    };
+    // 1-D basis values at the corner coordinates 0 and 1
+    std::vector<double> O[2], Cl[2];
+    for (int a = 0; a < 2; a++) { lagr(g, (double)a, O[a]); lagr(l, (double)a, Cl[a]); }
+    const int Lnd = bloch_local_size(h_, 1), Lrt = bloch_local_size(h_, 2);
+    std::vector<int32_t> mnd((size_t)n_elem_ * Lnd), mrt((size_t)n_elem_ * Lrt);
+    check(bloch_get_dofmap(h_, 1, mnd.data()), "bloch_get_dofmap");
+    check(bloch_get_dofmap(h_, 2, mrt.data()), "bloch_get_dofmap");
+    std::vector<double> ev;
+    GetEigenvalues(ev);
+    std::ofstream list(prefix + "/" + label + ".visit"), times(prefix + "/" + label + ".times");
+    list << "!NBLOCKS 1\n";
+    std::vector<double> F[4];
+    for (int i = 0; i < nev_; i++) {
+      GetEigenvector(i, F[0], F[1], F[2], F[3]);
+      char name[64];
+      std::snprintf(name, sizeof(name), "_%06d.vtk", i + 1);
+      const std::string fn = label + name;
+      std::FILE *f = std::fopen((prefix + "/" + fn).c_str(), "w");
+      if (!f) throw Error(("cannot write " + prefix + "/" + fn).c_str());
+      std::fprintf(f, "# vtk DataFile Version 3.0\nmfem-bravais_b200 Bloch fields\nASCII\nDATASET UNSTRUCTURED_GRID\n");
+      std::fprintf(f, "POINTS %lld double\n", (long long)(8 * n_elem_));
+      for (int64_t e = 0; e < n_elem_; e++) {
+        const double *Je = &J[9 * cls[e]];
+        for (int c = 0; c < 8; c++) {
+          double x[3];
+          for (int d = 0; d < 3; d++) x[d] = x0[3 * e + d] + Je[3 * d] * ref[c][0] + Je[3 * d + 1] * ref[c][1] + Je[3 * d + 2] * ref[c][2];
+          std::fprintf(f, "%.12g %.12g %.12g\n", x[0], x[1], x[2]);
+        }
+      }
+      std::fprintf(f, "CELLS %lld %lld\n", (long long)n_elem_, (long long)(9 * n_elem_));
+      for (int64_t e = 0; e < n_elem_; e++) {
+        std::fprintf(f, "8");
+        for (int c = 0; c < 8; c++) std::fprintf(f, " %lld", (long long)(8 * e + c));
+        std::fprintf(f, "\n");
+      }
+      std::fprintf(f, "CELL_TYPES %lld\n", (long long)n_elem_);
+      for (int64_t e = 0; e < n_elem_; e++) std::fprintf(f, "12\n");
+      std::fprintf(f, "POINT_DATA %lld\n", (long long)(8 * n_elem_));
+      static const char *names[4] = {"E_r", "E_i", "B_r", "B_i"};
+      for (int w = 0; w < 4; w++) {
+        const bool nd = w < 2;
+        const int L = nd ? Lnd : Lrt, nbc = nd ? p * q * q : p * p * q;
+        const std::vector<int32_t> &map = nd ? mnd : mrt;
+        std::fprintf(f, "VECTORS %s double\n", names[w]);
+        for (int64_t e = 0; e < n_elem_; e++) {
+          const double *Je = &J[9 * cls[e]];
+          const double det = Je[0] * (Je[4] * Je[8] - Je[5] * Je[7]) - Je[1] * (Je[3] * Je[8] - Je[5] * Je[6]) + Je[2] * (Je[3] * Je[7] - Je[4] * Je[6]);
+          double Ji[9];   // inverse of Je (row-major)
+          Ji[0] = (Je[4] * Je[8] - Je[5] * Je[7]) / det; Ji[1] = (Je[2] * Je[7] - Je[1] * Je[8]) / det; Ji[2] = (Je[1] * Je[5] - Je[2] * Je[4]) / det;
+          Ji[3] = (Je[5] * Je[6] - Je[3] * Je[8]) / det; Ji[4] = (Je[0] * Je[8] - Je[2] * Je[6]) / det; Ji[5] = (Je[2] * Je[3] - Je[0] * Je[5]) / det;
+          Ji[6] = (Je[3] * Je[7] - Je[4] * Je[6]) / det; Ji[7] = (Je[1] * Je[6] - Je[0] * Je[7]) / det; Ji[8] = (Je[0] * Je[4] - Je[1] * Je[3]) / det;
+          for (int c = 0; c < 8; c++) {
+            const int a[3] = {(int)ref[c][0], (int)ref[c][1], (int)ref[c][2]};
+            double vr[3];   // reference-space components
+            for (int comp = 0; comp < 3; comp++) {
+              // ND component: open along comp, closed otherwise; RT component: closed along comp, open otherwise
+              int n[3];
+              const std::vector<double> *B[3];
+              for (int d = 0; d < 3; d++) {
+                const bool open = nd ? d == comp : d != comp;
+                n[d] = open ? p : q;
+                B[d] = open ? &O[a[d]] : &Cl[a[d]];
+              }
+              double acc = 0;
+              for (int k2 = 0; k2 < n[2]; k2++) for (int k1 = 0; k1 < n[1]; k1++) for (int k0 = 0; k0 < n[0]; k0++) {
+                const double wgt = (*B[0])[k0] * (*B[1])[k1] * (*B[2])[k2];
+                if (wgt == 0.0) continue;
+                const int32_t sg = map[(size_t)e * L + comp * nbc + k0 + n[0] * (k1 + n[1] * k2)];
+                const double val = F[w][(sg < 0 ? -sg : sg) - 1];
+                acc += wgt * (sg < 0 ? -val : val);
+              }
+              vr[comp] = acc;
+            }
+            double v[3];
+            for (int d = 0; d < 3; d++)
+              v[d] = nd ? Ji[d] * vr[0] + Ji[3 + d] * vr[1] + Ji[6 + d] * vr[2]                       // J^-T v
+                        : (Je[3 * d] * vr[0] + Je[3 * d + 1] * vr[1] + Je[3 * d + 2] * vr[2]) / det;   // J v / det
+            std::fprintf(f, "%.12g %.12g %.12g\n", v[0], v[1], v[2]);
+          }
+        }
+      }
+      std::fclose(f);
+      const double om = ev[i] > 0.0 ? std::sqrt(ev[i]) : (ev[i] > -1.0e-6 ? 0.0 : -1.0);
+      list << fn << "\n";
+      times << (i + 1) << " " << fn << " " << om << "\n";
+    }
+  }
+
   // GetAOperator()->Mult / GetMOperator()->Mult / GetSubSpaceProjector()->Mult on 2N vectors
   void MultA(const std::vector<double> &x, std::vector<double> &y) { y.resize(x.size()); check(bloch_apply_A(h_, x.data(), y.data(), (int)(x.size() / (2 * N_))), "MultA"); }
   void MultM(const std::vector<double> &x, std::vector<double> &y) { y.resize(x.size()); check(bloch_apply_M(h_, x.data(), y.data(), (int)(x.size() / (2 * N_))), "MultM"); }
@@ -455,7 +609,7 @@ private:
   int order_ = 1;
   int nev_ = 20;
   double beta_ = 0;
-  std::vector<double> zeta_;
+  std::vector<double> zeta_, kappa_;
   std::vector<double> times_, iters_;
 };
 

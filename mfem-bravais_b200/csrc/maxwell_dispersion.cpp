@@ -56,7 +56,7 @@ static void WriteDispersionData(std::ostream &os, int c, const std::string &labe
 
 int main(int argc, char **argv) {
   int bl_type = 1, order = 1, sr = 0, pr = 2, np = 0, nb = 10, dev = -1;
-  bool write_mats = false, write_mesh = false, plane_wave_init = false;
+  bool write_mats = false, write_mesh = false, plane_wave_init = false, visit = false;
   double a = -1.0;
   std::string out = ".";
   for (int i = 1; i < argc; i++) {
@@ -78,6 +78,7 @@ int main(int argc, char **argv) {
     else if (f == "-wm" || f == "--write-mats") write_mats = true;
     else if (f == "-wmesh" || f == "--write-mesh") write_mesh = true;      // ws-cell.mesh (+ .trans, .coef) for MFEM cross-checks
     else if (f == "-iv" || f == "--plane-wave-init") plane_wave_init = true; // CreateInitialVectors block per k-point (:531)
+    else if (f == "-visit" || f == "--visit") visit = true;   // field files of the symmetry points (WriteVisitFields, :546-550, 641)
     else if (f == "-no-vis" || f == "-no-visit" || f == "-no-wm" || f == "-mp" || f == "-no-mp") {}
     else { std::cerr << "unknown option " << f << std::endl; return 1; }
   }
@@ -131,6 +132,7 @@ int main(int argc, char **argv) {
           } else {
             solve(kappa, eigenvalues);
             if (i == 0) sp_eigs[label] = eigenvalues;
+            if (visit && label != "-") eq.WriteVisitFields(out, "Maxwell-Dispersion-" + label);
             if (write_mats && label != "-") {            // Ar / Ai / M dump (:553-590), hypre IJ text format
               eq.WriteMatrix(0, false, out + "/Ar" + label + ".mat");
               eq.WriteMatrix(0, true, out + "/Ai" + label + ".mat");

@@ -115,6 +115,27 @@ __global__ void k_h1_restrict(const __grid_constant__ Transfer1D T, const int32_
   }
 }
 
+// Y[row][v] (+)= sum_k val[k] X[col[k]][v]: the nested-mesh transfers as explicit sparse matrices (real weights,
+// complex block vectors).  Prolongation: rows = fine dofs (1 - 27 entries each at p = 2), restriction = its
+// transpose: rows = coarse dofs gathering their fine neighbours - no atomics, every output written once, the
+// gathered rows are contiguous in v (coalesced) and L2 resident.
+__global__ void k_csr_apply(const int *__restrict__ ptr, const int32_t *__restrict__ col, const double *__restrict__ val,
+                            const D2 *__restrict__ X, D2 *__restrict__ Y, long nrows, int m, int accumulate) {
+  const long total = nrows * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long r = t / m;
+    const int v = (int)(t - r * m);
+    D2 acc = accumulate ? Y[t] : make_double2(0.0, 0.0);
+    const int k1 = __ldg(ptr + r + 1);
+    for (int k = __ldg(ptr + r); k < k1; k++) {
+      const double w = __ldg(val + k);
+      const D2 x = X[(long)__ldg(col + k) * m + v];
+      acc.x = fma(w, x.x, acc.x); acc.y = fma(w, x.y, acc.y);
+    }
+    Y[t] = acc;
+  }
+}
+
 __global__ void k_count(const int32_t *__restrict__ map, long total, double *__restrict__ cnt) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x)
     atomicAdd(cnt + (map[t] - 1), 1.0);
@@ -485,6 +506,10 @@ struct H1Level {
   DevBuf<D2> Sloc;                    // dense element matrices per class [n_class][L][L] (small levels, p <= 2)
   bool have_S = false;
   DevBuf<int32_t> rep;                // one (element, local index) copy e*L + i per dof (owner of the prolongation)
+  DevBuf<int> P_ptr, R_ptr;           // CSR of the prolongation from the next coarser level (rows = this level's dofs)
+  DevBuf<int32_t> P_col, R_col;       // and of its transpose, the restriction (rows = coarser level's dofs)
+  DevBuf<double> P_val, R_val;
+  bool have_csr = false;
   bool dense = false;
 };
 
@@ -602,6 +627,57 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
       L.tp_loc.upload(loc, s);
       h_sync(s);
     }
+  }
+  // explicit transfer matrices between consecutive levels (kappa independent, built once)
+  for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
+    H1Level &F = mg->lev[l], &Cl = mg->lev[l + 1];
+    const std::vector<int32_t> &nat_f = l == 0 ? h->maps.h1 : F.maps.h1;
+    const std::vector<int32_t> &nat_c = Cl.maps.h1;
+    const long ne = l == 0 ? h->mesh.n_elem : F.mesh.n_elem;
+    const int LH = h->L_h1, nf = F.n, nc = nf / 2, n3 = nf * nf * nf;
+    std::vector<int32_t> rep(F.N0, -1);
+    for (long e = 0; e < ne; e++)
+      for (int k = 0; k < LH; k++) {
+        const int i0 = k / (Q * Q), i1 = (k / Q) % Q, i2 = k % Q;
+        rep[nat_f[(size_t)e * LH + i0 + Q * (i1 + Q * i2)] - 1] = (int32_t)(e * LH + k);
+      }
+    std::vector<int> pptr(F.N0 + 1, 0);
+    std::vector<int32_t> pcol;
+    std::vector<double> pval;
+    for (long g = 0; g < F.N0; g++) {
+      const int ei = rep[g], k = ei % LH, e = ei / LH;
+      const int i0 = k / (Q * Q), i1 = (k / Q) % Q, i2 = k % Q;
+      const int blk = e / n3, rem = e - blk * n3;
+      const int ix = rem % nf, jy = (rem / nf) % nf, kz = rem / (nf * nf);
+      const int par = blk * nc * nc * nc + ((kz / 2) * nc + jy / 2) * nc + ix / 2;
+      const int a0 = ix & 1, a1 = jy & 1, a2 = kz & 1;
+      for (int j0 = 0; j0 < Q; j0++)
+        for (int j1 = 0; j1 < Q; j1++)
+          for (int j2 = 0; j2 < Q; j2++) {
+            const double w = mg->T.P[a0][i0][j0] * mg->T.P[a1][i1][j1] * mg->T.P[a2][i2][j2];
+            if (w == 0.0) continue;
+            pcol.push_back(nat_c[(size_t)par * LH + j0 + Q * (j1 + Q * j2)] - 1);
+            pval.push_back(w);
+          }
+      pptr[g + 1] = (int)pcol.size();
+    }
+    // transpose (counting sort by coarse dof)
+    std::vector<int> rptr(Cl.N0 + 1, 0);
+    for (int32_t c : pcol) rptr[c + 1]++;
+    for (long c = 0; c < Cl.N0; c++) rptr[c + 1] += rptr[c];
+    std::vector<int32_t> rcol(pcol.size());
+    std::vector<double> rval(pcol.size());
+    std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+    for (long g = 0; g < F.N0; g++)
+      for (int k = pptr[g]; k < pptr[g + 1]; k++) {
+        const int pos = fill[pcol[k]]++;
+        rcol[pos] = (int32_t)g;
+        rval[pos] = pval[k];
+      }
+    F.P_ptr.upload(pptr, s); F.P_col.upload(pcol, s); F.P_val.upload(pval, s);
+    F.R_ptr.upload(rptr, s); F.R_col.upload(rcol, s); F.R_val.upload(rval, s);
+    h_sync(s);
+    F.have_csr = true;
   }
   // multiplicity weights of every level that restricts (all but the coarsest)
   for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
@@ -852,23 +928,32 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   // residual, restriction
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
-  BLOCH_CUDA(cudaMemsetAsync(C.b.p, 0, sizeof(D2) * C.N0 * m, s));
-  switch (h->p) {
-    case 1: restrict_t<1>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
-    case 2: restrict_t<2>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
-    case 3: restrict_t<3>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
-    default: restrict_t<4>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+  static const bool use_csr = env_double("BLOCH_MG_CSR_TRANSFER", 1.0) != 0.0;
+  if (use_csr && L.have_csr) {
+    k_csr_apply<<<grid_for(C.N0 * m), TPB, 0, s>>>(L.R_ptr.p, L.R_col.p, L.R_val.p, L.r.p, C.b.p, C.N0, m, 0);
+  } else {
+    BLOCH_CUDA(cudaMemsetAsync(C.b.p, 0, sizeof(D2) * C.N0 * m, s));
+    switch (h->p) {
+      case 1: restrict_t<1>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+      case 2: restrict_t<2>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+      case 3: restrict_t<3>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+      default: restrict_t<4>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, L.r.p, C.b.p, m, s); break;
+    }
   }
   h->count_launch(2);
   vcycle(mg, h, l + 1, m, deg, ratio);
   // prolongation + correction
-  switch (h->p) {
-    case 1: prolong_t<1>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
-    case 2: prolong_t<2>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
-    case 3: prolong_t<3>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
-    default: prolong_t<4>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+  if (use_csr && L.have_csr) {
+    k_csr_apply<<<grid_for(tot), TPB, 0, s>>>(L.P_ptr.p, L.P_col.p, L.P_val.p, C.x.p, L.x.p, L.N0, m, 1);
+  } else {
+    switch (h->p) {
+      case 1: prolong_t<1>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      case 2: prolong_t<2>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      case 3: prolong_t<3>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      default: prolong_t<4>(mg->T, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+    }
+    k_add<<<grid_for(tot), TPB, 0, s>>>(L.x.p, L.d.p, tot);
   }
-  k_add<<<grid_for(tot), TPB, 0, s>>>(L.x.p, L.d.p, tot);
   // post-smoothing
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);

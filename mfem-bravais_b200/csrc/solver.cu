@@ -271,6 +271,38 @@ __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict
   }
 }
 
+// Chebyshev as a three-term recurrence on the iterate (x_0 = 0):
+//   x_next = x + a (x - x_prev) + b jac .* (r - q),   q = (A + sigma M) x
+// 4 reads + 1 write per entry (x_next overwrites x_prev), against 4 reads + 3 writes of the (r, d, x) form above, and
+// the right-hand side r is never modified (no working copy).  first != 0: x_prev is the zero vector (not read).
+__global__ void k_cheb3(const double *__restrict__ jac, const D2 *__restrict__ q, const D2 *__restrict__ r,
+                        const D2 *__restrict__ x, D2 *__restrict__ xprev_next, double a, double b, long n, int m, int nk,
+                        int cpk, int first) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long row = t / m;
+    const double s = b * jac[row * nk + (int)(t - row * m) / cpk];
+    const D2 qq = q[t], rr = r[t], xx = x[t];
+    D2 xp = make_double2(0.0, 0.0);
+    if (!first) xp = xprev_next[t];
+    D2 o;
+    o.x = xx.x + a * (xx.x - xp.x) + s * (rr.x - qq.x);
+    o.y = xx.y + a * (xx.y - xp.y) + s * (rr.y - qq.y);
+    xprev_next[t] = o;
+  }
+}
+// x = c0 * jac .* r
+__global__ void k_cheb3_first(const double *__restrict__ jac, const D2 *__restrict__ r, D2 *__restrict__ x, double c0,
+                              long n, int m, int nk, int cpk) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long row = t / m;
+    const double s = c0 * jac[row * nk + (int)(t - row * m) / cpk];
+    const D2 v = r[t];
+    x[t] = make_double2(s * v.x, s * v.y);
+  }
+}
+
 // jac[i] = 1 / (dA[i] + sigma * dM[i])   (elementwise over the [n][nk] tables)
 __global__ void k_make_jacobi(const double *dA, const double *dM, double sigma, double *jac, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
@@ -615,17 +647,36 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   auto precondition = [&](const D2 *r_in, D2 *out) {
     prof_begin(3);
     prof_in_precond = true;
-    BLOCH_CUDA(cudaMemcpyAsync(Tq.p, r_in, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
     const unsigned g = grid_for(Nl * gs);
-    k_cheb_first<<<g, TPB, 0, s>>>(d_jac.p, Tq.p, Dd.p, out, 1.0 / theta, Nl, gs, K, mb);
-    count_launch();
-    double rho = 1.0 / sigma1;
-    for (int k = 1; k < cheb_degree; k++) {
-      op(Dd.p, gs, Qb.p, gs, gs, 1.0, sigma);
-      const double rho_n = 1.0 / (2.0 * sigma1 - rho);
-      k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / delta, Nl, gs, K, mb);
+    static const bool three_term = env_double("BLOCH_CHEB_THREE_TERM", 1.0) != 0.0;
+    if (three_term) {
+      // iterates alternate between Dd and `out`; with x_1 placed so that the last one lands in `out`
+      D2 *xa = (cheb_degree % 2 == 0) ? Dd.p : out, *xb = (cheb_degree % 2 == 0) ? out : Dd.p;   // x_1 in xa
+      k_cheb3_first<<<g, TPB, 0, s>>>(d_jac.p, r_in, xa, 1.0 / theta, Nl, gs, K, mb);
       count_launch();
-      rho = rho_n;
+      double rho = 1.0 / sigma1;
+      D2 *xcur = xa, *xoth = xb;
+      for (int k = 1; k < cheb_degree; k++) {
+        op(xcur, gs, Qb.p, gs, gs, 1.0, sigma);
+        const double rho_n = 1.0 / (2.0 * sigma1 - rho);
+        k_cheb3<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, r_in, xcur, xoth, rho_n * rho, 2.0 * rho_n / delta, Nl, gs, K, mb, k == 1 ? 1 : 0);
+        count_launch();
+        rho = rho_n;
+        std::swap(xcur, xoth);
+      }
+      if (xcur != out) BLOCH_CUDA(cudaMemcpyAsync(out, xcur, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
+    } else {
+      BLOCH_CUDA(cudaMemcpyAsync(Tq.p, r_in, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
+      k_cheb_first<<<g, TPB, 0, s>>>(d_jac.p, Tq.p, Dd.p, out, 1.0 / theta, Nl, gs, K, mb);
+      count_launch();
+      double rho = 1.0 / sigma1;
+      for (int k = 1; k < cheb_degree; k++) {
+        op(Dd.p, gs, Qb.p, gs, gs, 1.0, sigma);
+        const double rho_n = 1.0 / (2.0 * sigma1 - rho);
+        k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / delta, Nl, gs, K, mb);
+        count_launch();
+        rho = rho_n;
+      }
     }
     prof_in_precond = false;
     prof_end(3);

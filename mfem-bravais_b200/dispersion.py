@@ -187,6 +187,19 @@ def dispersion_path(lattice, np_per_segment):
     return rows, np.array(uniq)
 
 
+def sharded_dispersion_sweep(eqs, lattice, np_per_segment, n_bands, batch, world=1, rank=0, tol=1e-6):
+    """This rank's share of the maxwell_dispersion sweep: the UNIQUE k-points of
+    dispersion_path() are split into `world` contiguous chunks (shard_kpoints), rank `rank` solves its chunk with
+    batched_sweep on its handles - no collective on the solve path.  Returns (rows, unique_kappas, lo, result) with
+    result = batched_sweep's dict for the k-points [lo, lo + len(result["lam"])); the caller gathers the per-rank
+    blocks (n_bands doubles per k-point) and writes disp.dat with write_dispersion_data."""
+    rows, uk = dispersion_path(lattice, np_per_segment)
+    lo, hi = shard_kpoints(len(uk), world, rank)
+    res = batched_sweep(eqs, uk[lo:hi], n_bands, batch, tol) if hi > lo else \
+        {"lam": np.zeros((0, n_bands)), "iterations": np.zeros(0, int), "converged": np.zeros(0, int), "wasted": 0, "rounds": 0}
+    return rows, uk, lo, res
+
+
 def write_dispersion_data(path, rows, lam_unique):
     """disp.dat exactly as WriteDispersionData prints it (maxwell_dispersion.cpp:1062-1087): counter, label, then
     omega = sqrt(lambda) (0 for -1e-6 < lambda <= 0, -1 otherwise) of every REAL mode - each complex band twice,
@@ -282,6 +295,106 @@ def nd_interpolate(eq, field):
         sl = slice(c * nb, (c + 1) * nb)
         out[gid[:, sl].ravel()] = (sign[:, sl] * loc).ravel()                 # copies agree (tangential continuity)
     return np.concatenate([out.real, out.imag])
+
+
+def _lagrange(nodes, x):
+    """values of the Lagrange basis on `nodes` at the points x: [len(x), len(nodes)]"""
+    nodes, x = np.asarray(nodes, float), np.asarray(x, float)
+    out = np.ones((len(x), len(nodes)))
+    for j in range(len(nodes)):
+        for k in range(len(nodes)):
+            if k != j:
+                out[:, j] *= (x - nodes[k]) / (nodes[j] - nodes[k])
+    return out
+
+
+def evaluate_fields(eq, e_reim=None, b_reim=None, ref_points=None):
+    """Point values of a Nedelec field E (dofs in the boundary layout [re(N); im(N)]) and / or a Raviart-Thomas
+    field B ([re(N_rt); im(N_rt)]) at the reference points `ref_points` [npts, 3] of EVERY element (default: the 8
+    hex corners in MFEM vertex order) - what a GridFunction evaluation does: covariant Piola map J^-T for ND,
+    contravariant J / det for RT, MFEM's tensor bases (open = Lagrange on Gauss-Legendre, closed = Lagrange on
+    Gauss-Lobatto points).  Returns (x[ne, npts, 3], E[ne, npts, 3] complex or None, B[...] complex or None)."""
+    p = eq.order
+    g, l = _gauss_legendre01(p), _gauss_lobatto01(p + 1)
+    pts = _HEX_REF if ref_points is None else np.asarray(ref_points, float)
+    x0, cls, J = eq.element_geometry()
+    Je = J[cls]
+    X = x0[:, None, :] + np.einsum("eij,kj->eki", Je, pts)
+    O = [_lagrange(g, pts[:, d]) for d in range(3)]        # open basis per direction  [npts, p]
+    Cc = [_lagrange(l, pts[:, d]) for d in range(3)]       # closed basis per direction [npts, p + 1]
+
+    def shapes(kind):
+        """[3 components][npts, n_loc_per_component], natural local order (i fastest)"""
+        out = []
+        for c in range(3):
+            f = [(O[d] if (d == c) == (kind == "nd") else Cc[d]) for d in range(3)]
+            out.append(np.einsum("qi,qj,qk->qkji", f[0], f[1], f[2]).reshape(len(pts), -1))
+        return out
+
+    E = B = None
+    if e_reim is not None:
+        e_reim = np.asarray(e_reim, float)
+        ec = e_reim[:eq.N] + 1j * e_reim[eq.N:]
+        gid, sign = eq.dofmap("nd")
+        loc = ec[gid] * sign                                # [ne, L_nd]
+        nb = p * (p + 1) ** 2
+        ref = np.stack([loc[:, c * nb:(c + 1) * nb] @ sh.T for c, sh in enumerate(shapes("nd"))], axis=-1)   # [ne, npts, 3]
+        Jinv = np.linalg.inv(Je)
+        E = np.einsum("eji,eqj->eqi", Jinv, ref)            # J^-T v
+    if b_reim is not None:
+        b_reim = np.asarray(b_reim, float)
+        bc = b_reim[:eq.N_rt] + 1j * b_reim[eq.N_rt:]
+        gid, sign = eq.dofmap("rt")
+        loc = bc[gid] * sign
+        nb = p * p * (p + 1)
+        ref = np.stack([loc[:, c * nb:(c + 1) * nb] @ sh.T for c, sh in enumerate(shapes("rt"))], axis=-1)
+        det = np.linalg.det(Je)
+        B = np.einsum("eij,eqj->eqi", Je, ref) / det[:, None, None]
+    return X, E, B
+
+
+def write_vtk_fields(eq, path, fields, cell_data=None):
+    """Legacy-VTK unstructured grid of the refined Wigner-Seitz cell with point data on per-element corner copies
+    (fields may be discontinuous across faces in their normal / tangential parts, like the FE fields themselves):
+    `fields` = {name: real array [ne, 8, 3]}, cell_data = {name: array [ne]}.  Stand-in for the reference's VisIt
+    data collection (maxwell_bloch.cpp:1730-1822), readable by VisIt / ParaView."""
+    x0, cls, J = eq.element_geometry()
+    X = x0[:, None, :] + np.einsum("eij,kj->eki", J[cls], _HEX_REF)
+    ne = len(x0)
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 3.0\nmfem-bravais_b200 Bloch fields\nASCII\nDATASET UNSTRUCTURED_GRID\n")
+        f.write("POINTS %d double\n" % (8 * ne))
+        np.savetxt(f, X.reshape(-1, 3), fmt="%.12g")
+        f.write("CELLS %d %d\n" % (ne, 9 * ne))
+        np.savetxt(f, np.column_stack([np.full(ne, 8), np.arange(8 * ne).reshape(ne, 8)]), fmt="%d")
+        f.write("CELL_TYPES %d\n" % ne)
+        np.savetxt(f, np.full(ne, 12), fmt="%d")
+        if cell_data:
+            f.write("CELL_DATA %d\n" % ne)
+            for name, v in cell_data.items():
+                f.write("SCALARS %s double 1\nLOOKUP_TABLE default\n" % name)
+                np.savetxt(f, np.asarray(v, float), fmt="%.12g")
+        f.write("POINT_DATA %d\n" % (8 * ne))
+        for name, v in fields.items():
+            f.write("VECTORS %s double\n" % name)
+            np.savetxt(f, np.asarray(v, float).reshape(-1, 3), fmt="%.12g")
+
+
+def read_vtk_fields(path):
+    """minimal reader of write_vtk_fields' output (tests): returns (points[n,3], {name: array[n,3]})"""
+    lines = open(path).read().split("\n")
+    i, pts, fields = 0, None, {}
+    while i < len(lines):
+        tok = lines[i].split()
+        if tok and tok[0] == "POINTS":
+            n = int(tok[1])
+            pts = np.array([[float(v) for v in lines[i + 1 + k].split()] for k in range(n)])
+            i += n
+        elif tok and tok[0] == "VECTORS":
+            fields[tok[1]] = np.array([[float(v) for v in lines[i + 1 + k].split()] for k in range(len(pts))])
+            i += len(pts)
+        i += 1
+    return pts, fields
 
 
 def plane_wave_initial_vectors(eq, lattice, kappa, count=None, literal=True):

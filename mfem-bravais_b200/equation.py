@@ -173,6 +173,7 @@ class MaxwellBlochWaveEquation:
 
     def SetKappa(self, kappa):
         k = np.ascontiguousarray(kappa, float)
+        self._kappa_set = k.copy()
         check(self._L.bloch_set_kappa(self._h, dptr(k)), "bloch_set_kappa")
 
     # ---- k-point batch: several Bloch vectors iterated together (independent eigenproblems, one set of kernel
@@ -303,6 +304,86 @@ class MaxwellBlochWaveEquation:
         re, im = np.zeros(self.N_rt), np.zeros(self.N_rt)
         check(self._L.bloch_get_eigenvector_B(self._h, i, dptr(re), dptr(im)), "bloch_get_eigenvector_B")
         return re, im
+
+    def GetEigenvector(self, i):
+        """GetEigenvector(i, Er, Ei, Br, Bi) (maxwell_bloch.hpp:187-190, .cpp:1371-1458): all four parts of mode i"""
+        er, ei = self.GetEigenvectorE(i)
+        br, bi = self.GetEigenvectorB(i)
+        return er, ei, br, bi
+
+    def IdentifyDegeneracies(self, zero_tol, rel_tol):
+        """IdentifyDegeneracies (maxwell_bloch.cpp:1493-1548): groups of (real-mode) eigenvalue indices that are
+        zero (< zero_tol) or agree to rel_tol relative to their mean; list of sets in ascending order."""
+        ev = self.GetEigenvalues()
+        if len(ev) == 0:
+            return []
+        degen = [{0}]
+        zeroes = ev[0] < zero_tol
+        for i in range(1, len(ev)):
+            if zeroes:
+                if ev[i] > zero_tol:
+                    degen.append(set())
+                    zeroes = False
+            elif abs(ev[i] - ev[i - 1]) > 0.5 * (ev[i] + ev[i - 1]) * rel_tol:
+                degen.append(set())
+            degen[-1].add(i)
+        return degen
+
+    def DetermineBasis(self, v1):
+        """DetermineBasis (maxwell_bloch.cpp:1700-1727): right-handed orthonormal frame (e0, e1, e2) with e2 = kappa /
+        |kappa|, e1 = the part of v1 orthogonal to kappa, e0 = e1 x e2; the Cartesian frame when |kappa| < 1e-4.
+        (The reference's body subtracts (e2.v1) v1 instead of (e2.v1) e2 and assigns e0[0] twice, leaving e0[1]
+        unset - INTEGRATION.md section 4; this returns the frame those lines are evidently meant to build.)"""
+        kappa = self._kappa0()
+        kn = np.linalg.norm(kappa)
+        if kn < 1e-4:
+            return [np.eye(3)[i] for i in range(3)]
+        e2 = kappa / kn
+        v1 = np.asarray(v1, float)
+        e1 = v1 - (e2 @ v1) * e2
+        e1 /= np.linalg.norm(e1)
+        return [np.cross(e1, e2), e1, e2]
+
+    def ComputeHomogenizedCoefs(self):
+        """empty in the reference too (maxwell_bloch.cpp:1694-1698); the effective-medium inputs are GetFieldAverages"""
+        return None
+
+    def _kappa0(self):
+        return np.array(getattr(self, "_kappa_set", np.zeros(3)), float)
+
+    def WriteVisitFields(self, prefix, label, eps=None, muinv=None):
+        """WriteVisitFields (maxwell_bloch.cpp:1730-1822): E_r, E_i, B_r, B_i of every mode (cycle = mode number,
+        time = omega) plus the coefficient fields.  The reference writes an MFEM VisIt data collection; here one
+        legacy-VTK file per mode, `<prefix>/<label>_<cycle:06d>.vtk`, with the fields evaluated at the element corners
+        (VisIt and ParaView read these directly) and `<prefix>/<label>.visit` listing them with their times."""
+        import os
+        from .dispersion import evaluate_fields, omega_of_lambda, write_vtk_fields
+        os.makedirs(prefix, exist_ok=True)
+        lam = self.GetEigenvalues()
+        om = omega_of_lambda(lam)
+        names = []
+        cells = {}
+        if eps is not None:
+            cells["epsilon"] = eps
+        if muinv is not None:
+            cells["muInv"] = muinv
+        for i in range(self.nev):
+            band = i // 2
+            er, ei, br, bi = self.GetEigenvector(band)
+            if i & 1:      # the reference's second real mode of a complex band is i times the first
+                er, ei, br, bi = -ei, er, -bi, br
+            _, E, B = evaluate_fields(self, np.concatenate([er, ei]), np.concatenate([br, bi]))
+            fn = "%s_%06d.vtk" % (label, i + 1)
+            write_vtk_fields(self, os.path.join(prefix, fn), {"E_r": E.real, "E_i": E.imag, "B_r": B.real, "B_i": B.imag}, cells)
+            names.append((fn, om[i]))
+        with open(os.path.join(prefix, label + ".visit"), "w") as f:
+            f.write("!NBLOCKS 1\n")
+            for fn, t in names:
+                f.write("%s\n" % fn)
+        with open(os.path.join(prefix, label + ".times"), "w") as f:
+            for k, (fn, t) in enumerate(names):
+                f.write("%d %s %.12g\n" % (k + 1, fn, t))
+        return [n for n, _ in names]
 
     def GetFieldAverages(self, i):
         """GetFieldAverages (maxwell_bloch.cpp:1550-1632) of band i: dict of complex 3-vectors E, B, D, H."""
