@@ -451,7 +451,10 @@ void bloch_handle_s::apply_nd_ld(const D2 *x, int ldx, D2 *y, int ldy, int nvec,
     const int cat = prof_in_precond ? 7 : 1;
     prof_begin(cat);
     BLOCH_CUDA(cudaMemset2DAsync(y, sizeof(D2) * ldy, 0, sizeof(D2) * nvec, N, stream));
-    BLOCH_CUDA(launch_nd_apply(p, tabs, E, x, ldx, y, ldy, nvec, ca, cm, stream));
+    ElemData Ef = E;
+    static const bool fresh = [] { const char *e = std::getenv("BLOCH_ND_FRESH_Y"); return !e || std::atoi(e) != 0; }();
+    Ef.fresh_y = fresh ? 1 : 0;     // y is cleared right above and only this launch writes it
+    BLOCH_CUDA(launch_nd_apply(p, tabs, Ef, x, ldx, y, ldy, nvec, ca, cm, stream));
     count_launch();
     prof_end(cat);
   }

@@ -125,14 +125,28 @@ __global__ void k_csr_apply(const int *__restrict__ ptr, const int32_t *__restri
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const long r = t / m;
     const int v = (int)(t - r * m);
-    D2 acc = accumulate ? Y[t] : make_double2(0.0, 0.0);
+    D2 acc0 = accumulate ? Y[t] : make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
     const int k1 = __ldg(ptr + r + 1);
-    for (int k = __ldg(ptr + r); k < k1; k++) {
+    int k = __ldg(ptr + r);
+    for (; k + 4 <= k1; k += 4) {      // four independent index -> value chains in flight
+      int c[4];
+      double w[4];
+      D2 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { c[u] = __ldg(col + k + u); w[u] = __ldg(val + k + u); }
+#pragma unroll
+      for (int u = 0; u < 4; u++) x[u] = X[(long)c[u] * m + v];
+      acc0.x = fma(w[0], x[0].x, acc0.x); acc0.y = fma(w[0], x[0].y, acc0.y);
+      acc1.x = fma(w[1], x[1].x, acc1.x); acc1.y = fma(w[1], x[1].y, acc1.y);
+      acc0.x = fma(w[2], x[2].x, acc0.x); acc0.y = fma(w[2], x[2].y, acc0.y);
+      acc1.x = fma(w[3], x[3].x, acc1.x); acc1.y = fma(w[3], x[3].y, acc1.y);
+    }
+    for (; k < k1; k++) {
       const double w = __ldg(val + k);
       const D2 x = X[(long)__ldg(col + k) * m + v];
-      acc.x = fma(w, x.x, acc.x); acc.y = fma(w, x.y, acc.y);
+      acc0.x = fma(w, x.x, acc0.x); acc0.y = fma(w, x.y, acc0.y);
     }
-    Y[t] = acc;
+    Y[t] = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
   }
 }
 

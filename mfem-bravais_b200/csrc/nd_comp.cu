@@ -309,7 +309,9 @@ k_nd_comp(const __grid_constant__ CompTabs T, const ElemData E, const double *__
         for (int b = 0; b < Q; b++) {
           const int s = sc[a * Q + b];
           const unsigned off = (unsigned)(s < 0 ? -s : s) * ystep + yoff;
-          red_add_if(Y + off, flip(f[a][b], s), writes);
+          const bool interior = a > 0 && a < P && b > 0 && b < P;        // compile time: dof of no other element
+          if (interior && E.fresh_y) { if (writes) Y[off] = flip(f[a][b], s); }
+          else red_add_if(Y + off, flip(f[a][b], s), writes);
         }
     }
     __syncwarp();   // all lanes are done with this tile's columns before the next tile overwrites them

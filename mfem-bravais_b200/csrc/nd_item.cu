@@ -310,7 +310,9 @@ __device__ __forceinline__ void nd_item_body(const ItemTabs &T, const ElemData &
           for (int b = 0; b < Q; b++) {
             const int s = __ldg(mp + D::nd(c, o, a, b));
             const unsigned off = (unsigned)(s < 0 ? -s : s) * ystep + yoff;
-            atomicAdd(Y + off, flip(f[a][b], s));
+            const bool interior = a > 0 && a < P && b > 0 && b < P;      // compile time: dof of no other element
+            if (interior && E.fresh_y) { if (active) Y[off] = flip(f[a][b], s); }
+            else atomicAdd(Y + off, flip(f[a][b], s));
           }
         asm volatile("" ::: "memory");
       }
