@@ -139,7 +139,7 @@ def workload_config(args, N, nk):
                         "sweep at n_sub=%d, operator apply on BCC order 3 n_sub=12"
                         % (args.lattice, args.order, args.n_sub, N, nk, args.bands, args.tol, 2 * args.n_sub),
             "lattice": args.lattice, "order": args.order, "n_sub": args.n_sub, "bands": args.bands, "tol": args.tol,
-            "k_points_per_rank": args.steps,
+            "k_points_per_rank": args.steps, "k_points": "path indices 0..%d on every rank" % (args.steps - 1),
             "l2": "solver working set (basis [N][3 x batch x 16 columns] x3 + temporaries, ~1 GB) exceeds the 126 MB "
                   "L2; the apply micro-benchmarks flush L2 (256 MiB write) between launches"}
 
@@ -244,14 +244,20 @@ def run_b200(args):
     B = max(1, args.batch)
     while T * B > args.steps and B > 1:
         B -= 1
-    if T * world * 2 > cores:
-        os.environ["BLOCH_BLOCKING_SYNC"] = "1"                    # sleep, do not spin, when threads are scarce
+    # host side: a handle's thread sleeps while it waits for its stream (a batched iteration takes ~20 ms, the wake-up
+    # latency of a blocking wait is noise) instead of spinning on a core that the Rayleigh-Ritz threads of the other
+    # handles / ranks need; the per-handle Rayleigh-Ritz pool is sized to the cores this rank can count on
+    os.environ.setdefault("BLOCH_BLOCKING_SYNC", "1")
+    os.environ.setdefault("BLOCH_RR_THREADS", str(max(1, min(4, cores // max(1, world * T)))))
     eqs = [m.MaxwellBlochWaveEquation(lat, args.n_sub, args.order, device=local) for _ in range(T)]
     eps = m.sphere_eps(eqs[0].element_centers())
     for eq in eqs:
         eq.SetMassCoef(eps)
     N = eqs[0].N
-    base = rank * args.steps          # weak scaling: every rank gets its own `steps` k-points
+    # weak scaling: every rank solves the SAME `steps` k-points (path indices 0 .. steps-1), i.e. identical work per
+    # GPU, so that the max-over-ranks time measures the machine and not which stretch of the path (the Gamma point,
+    # degenerate symmetry points) a rank happened to draw; the sweep of ONE path sharded over the ranks is --sweep
+    base = 0
 
     def kappa_at(pos):
         """position on the closed path in units of path points (fractional positions interpolate)"""

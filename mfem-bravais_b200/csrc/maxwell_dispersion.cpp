@@ -55,7 +55,7 @@ static void WriteDispersionData(std::ostream &os, int c, const std::string &labe
 }
 
 int main(int argc, char **argv) {
-  int bl_type = 1, order = 1, sr = 0, pr = 2, np = 0, nb = 10, dev = -1;
+  int bl_type = 1, order = 1, sr = 0, pr = 2, np = 0, nb = 10, dev = -1, kb = 1;
   bool write_mats = false, write_mesh = false, plane_wave_init = false, visit = false;
   double a = -1.0;
   std::string out = ".";
@@ -74,6 +74,7 @@ int main(int argc, char **argv) {
     else if (f == "-np") np = std::atoi(next("-np"));
     else if (f == "-nb") nb = std::atoi(next("-nb"));
     else if (f == "-dev") dev = std::atoi(next("-dev"));
+    else if (f == "-kb" || f == "--k-batch") kb = std::atoi(next("-kb"));   // k-points iterated together (1 = the reference's loop)
     else if (f == "-out") out = next("-out");
     else if (f == "-wm" || f == "--write-mats") write_mats = true;
     else if (f == "-wmesh" || f == "--write-mesh") write_mesh = true;      // ws-cell.mesh (+ .trans, .coef) for MFEM cross-checks
@@ -111,46 +112,95 @@ int main(int argc, char **argv) {
       }
     };
 
-    std::ofstream ofs_disp(out + "/disp.dat");
-    std::map<std::string, std::vector<double>> sp_eigs;   // symmetry-point cache (:506, 604-614)
-    int c = 0;
-    for (unsigned p = 0; p < bravais.GetNumberPaths(); p++) {
-      for (unsigned s = 0; s < bravais.GetNumberPathSegments(p); s++) {
-        int e0, e1;
-        bravais.GetPathSegmentEndPointIndices(p, s, e0, e1);
-        std::vector<double> kappa0, kappa1, kappa(3), eigenvalues;
-        bravais.GetSymmetryPoint(e0, kappa0);
-        bravais.GetSymmetryPoint(e1, kappa1);
-        for (int i = 0; i <= np; i++) {
-          for (int d = 0; d < 3; d++)
-            kappa[d] = double(np + 1 - i) / (np + 1) * kappa0[d] + double(i) / (np + 1) * kappa1[d];
-          std::string label = "-";
-          if (i == 0) label = bravais.GetSymmetryPointLabel(e0);
-          else if (np % 2 == 1 && i == (np + 1) / 2) label = bravais.GetIntermediatePointLabel(p, s);
-          if (i == 0 && sp_eigs.count(label)) {
-            eigenvalues = sp_eigs[label];
-          } else {
-            solve(kappa, eigenvalues);
-            if (i == 0) sp_eigs[label] = eigenvalues;
-            if (visit && label != "-") eq.WriteVisitFields(out, "Maxwell-Dispersion-" + label);
-            if (write_mats && label != "-") {            // Ar / Ai / M dump (:553-590), hypre IJ text format
-              eq.WriteMatrix(0, false, out + "/Ar" + label + ".mat");
-              eq.WriteMatrix(0, true, out + "/Ai" + label + ".mat");
-              eq.WriteMatrix(1, false, out + "/M" + label + ".mat");
-            }
+    if (kb > 1) {
+      // Batched walk: the same rows in the same order, but the unique k-points (symmetry points cached by label,
+      // :506, 604-614) are collected first and solved kb at a time with GetEigenvaluesBatch (independent
+      // eigenproblems, one set of kernel launches); disp.dat is identical to the sequential walk's.
+      struct Row { std::string label; int unique; unsigned path; };
+      std::vector<Row> rows;
+      std::vector<std::vector<double>> ukappa;
+      std::map<std::string, int> by_label;
+      auto add = [&](const std::string &label, const std::vector<double> &kap, unsigned p, bool cache) {
+        int u;
+        if (cache && by_label.count(label)) u = by_label[label];
+        else { u = (int)ukappa.size(); ukappa.push_back(kap); if (cache) by_label[label] = u; }
+        rows.push_back({label, u, p});
+      };
+      for (unsigned p = 0; p < bravais.GetNumberPaths(); p++)
+        for (unsigned s = 0; s < bravais.GetNumberPathSegments(p); s++) {
+          int e0, e1;
+          bravais.GetPathSegmentEndPointIndices(p, s, e0, e1);
+          std::vector<double> kappa0, kappa1, kappa(3);
+          bravais.GetSymmetryPoint(e0, kappa0);
+          bravais.GetSymmetryPoint(e1, kappa1);
+          for (int i = 0; i <= np; i++) {
+            for (int d = 0; d < 3; d++)
+              kappa[d] = double(np + 1 - i) / (np + 1) * kappa0[d] + double(i) / (np + 1) * kappa1[d];
+            std::string label = "-";
+            if (i == 0) label = bravais.GetSymmetryPointLabel(e0);
+            else if (np % 2 == 1 && i == (np + 1) / 2) label = bravais.GetIntermediatePointLabel(p, s);
+            add(label, kappa, p, i == 0);
           }
-          WriteDispersionData(ofs_disp, c++, label, eigenvalues);
+          if (s + 1 == bravais.GetNumberPathSegments(p)) add(bravais.GetSymmetryPointLabel(e1), kappa1, p, true);
         }
-        if (s + 1 == bravais.GetNumberPathSegments(p)) {   // close the path at its last symmetry point
-          std::string label = bravais.GetSymmetryPointLabel(e1);
-          if (!sp_eigs.count(label)) {
-            solve(kappa1, eigenvalues);
-            sp_eigs[label] = eigenvalues;
-          }
-          WriteDispersionData(ofs_disp, c++, label, sp_eigs[label]);
-        }
+      std::vector<std::vector<double>> uev(ukappa.size());
+      for (size_t u0 = 0; u0 < ukappa.size(); u0 += kb) {
+        const size_t u1 = std::min(ukappa.size(), u0 + (size_t)kb);
+        std::vector<double> flat;
+        for (size_t u = u0; u < u1; u++) flat.insert(flat.end(), ukappa[u].begin(), ukappa[u].end());
+        std::vector<std::vector<double>> ev;
+        eq.GetEigenvaluesBatch(2 * nb, flat, ev);
+        for (size_t u = u0; u < u1; u++) uev[u] = ev[u - u0];
+      }
+      std::ofstream ofs_disp(out + "/disp.dat");
+      int c = 0;
+      for (size_t r = 0; r < rows.size(); r++) {
+        if (r > 0 && rows[r].path != rows[r - 1].path) ofs_disp << std::endl;
+        WriteDispersionData(ofs_disp, c++, rows[r].label, uev[rows[r].unique]);
       }
       ofs_disp << std::endl;
+    } else {
+      std::ofstream ofs_disp(out + "/disp.dat");
+      std::map<std::string, std::vector<double>> sp_eigs;   // symmetry-point cache (:506, 604-614)
+      int c = 0;
+      for (unsigned p = 0; p < bravais.GetNumberPaths(); p++) {
+        for (unsigned s = 0; s < bravais.GetNumberPathSegments(p); s++) {
+          int e0, e1;
+          bravais.GetPathSegmentEndPointIndices(p, s, e0, e1);
+          std::vector<double> kappa0, kappa1, kappa(3), eigenvalues;
+          bravais.GetSymmetryPoint(e0, kappa0);
+          bravais.GetSymmetryPoint(e1, kappa1);
+          for (int i = 0; i <= np; i++) {
+            for (int d = 0; d < 3; d++)
+              kappa[d] = double(np + 1 - i) / (np + 1) * kappa0[d] + double(i) / (np + 1) * kappa1[d];
+            std::string label = "-";
+            if (i == 0) label = bravais.GetSymmetryPointLabel(e0);
+            else if (np % 2 == 1 && i == (np + 1) / 2) label = bravais.GetIntermediatePointLabel(p, s);
+            if (i == 0 && sp_eigs.count(label)) {
+              eigenvalues = sp_eigs[label];
+            } else {
+              solve(kappa, eigenvalues);
+              if (i == 0) sp_eigs[label] = eigenvalues;
+              if (visit && label != "-") eq.WriteVisitFields(out, "Maxwell-Dispersion-" + label);
+              if (write_mats && label != "-") {            // Ar / Ai / M dump (:553-590), hypre IJ text format
+                eq.WriteMatrix(0, false, out + "/Ar" + label + ".mat");
+                eq.WriteMatrix(0, true, out + "/Ai" + label + ".mat");
+                eq.WriteMatrix(1, false, out + "/M" + label + ".mat");
+              }
+            }
+            WriteDispersionData(ofs_disp, c++, label, eigenvalues);
+          }
+          if (s + 1 == bravais.GetNumberPathSegments(p)) {   // close the path at its last symmetry point
+            std::string label = bravais.GetSymmetryPointLabel(e1);
+            if (!sp_eigs.count(label)) {
+              solve(kappa1, eigenvalues);
+              sp_eigs[label] = eigenvalues;
+            }
+            WriteDispersionData(ofs_disp, c++, label, sp_eigs[label]);
+          }
+        }
+        ofs_disp << std::endl;
+      }
     }
     double mt, st, mi, si;
     int ns;

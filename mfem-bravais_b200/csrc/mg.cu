@@ -942,7 +942,11 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   // residual, restriction
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
-  static const bool use_csr = env_double("BLOCH_MG_CSR_TRANSFER", 1.0) != 0.0;
+  // explicit-matrix transfers win at orders 1-2 (measured: restrict 83 -> 45 us, prolong + add 79 -> 41 us on FCC
+  // order 2 n_sub 8 x 160 columns); at order 3 the coarse rows of the restriction hold up to 343 entries and the
+  // element-wise kernels are faster (BCC order 3 n_sub 8: projector 596 vs 696 ms per solve)
+  static const double csr_env = env_double("BLOCH_MG_CSR_TRANSFER", -1.0);
+  const bool use_csr = csr_env < 0.0 ? h->p <= 2 : csr_env != 0.0;
   if (use_csr && L.have_csr) {
     k_csr_apply<<<grid_for(C.N0 * m), TPB, 0, s>>>(L.R_ptr.p, L.R_col.p, L.R_val.p, L.r.p, C.b.p, C.N0, m, 0);
   } else {

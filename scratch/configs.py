@@ -27,4 +27,4 @@ run("3 BCC p3 n8 (parity size)","BCC",8,3,10,kH)
 run("3 BCC p3 n12 (2.24M DOF)","BCC",12,3,10,kH)
 run("4 HEX p2 n8","HEX",8,2,10,0.5*m.BravaisLattice("HEX").GetSymmetryPoint(5))
 run("5 scalar H1 p4 BCC n8","BCC",8,4,20,kH,scalar=True)
-json.dump(out,open("gpurun_out/configs_r1.json","w"),indent=1)
+json.dump(out,open("gpurun_out/configs_%s.json" % (sys.argv[1] if len(sys.argv) > 1 else "r2"),"w"),indent=1)

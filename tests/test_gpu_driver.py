@@ -93,3 +93,24 @@ def test_cpp_driver_plane_wave_init_and_mesh_export(bloch, tmp_path):
     assert outs[0].shape == outs[1].shape and np.allclose(outs[0], outs[1], rtol=1e-5, atol=2e-5)
     V, H, attr, B = bloch.read_mfem_mesh(str(tmp_path / "b" / "ws-cell.mesh"))
     assert len(H) == 64 and set(attr) == {1, 2} and len(B) == 6 * 16
+
+
+def test_cpp_driver_batched_walk_equals_sequential(bloch, tmp_path):
+    """-kb N: the driver collects the unique k-points of the walk and solves them N at a time (bloch_set_kappa_batch);
+    disp.dat must be the one the reference-style sequential walk writes."""
+    exe = os.path.join(ROOT, "mfem-bravais_b200", "lib", "maxwell_dispersion_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    common = ["-bl", "2", "-o", "2", "-sr", "0", "-pr", "1", "-np", "1", "-nb", "4"]
+    seq, bat = tmp_path / "seq", tmp_path / "bat"
+    seq.mkdir(); bat.mkdir()
+    for d, extra in ((seq, []), (bat, ["-kb", "5"])):
+        r = subprocess.run([exe] + common + extra + ["-out", str(d)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+    ta, tb = (seq / "disp.dat").read_text(), (bat / "disp.dat").read_text()
+    la, lb = [l.split("\t") for l in ta.split("\n")], [l.split("\t") for l in tb.split("\n")]
+    assert len(la) == len(lb)
+    for ra, rb in zip(la, lb):
+        assert ra[:2] == rb[:2]                                           # counters, labels, blank lines between paths
+        if len(ra) > 2:
+            assert np.allclose([float(x) for x in ra[2:]], [float(x) for x in rb[2:]], rtol=1e-5, atol=1e-5)
