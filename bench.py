@@ -244,6 +244,11 @@ def run_b200(args):
     B = max(1, args.batch)
     while T * B > args.steps and B > 1:
         B -= 1
+    # prefer a batch size that fills every round (no padded repeats): the largest B' in [B/2, B] with steps % (T B') == 0
+    for cand in range(B, max(1, B // 2) - 1, -1):
+        if args.steps % (T * cand) == 0:
+            B = cand
+            break
     # host side: a handle's thread sleeps while it waits for its stream (a batched iteration takes ~20 ms, the wake-up
     # latency of a blocking wait is noise) instead of spinning on a core that the Rayleigh-Ritz threads of the other
     # handles / ranks need; the per-handle Rayleigh-Ritz pool is sized to the cores this rank can count on

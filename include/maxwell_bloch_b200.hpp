@@ -11,6 +11,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdint>
+#include <fstream>
 #include <map>
 #include <set>
 #include <stdexcept>
