@@ -773,10 +773,10 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     t_host_rr += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count();
     prof_begin(4);
     if (mb <= 16) {
-      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 8 / K));   // 8 CTAs of 24 KB per SM
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 4 / K));   // (8 CTAs per SM measured slower: 1066 vs 939 us)
       k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 16 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
     } else {
-      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 8 / K));
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 4 / K));
       k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 8 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
     }
     count_launch();
