@@ -173,6 +173,14 @@ int bloch_unpack_device(bloch_handle h, const double *d_block, double *d_reim, i
 int bloch_debug_hegv(int n, int m, const double *ga_reim, const double *gm_reim, double *lambda, double *c_reim,
                      int values_only);
 
+/* The same dense problem solved by the DEVICE Rayleigh-Ritz kernel the eigensolver uses (csrc/rr_device.cu: one CTA
+ * per pencil, Cholesky + parallel Jacobi in shared memory): nk pencils of size n <= 63 stored one after the other,
+ * lowest m <= 32 pairs each; act (nk x m bytes, may be NULL = all) and use_p select the basis columns like the solver
+ * does (column i >= m takes part only if act[i % m]; columns >= 2m only if use_p); info[k] = 0 ok, 1 = basis shrunk,
+ * -1 = failed.  Test hook: parity against bloch_debug_hegv. */
+int bloch_debug_hegv_device(int n, int m, int nk, const double *ga_reim, const double *gm_reim, const unsigned char *act,
+                            int use_p, double *lambda, double *c_reim, int *info);
+
 /* Assembled operators for interchange (the reference's -wm dump of Ar / Ai / M, maxwell_dispersion.cpp:553-590).
  * which = 0: A = S1 - i beta DKZ (complex Hermitian; Re = the reference's Ar block, Im = its (1,0) block with the
  * coefficient folded in), which = 1: M = M1(eps) (real).  CSR over the ND dofs of bloch_get_dofmap numbering.

@@ -82,6 +82,7 @@ SIGNATURES = {
     "bloch_pack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_unpack_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "bloch_debug_hegv": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
+    "bloch_debug_hegv_device": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_ubyte), C.c_int, _dp, _dp, _ip]),
     "bloch_assemble_matrix": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "bloch_get_matrix": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, _dp]),
     "bloch_prolong_eigenvectors": (C.c_int, [_vp, _vp]),

@@ -971,6 +971,36 @@ int bloch_debug_hegv(int n, int m, const double *ga_reim, const double *gm_reim,
   API_END
 }
 
+// ---- device-side dense Rayleigh-Ritz solver (rr_device.cu), exposed for the parity tests against dense.hpp ----
+int bloch_debug_hegv_device(int n, int m, int nk, const double *ga_reim, const double *gm_reim, const unsigned char *act,
+                            int use_p, double *lambda, double *c_reim, int *info) {
+  API_BEGIN
+  REQUIRE(n >= 1 && n <= 63 && m >= 1 && m <= n && m <= 32 && nk >= 1 && ga_reim && gm_reim && lambda && c_reim && info,
+          "bad argument");
+  int ndev = 0;
+  REQUIRE(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device");
+  DevBuf<D2> dGA, dGM, dC;
+  DevBuf<double> dlam;
+  DevBuf<unsigned char> dact, dusep;
+  DevBuf<int> dinfo;
+  const size_t nn = (size_t)nk * n * n;
+  dGA.alloc(nn); dGM.alloc(nn); dC.alloc((size_t)nk * n * m); dlam.alloc((size_t)nk * m);
+  dact.alloc((size_t)nk * m); dusep.alloc(nk); dinfo.alloc(nk);
+  std::vector<unsigned char> a((size_t)nk * m, 1), up(nk, use_p ? 1 : 0);
+  if (act) a.assign(act, act + (size_t)nk * m);
+  BLOCH_CUDA(cudaMemcpy(dGA.p, ga_reim, sizeof(D2) * nn, cudaMemcpyHostToDevice));
+  BLOCH_CUDA(cudaMemcpy(dGM.p, gm_reim, sizeof(D2) * nn, cudaMemcpyHostToDevice));
+  BLOCH_CUDA(cudaMemcpy(dact.p, a.data(), a.size(), cudaMemcpyHostToDevice));
+  BLOCH_CUDA(cudaMemcpy(dusep.p, up.data(), up.size(), cudaMemcpyHostToDevice));
+  BLOCH_CUDA(launch_rr_solve(dGA.p, dGM.p, n, m, nk, dact.p, dusep.p, dC.p, dlam.p, dinfo.p, nullptr));
+  BLOCH_CUDA(cudaDeviceSynchronize());
+  BLOCH_CUDA(cudaMemcpy(lambda, dlam.p, sizeof(double) * nk * m, cudaMemcpyDeviceToHost));
+  BLOCH_CUDA(cudaMemcpy(c_reim, dC.p, sizeof(D2) * nk * n * m, cudaMemcpyDeviceToHost));
+  BLOCH_CUDA(cudaMemcpy(info, dinfo.p, sizeof(int) * nk, cudaMemcpyDeviceToHost));
+  return BLOCH_OK;
+  API_END
+}
+
 // ---- assembled operators (the -wm dump of maxwell_dispersion.cpp:553-590) ----
 int bloch_assemble_matrix(bloch_handle h, int which, int64_t *nnz) {
   API_BEGIN

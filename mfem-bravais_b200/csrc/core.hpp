@@ -204,6 +204,8 @@ struct bloch_handle_s {
   struct LobpcgWork {
     bloch_b200::DevBuf<D2> S, AS, MS, R, Wc, Dd, Tq, Qb, dC, dGA, dGM, Lu, Lphi, Lg;
     bloch_b200::DevBuf<double> dlam, drn, dtau;
+    bloch_b200::DevBuf<unsigned char> dact, dusep;   // device Rayleigh-Ritz: active-column mask [nk][m], P-block flags [nk]
+    bloch_b200::DevBuf<int> dinfo;
   } lw;
 
   // workspace of the divergence projector (inner S0 solve); owned by the handle so that it is released by

@@ -158,6 +158,14 @@ cudaError_t launch_scatter_diag(const int32_t *map, int L, const int *cls, const
 cudaError_t launch_proj_cg(int p, const Tabs &T, const ElemData &E, const double *jac, double2 *phi,
                            double2 *r, double2 *z, double2 *pp, double2 *q, double *scal, int m,
                            long n0, int max_it, double rel_tol, int *info, cudaStream_t s);
+// Device-side Rayleigh-Ritz (rr_device.cu): for each of K k-points the lowest mb eigenpairs of the pencil
+// (GA[k], GM[k]) (kc x kc, row-major, both triangles present) restricted to the selected basis columns - all of the
+// first mb, column i >= mb only if act[k][i % mb] != 0 and GM_ii > 0, the third group only if usep[k] != 0.
+// Outputs C[k] (kc x mb, zero rows for unselected columns), lam[k][mb], info[k] (0 ok, 1 = basis had to be shrunk,
+// -1 = failed), and usep[k] for the next call (0 after a shrunk basis).  kc <= 63, mb <= 32.  One CTA per k-point.
+cudaError_t launch_rr_solve(const double2 *GA, const double2 *GM, int kc, int mb, int K, const unsigned char *act,
+                            unsigned char *usep, double2 *C, double *lam, int *info, cudaStream_t s);
+
 // fill with deterministic pseudo-random complex numbers in (-1,1)
 cudaError_t launch_fill_random(double2 *X, long total, unsigned long long seed, cudaStream_t s);
 

@@ -591,6 +591,16 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   const int kmax = 3 * mb;
   dC.alloc((size_t)K * kmax * mb); dGA.alloc((size_t)K * kmax * kmax); dGM.alloc((size_t)K * kmax * kmax);
   dlam.alloc(gs); drn.alloc(gs); lw.dtau.alloc(K);
+  // Rayleigh-Ritz on the device (rr_device.cu) unless BLOCH_RR_DEVICE=0: no host dense algebra, no copies of the
+  // Gram matrices, no synchronisation between the Gram kernel and the rotation
+  static const bool rr_device = env_double("BLOCH_RR_DEVICE", 1.0) != 0.0;
+  lw.dact.alloc((size_t)gs); lw.dusep.alloc(K); lw.dinfo.alloc(K);
+  std::vector<unsigned char> act8((size_t)gs, 1);
+  std::vector<int> hinfo(K, 0);
+  if (rr_device) {
+    BLOCH_CUDA(cudaMemsetAsync(lw.dusep.p, 0, K, s));
+    BLOCH_CUDA(cudaMemsetAsync(lw.dinfo.p, 0, sizeof(int) * K, s));
+  }
 
   auto op = [&](const D2 *x, int ldx, D2 *y, int ldy, int nvec, double ca, double cm) {
     prob.apply(x, ldx, y, ldy, nvec, ca, cm);
@@ -745,6 +755,21 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     else if (kc <= 48) BLOCH_CUDA(launch_gram2<3>(S.p, AS.p, MS.p, ld, kc, mb, gs, Nl, K, dGA.p, dGM.p, s));
     else BLOCH_CUDA(launch_gram2<4>(S.p, AS.p, MS.p, ld, kc, mb, gs, Nl, K, dGA.p, dGM.p, s));
     count_launch();
+    if (rr_device) {
+      for (size_t t = 0; t < (size_t)gs; t++) act8[t] = active[t] ? 1 : 0;
+      BLOCH_CUDA(cudaMemcpyAsync(lw.dact.p, act8.data(), (size_t)gs, cudaMemcpyHostToDevice, s));
+      BLOCH_CUDA(launch_rr_solve(dGA.p, dGM.p, kc, mb, K, lw.dact.p, lw.dusep.p, dC.p, dlam.p, lw.dinfo.p, s));
+      if (mb <= 16) {
+        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 4 / K));
+        k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 16 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+      } else {
+        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 4 / K));
+        k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 8 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+      }
+      count_launch(2);
+      prof_end(4);
+      return;
+    }
     prof_end(4);
     BLOCH_CUDA(cudaMemcpyAsync(hGA.data(), dGA.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
     BLOCH_CUDA(cudaMemcpyAsync(hGM.data(), dGM.p, sizeof(D2) * K * kc * kc, cudaMemcpyDeviceToHost, s));
@@ -815,6 +840,19 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     }
     std::fill(refresh_k.begin(), refresh_k.end(), 0);
   }
+  auto fetch_ritz = [&]() {   // device Rayleigh-Ritz: Ritz values and status of the last call (caller synchronises)
+    BLOCH_CUDA(cudaMemcpyAsync(lam.data(), dlam.p, sizeof(double) * gs, cudaMemcpyDeviceToHost, s));
+    BLOCH_CUDA(cudaMemcpyAsync(hinfo.data(), lw.dinfo.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  };
+  auto check_ritz = [&](const char *what) {
+    for (int b = 0; b < K; b++)
+      if (hinfo[b] < 0) throw std::runtime_error(what);
+  };
+  if (rr_device) {
+    fetch_ritz();
+    h_sync(s);
+    check_ritz("initial block is rank deficient");
+  }
   std::vector<double> top_prev(K, 0.0);
   auto top_ritz = [&](int b) {
     double top = 0.0;
@@ -856,8 +894,19 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     k_resid_norm<<<grid_for(Nl * gs), TPB, sizeof(double) * gs, s>>>(AS.p, MS.p, ld, dlam.p, R.p, Nl, gs, drn.p);
     count_launch();
     BLOCH_CUDA(cudaMemcpyAsync(rn.data(), drn.p, sizeof(double) * gs, cudaMemcpyDeviceToHost, s));
+    if (rr_device && it > 0) fetch_ritz();       // the only synchronisation of the outer loop besides the inner PCG checks
     h_sync(s);
     t_res += since(t0);
+    if (rr_device && it > 0) {
+      check_ritz("Rayleigh-Ritz failed (basis numerically rank deficient)");
+      if (lift_allowed)       // the check the host path makes right after its Rayleigh-Ritz (one synchronisation later here)
+        for (int b = 0; b < K; b++) {
+          if (lift[b] || frozen[b]) continue;
+          const double top = top_ritz(b);
+          if (it >= 2 && std::fabs(top - top_prev[b]) <= 0.1 * top) enable_lift(b);
+          top_prev[b] = top;
+        }
+    }
     bool all_done = true;
     for (int b = 0; b < K; b++) {
       if (frozen[b]) continue;
@@ -921,7 +970,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
       opA(S.p, ld, AS.p, ld, gs);
       op(S.p, ld, MS.p, ld, gs, 0.0, 1.0);
     }
-    if (lift_allowed) {
+    if (lift_allowed && !rr_device) {
       for (int b = 0; b < K; b++) {
         if (lift[b] || frozen[b]) continue;
         const double top = top_ritz(b);
