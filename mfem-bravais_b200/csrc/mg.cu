@@ -236,6 +236,64 @@ __global__ void k_cheb_step(const double *__restrict__ jac, const D2 *__restrict
     x[t] = xx;
   }
 }
+// ---- degree-2 Chebyshev smoothing of the plain schedule written out (coef: c0 = coef[0], a = coef[1], b = coef[2]):
+// the (r, d, x) recurrence collapses to  x2 = (1 + a) d0 + b D^-1 (rhs - S0 d0),  d0 = c0 D^-1 rhs, which needs
+// 2 + 4 vector passes from a zero guess (instead of copy 2 + first 3 + step 7) and 4 + 5 as a correction of x
+// (instead of residual 3 + first 4 + step 7). ----
+// x = c0 jac b
+__global__ void k_sm2_pre1(const double *__restrict__ jac, const D2 *__restrict__ b, D2 *__restrict__ x,
+                           const double *__restrict__ coef, long n, int m, int nk, int cpk) {
+  const double c0 = coef[0];
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[(t / m) * nk + (int)(t % m) / cpk];
+    const D2 v = b[t];
+    x[t] = make_double2(s * v.x, s * v.y);
+  }
+}
+// x = (1 + a) x + b jac (rhs - q),  q = S0 x
+__global__ void k_sm2_pre2(const double *__restrict__ jac, const D2 *__restrict__ rhs, const D2 *__restrict__ q,
+                           D2 *__restrict__ x, const double *__restrict__ coef, long n, int m, int nk, int cpk) {
+  const double a1 = 1.0 + coef[1], bb = coef[2];
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = bb * jac[(t / m) * nk + (int)(t % m) / cpk];
+    const D2 r = rhs[t], qq = q[t];
+    D2 xx = x[t];
+    xx.x = a1 * xx.x + s * (r.x - qq.x);
+    xx.y = a1 * xx.y + s * (r.y - qq.y);
+    x[t] = xx;
+  }
+}
+// r = b - q ; d = c0 jac r        (q = S0 x)
+__global__ void k_sm2_post1(const double *__restrict__ jac, const D2 *__restrict__ b, const D2 *__restrict__ q,
+                            D2 *__restrict__ r, D2 *__restrict__ d, const double *__restrict__ coef, long n, int m, int nk,
+                            int cpk) {
+  const double c0 = coef[0];
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = c0 * jac[(t / m) * nk + (int)(t % m) / cpk];
+    const D2 bb = b[t], qq = q[t];
+    const D2 rr = make_double2(bb.x - qq.x, bb.y - qq.y);
+    r[t] = rr;
+    d[t] = make_double2(s * rr.x, s * rr.y);
+  }
+}
+// x += (1 + a) d + b jac (r - q)   (q = S0 d)
+__global__ void k_sm2_post2(const double *__restrict__ jac, const D2 *__restrict__ r, const D2 *__restrict__ q,
+                            const D2 *__restrict__ d, D2 *__restrict__ x, const double *__restrict__ coef, long n, int m,
+                            int nk, int cpk) {
+  const double a1 = 1.0 + coef[1], bb = coef[2];
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const double s = bb * jac[(t / m) * nk + (int)(t % m) / cpk];
+    const D2 rr = r[t], qq = q[t], dd = d[t];
+    D2 xx = x[t];
+    xx.x += a1 * dd.x + s * (rr.x - qq.x);
+    xx.y += a1 * dd.y + s * (rr.y - qq.y);
+    x[t] = xx;
+  }
+}
 __global__ void k_jacobi(const double *d, double *jac, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
     jac[t] = d[t] > 0 ? 1.0 / d[t] : 0.0;
@@ -936,9 +994,19 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   H1Level &C = mg->lev[l + 1];
   const int32_t *map_f = L.E.map_h1, *map_c = C.E.map_h1;
   const int nef = L.E.n_elem;
+  static const bool sm2 = env_double("BLOCH_MG_SM2", 1.0) != 0.0;
+  const int nk = h->nk, cpk = m / h->nk;
+  const unsigned gv = grid_for(tot);
   // pre-smoothing from a zero initial guess
-  BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
-  chebyshev(h, L, L.x.p, m, deg, L.cheb.p, false);
+  if (deg == 2 && sm2) {
+    k_sm2_pre1<<<gv, TPB, 0, s>>>(L.jac.p, L.b.p, L.x.p, L.cheb.p, L.N0, m, nk, cpk);
+    level_apply(h, L, L.x.p, L.q.p, m);
+    k_sm2_pre2<<<gv, TPB, 0, s>>>(L.jac.p, L.b.p, L.q.p, L.x.p, L.cheb.p, L.N0, m, nk, cpk);
+    h->count_launch(2);
+  } else {
+    BLOCH_CUDA(cudaMemcpyAsync(L.r.p, L.b.p, sizeof(D2) * tot, cudaMemcpyDeviceToDevice, s));
+    chebyshev(h, L, L.x.p, m, deg, L.cheb.p, false);
+  }
   // residual, restriction
   level_apply(h, L, L.x.p, L.q.p, m);
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
@@ -974,6 +1042,13 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   }
   // post-smoothing
   level_apply(h, L, L.x.p, L.q.p, m);
+  if (deg == 2 && sm2) {
+    k_sm2_post1<<<gv, TPB, 0, s>>>(L.jac.p, L.b.p, L.q.p, L.r.p, L.d.p, L.cheb.p, L.N0, m, nk, cpk);
+    level_apply(h, L, L.d.p, L.q.p, m);
+    k_sm2_post2<<<gv, TPB, 0, s>>>(L.jac.p, L.r.p, L.q.p, L.d.p, L.x.p, L.cheb.p, L.N0, m, nk, cpk);
+    h->count_launch(4);
+    return;
+  }
   k_resid<<<grid_for(tot), TPB, 0, s>>>(L.b.p, L.q.p, L.r.p, tot);
   h->count_launch(3);
   chebyshev(h, L, L.x.p, m, deg, L.cheb.p, true);
