@@ -74,7 +74,9 @@ template <int CW>
 __global__ void __launch_bounds__(256)
 k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld, int k, int m, int gs,
             const D2 *__restrict__ Call, long n) {
-  constexpr int RP = 256 / CW;
+  // thread (rr, j) owns column j of RB = 4 consecutive rows: every coefficient C[i][j] fetched from shared memory is
+  // used for four rows (5 instead of 8 shared loads per 4 complex MACs) and the four accumulation chains are independent
+  constexpr int RB = 4, RG = 256 / CW, RP = RG * RB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   D2 *sC = reinterpret_cast<D2 *>(smem_raw);     // [k][m]
   D2 *sT = sC + k * m;                           // [RP][k]
@@ -92,25 +94,54 @@ k_rr_update(D2 *__restrict__ S, D2 *__restrict__ AS, D2 *__restrict__ MS, int ld
       __syncthreads();
       for (int t = threadIdx.x; t < nr * k; t += 256) sT[t] = base[(long)(t / k) * ld + basis_col(t % k, m, gs, b)];
       __syncthreads();
-      if (rr < nr && j < m) {
-        const D2 *row = sT + rr * k;
-        D2 x = make_double2(0.0, 0.0), pn = make_double2(0.0, 0.0);
+      if (j < m) {
+        D2 x[RB], pn[RB];
+#pragma unroll
+        for (int u = 0; u < RB; u++) { x[u] = make_double2(0.0, 0.0); pn[u] = make_double2(0.0, 0.0); }
+        const D2 *row = sT + (rr * RB) * k;
         for (int i = 0; i < m; i++) {
-          const D2 s = row[i], c = sC[i * m + j];
-          x.x = fma(s.x, c.x, x.x); x.x = fma(-s.y, c.y, x.x);
-          x.y = fma(s.x, c.y, x.y); x.y = fma(s.y, c.x, x.y);
+          const D2 c = sC[i * m + j];
+#pragma unroll
+          for (int u = 0; u < RB; u++) {
+            const D2 s = row[u * k + i];
+            x[u].x = fma(s.x, c.x, x[u].x); x[u].x = fma(-s.y, c.y, x[u].x);
+            x[u].y = fma(s.x, c.y, x[u].y); x[u].y = fma(s.y, c.x, x[u].y);
+          }
         }
         for (int i = m; i < k; i++) {
-          const D2 s = row[i], c = sC[i * m + j];
-          pn.x = fma(s.x, c.x, pn.x); pn.x = fma(-s.y, c.y, pn.x);
-          pn.y = fma(s.x, c.y, pn.y); pn.y = fma(s.y, c.x, pn.y);
+          const D2 c = sC[i * m + j];
+#pragma unroll
+          for (int u = 0; u < RB; u++) {
+            const D2 s = row[u * k + i];
+            pn[u].x = fma(s.x, c.x, pn[u].x); pn[u].x = fma(-s.y, c.y, pn[u].x);
+            pn[u].y = fma(s.x, c.y, pn[u].y); pn[u].y = fma(s.y, c.x, pn[u].y);
+          }
         }
-        D2 *out = base + (long)rr * ld + b * m;
-        out[j] = make_double2(x.x + pn.x, x.y + pn.y);
-        out[2 * gs + j] = pn;
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+          const int r = rr * RB + u;
+          if (r < nr) {
+            D2 *out = base + (long)r * ld + b * m;
+            out[j] = make_double2(x[u].x + pn[u].x, x[u].y + pn[u].y);
+            out[2 * gs + j] = pn[u];
+          }
+        }
       }
     }
   }
+}
+
+// the rotation kernel stages 64 (CW = 16) / 32 (CW = 32) rows: up to ~62 KB of dynamic shared memory, opt-in per device
+static cudaError_t rr_update_attr() {
+  static bool attr_of[kMaxDevices] = {};
+  bool &attr = attr_of[current_device_slot()];
+  if (attr) return cudaSuccess;
+  cudaError_t err = cudaFuncSetAttribute(k_rr_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(k_rr_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (err != cudaSuccess) return err;
+  attr = true;
+  return cudaSuccess;
 }
 
 // Both Gram matrices of every k-point's basis in one pass over the rows:
@@ -748,6 +779,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     return true;
   };
   auto rayleigh_ritz = [&](int kc) {
+    BLOCH_CUDA(rr_update_attr());
     prof_begin(4);
     BLOCH_CUDA(cudaMemsetAsync(dGA.p, 0, sizeof(D2) * K * kc * kc, s));
     BLOCH_CUDA(cudaMemsetAsync(dGM.p, 0, sizeof(D2) * K * kc * kc, s));
@@ -760,11 +792,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
       BLOCH_CUDA(cudaMemcpyAsync(lw.dact.p, act8.data(), (size_t)gs, cudaMemcpyHostToDevice, s));
       BLOCH_CUDA(launch_rr_solve(dGA.p, dGM.p, kc, mb, K, lw.dact.p, lw.dusep.p, dC.p, dlam.p, lw.dinfo.p, s));
       if (mb <= 16) {
-        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 4 / K));
-        k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 16 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 63) / 64, 148L * 4 / K));
+        k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 64 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
       } else {
-        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 4 / K));
-        k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 8 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+        const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 31) / 32, 148L * 4 / K));
+        k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 32 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
       }
       count_launch(2);
       prof_end(4);
@@ -798,11 +830,11 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     t_host_rr += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count();
     prof_begin(4);
     if (mb <= 16) {
-      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 15) / 16, 148L * 4 / K));   // (8 CTAs per SM measured slower: 1066 vs 939 us)
-      k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 16 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 63) / 64, 148L * 4 / K));
+      k_rr_update<16><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 64 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
     } else {
-      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 7) / 8, 148L * 4 / K));
-      k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 8 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
+      const unsigned g = (unsigned)std::max(1L, std::min<long>((Nl + 31) / 32, 148L * 4 / K));
+      k_rr_update<32><<<dim3(g, K), 256, sizeof(D2) * (kc * mb + 32 * kc), s>>>(S.p, AS.p, MS.p, ld, kc, mb, gs, dC.p, Nl);
     }
     count_launch();
     prof_end(4);
