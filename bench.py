@@ -496,7 +496,8 @@ def hex_sweep(args):
     lat = m.BravaisLattice("HEX")
     rows, uk = m.dispersion_path(lat, args.sweep_np)
     lo, hi = m.shard_kpoints(len(uk), world, rank)
-    T, B = max(1, args.streams), max(1, args.batch)
+    T = max(1, args.streams)
+    B = m.choose_batch(hi - lo, T, max(1, args.batch))      # no mostly-padded last round on this rank's chunk
     eqs = [m.MaxwellBlochWaveEquation(lat, 8, 2, device=local) for _ in range(T)]
     eps = m.sphere_eps(eqs[0].element_centers())
     for eq in eqs:

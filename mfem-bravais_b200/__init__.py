@@ -7,4 +7,4 @@ device raises.
 """
 from .capi import lib, lib_path, BlochError, LATTICE_TYPES  # noqa: F401
 from .equation import BravaisLattice, MaxwellBlochWaveEquation, ScalarFloquetWaveEquation  # noqa: F401
-from .dispersion import sharded_dispersion_sweep, batched_sweep, slot_chunks, dispersion_path, write_dispersion_data, k_path, sphere_eps, lattice_coefficient, dispersion_sweep, shard_kpoints, sharded_sweep, MaxwellDispersion, MaxwellBlochWaveSolver, homogenization_sweep, write_hypre_ij, read_hypre_ij, write_matrices, write_mfem_mesh, read_mfem_mesh, plane_wave_initial_vectors, nd_interpolate, evaluate_fields, write_vtk_fields, read_vtk_fields  # noqa: F401
+from .dispersion import choose_batch, sharded_dispersion_sweep, batched_sweep, slot_chunks, dispersion_path, write_dispersion_data, k_path, sphere_eps, lattice_coefficient, dispersion_sweep, shard_kpoints, sharded_sweep, MaxwellDispersion, MaxwellBlochWaveSolver, homogenization_sweep, write_hypre_ij, read_hypre_ij, write_matrices, write_mfem_mesh, read_mfem_mesh, plane_wave_initial_vectors, nd_interpolate, evaluate_fields, write_vtk_fields, read_vtk_fields  # noqa: F401

@@ -100,6 +100,17 @@ def slot_chunks(n_points, n_slots):
     return [list(range(bounds[s], bounds[s + 1])) for s in range(n_slots)]
 
 
+def choose_batch(n_points, n_handles, max_batch):
+    """Batch size for a sweep of n_points k-points on n_handles handles: the smallest batch that keeps the number of
+    rounds of the largest allowed batch, so that the last round is not mostly padding (31 points on 2 handles, at
+    most 10 per batch: 2 rounds either way - a batch of 8 pads 1 solve, a batch of 10 pads 9)."""
+    if n_points <= 0:
+        return 1
+    slots_max = max(1, n_handles * max_batch)
+    rounds = -(-n_points // slots_max)
+    return max(1, min(max_batch, -(-n_points // (n_handles * rounds))))
+
+
 def batched_sweep(eqs, kappas, n_bands, batch, tol=1e-6, max_iter=2000, per_solve=None):
     """Solves every k-point of `kappas` exactly once on len(eqs) handles x `batch` slots per handle
     (bloch_set_kappa_batch).  The list is cut into len(eqs) * batch contiguous chunks; a handle walks its `batch`

@@ -31,6 +31,16 @@ class FakeEq:
         return lam, [{"iterations": 7, "converged_bands": self.nb} for _ in ks]
 
 
+def test_choose_batch(bloch):
+    assert bloch.choose_batch(31, 2, 10) == 8          # 2 rounds, 1 padded solve instead of 9
+    assert bloch.choose_batch(249, 2, 10) == 10        # 13 rounds of 20 slots
+    assert bloch.choose_batch(20, 2, 10) == 10 and bloch.choose_batch(5, 2, 10) == 3 and bloch.choose_batch(0, 2, 10) == 1
+    for n in range(1, 80):
+        for T in (1, 2, 3):
+            B = bloch.choose_batch(n, T, 10)
+            assert 1 <= B <= 10 and -(-n // (T * B)) == -(-n // (T * 10))     # never more rounds than the largest batch
+
+
 def test_slot_chunks(bloch):
     for n in (0, 1, 5, 20, 33):
         for s in (1, 3, 8, 10, 16):
