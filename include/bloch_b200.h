@@ -229,6 +229,16 @@ int bloch_scalar_apply(bloch_handle h, int which, const double *x, double *y, in
  *   mode 0: y(2 N_h1) = S0 x(2 N_h1), S0 = G^T M G;  mode 1: y(2 N) = G x(2 N_h1);
  *   mode 2: y(2 N_h1) = G^T M x(2 N) */
 int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y, int nvec);
+/* Test hook for the auxiliary-space part of the preconditioner (what HypreAMS contributes in the reference,
+ * maxwell_bloch.cpp:492-517): (H1)^3 vectors hold the Cartesian components as blocks, [re(3 N_h1); im(3 N_h1)].
+ *   mode 0: y(2 N) = Pi u   (nodal interpolation (H1)^3 -> ND);  mode 1: y(2 * 3 N_h1) = Pi^T x(2 N);
+ *   mode 2: y = B u, one multigrid V-cycle per component for (grad + i kappa)^H mu^-1 (grad + i kappa) */
+int bloch_debug_apply_aux(bloch_handle h, int mode, const double *x, double *y, int nvec);
+/* Test hook for the nested-mesh transfers of the projector's H1 multigrid (no counterpart in the reference, whose
+ * MINRES has no hierarchy): level 0 (the handle's mesh) <-> level 1 (n_sub / 2) in each implementation -
+ * variant 0 explicit CSR, 1 sum-factorised parent kernels, 2 element-wise kernels; dir 0: y(2 N_h1) = P x(2 n_coarse),
+ * dir 1: y(2 n_coarse) = P^T x(2 N_h1).  x == y == NULL only returns n_coarse. */
+int bloch_debug_mg_transfer(bloch_handle h, int variant, int dir, const double *x, double *y, int nvec, int64_t *n_coarse);
 /* Measurement hook: fp64 FMA throughput of the handle's device in TFLOP/s (roofline denominator
  * of the flop-bound side of the element kernels; not part of the reference interface). */
 int bloch_debug_fp64_peak(bloch_handle h, double *tflops);

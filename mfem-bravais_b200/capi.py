@@ -97,6 +97,8 @@ SIGNATURES = {
     "bloch_scalar_get_eigenvalues": (C.c_int, [_vp, _dp, C.c_int]),
     "bloch_scalar_apply": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "bloch_debug_apply_h1op": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
+    "bloch_debug_apply_aux": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
+    "bloch_debug_mg_transfer": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.POINTER(C.c_int64)]),
     "bloch_debug_fp64_peak": (C.c_int, [_vp, _dp]),
 }
 

@@ -304,6 +304,10 @@ void bloch_handle_s::setup() {
   if ((dirty_kappa || dirty_coef) && use_mg) {
     if (!mg) mg = mg_create(this);
     if (mg) mg_setup(mg, this);
+    if (mg && use_aux && p <= 3) {
+      if (!aux) aux = aux_create(this);
+      if (aux) aux_setup(aux, this);
+    }
   }
   dirty_coef = dirty_kappa = false;
 }
@@ -514,6 +518,7 @@ static bloch_handle_s *make_handle(const std::vector<std::array<double, 3>> &ver
     h->muinv.assign(h->mesh.n_elem, 1.0);
     if (const char *e = std::getenv("BLOCH_TWO_PASS")) h->two_pass = std::atoi(e);
     if (const char *e = std::getenv("BLOCH_MG")) h->use_mg = std::atoi(e);
+    if (const char *e = std::getenv("BLOCH_PRECOND")) h->use_aux = std::string(e) != "cheb";
     if (!host_only) build_kernel_maps(h);
   } catch (...) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -687,6 +692,7 @@ int bloch_destroy(bloch_handle h) {
   cudaStream_t own = h->own_stream;
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->mg) mg_destroy(h->mg);
+  if (h->aux) aux_destroy(h->aux);
   delete h;
   if (own) cudaStreamDestroy(own);
   return BLOCH_OK;
@@ -941,6 +947,60 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
   BLOCH_CUDA(cudaMemcpyAsync(ia.p, x, sizeof(double) * 2 * nin * nvec, cudaMemcpyHostToDevice, s));
   BLOCH_CUDA(launch_pack(ia.p, ba.p, nin, nvec, s));
   h->apply_h1(mode, ba.p, bb.p, nvec);
+  BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
+  BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// test hook: pieces of the auxiliary-space preconditioner (aux.cu) on host vectors; (H1)^3 vectors hold the three
+// Cartesian components as blocks of N0 entries: [re(3 N0); im(3 N0)].
+// mode 0: y(2 N) = Pi u(2 * 3 N0); mode 1: y(2 * 3 N0) = Pi^T x(2 N); mode 2: y(2 * 3 N0) = B u, one V-cycle per component
+int bloch_debug_apply_aux(bloch_handle h, int mode, const double *x, double *y, int nvec) {
+  API_BEGIN
+  REQUIRE(h && x && y && nvec >= 1 && mode >= 0 && mode <= 2, "bad argument");
+  h->setup();
+  REQUIRE(h->aux, "no auxiliary space on this handle (odd n_sub, order > 3 or BLOCH_PRECOND=cheb)");
+  REQUIRE(mode != 2 || nvec % h->nk == 0, "block width must be a multiple of the k-point batch size");
+  const long n3 = 3 * h->N0, nin = (mode == 1) ? h->N : n3, nout = (mode == 0) ? h->N : n3;
+  cudaStream_t s = h->stream;
+  DevBuf<double> ia, ib;
+  DevBuf<D2> ba, bb;
+  ia.alloc((size_t)2 * nin * nvec); ib.alloc((size_t)2 * nout * nvec);
+  ba.alloc((size_t)nin * nvec); bb.alloc((size_t)nout * nvec);
+  BLOCH_CUDA(cudaMemcpyAsync(ia.p, x, sizeof(double) * 2 * nin * nvec, cudaMemcpyHostToDevice, s));
+  BLOCH_CUDA(launch_pack(ia.p, ba.p, nin, nvec, s));
+  if (mode == 0) aux_apply_pi(h->aux, h, ba.p, bb.p, nvec, false);
+  else if (mode == 1) aux_apply_pit(h->aux, h, ba.p, bb.p, nvec);
+  else aux_vcycles(h->aux, h, ba.p, bb.p, nvec);
+  BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
+  BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
+  BLOCH_CUDA(cudaStreamSynchronize(s));
+  return BLOCH_OK;
+  API_END
+}
+
+// test hook: nested-mesh transfer of the H1 multigrid between the handle's mesh and the next coarser one in its three
+// implementations (variant 0 CSR, 1 sum-factorised, 2 element-wise); dir 0: y(2 N0) = P x(2 N0c), dir 1: y(2 N0c) = P^T x(2 N0)
+int bloch_debug_mg_transfer(bloch_handle h, int variant, int dir, const double *x, double *y, int nvec, int64_t *n_coarse) {
+  API_BEGIN
+  REQUIRE(h && variant >= 0 && variant <= 2 && dir >= 0 && dir <= 1, "bad argument");
+  h->setup();
+  REQUIRE(h->mg && mg_level_size(h->mg, 1) > 0, "no nested coarser mesh (odd n_sub)");
+  const long nc = mg_level_size(h->mg, 1), nf = h->N0;
+  if (n_coarse) *n_coarse = nc;
+  if (!x || !y) return BLOCH_OK;          // size query
+  REQUIRE(nvec >= 1, "bad argument");
+  const long nin = dir == 0 ? nc : nf, nout = dir == 0 ? nf : nc;
+  cudaStream_t s = h->stream;
+  DevBuf<double> ia, ib;
+  DevBuf<D2> ba, bb;
+  ia.alloc((size_t)2 * nin * nvec); ib.alloc((size_t)2 * nout * nvec);
+  ba.alloc((size_t)nin * nvec); bb.alloc((size_t)nout * nvec);
+  BLOCH_CUDA(cudaMemcpyAsync(ia.p, x, sizeof(double) * 2 * nin * nvec, cudaMemcpyHostToDevice, s));
+  BLOCH_CUDA(launch_pack(ia.p, ba.p, nin, nvec, s));
+  mg_debug_transfer(h->mg, h, variant, dir, ba.p, bb.p, nvec);
   BLOCH_CUDA(launch_unpack(bb.p, ib.p, nout, nvec, s));
   BLOCH_CUDA(cudaMemcpyAsync(y, ib.p, sizeof(double) * 2 * nout * nvec, cudaMemcpyDeviceToHost, s));
   BLOCH_CUDA(cudaStreamSynchronize(s));

@@ -17,6 +17,7 @@
 #include "kernels.hpp"
 #include "mesh.hpp"
 #include "mg.hpp"
+#include "aux.hpp"
 
 struct bloch_lattice_s {
   bloch_b200::bravais::BravaisLattice *lat = nullptr;
@@ -115,6 +116,8 @@ struct bloch_handle_s {
   std::vector<std::array<int, 8>> coarse_hex;
   bloch_b200::H1Multigrid *mg = nullptr;            // h-multigrid for the projector's S0 solves
   int use_mg = 1;
+  bloch_b200::AuxSpace *aux = nullptr;              // auxiliary nodal space of the ND preconditioner (aux.cu)
+  int use_aux = 1;                                  // 0: Chebyshev-Jacobi polynomial only (BLOCH_PRECOND=cheb)
   bloch_b200::DofMaps maps;
   bloch_b200::Basis1D basis;
   bloch_b200::Tabs tabs;

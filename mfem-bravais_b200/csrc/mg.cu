@@ -115,6 +115,158 @@ __global__ void k_h1_restrict(const __grid_constant__ Transfer1D T, const int32_
   }
 }
 
+// ---- sum-factorised nested-mesh transfers ------------------------------------------------------------------
+// One thread per (parent element, vector, re/im part).  A parent edge carries the 2P+1 distinct fine nodes of its
+// two children; W[i][j] = c_j(x_i) is the 1-D interpolation from the parent's P+1 nodes to them, and the 3-D
+// transfer is W (x) W (x) W: streamed plane by plane it costs (2P+1)(Q^2 Q + (2P+1) Q Q + (2P+1)^2 Q) multiply-adds
+// per parent (2604 at order 3) against Q^3 (2P+1)^3 = 21952 of the entry-by-entry forms (the element-wise kernels
+// above, the CSR rows), with the Q^3 parent values (prolongation) / accumulators (restriction) in registers.
+// Prolongation stores (fine nodes shared by several parents receive the same value from each); restriction
+// weights every fine node by 1 / (number of parent positions that hold it) and adds into the cleared coarse vector.
+struct TransferW { double W[2 * kMaxP + 1][kMaxP + 1]; };
+
+template <int P>
+__device__ __forceinline__ long sf_fine_dof(const int32_t *__restrict__ map_f, int n_f, int blk, int ix, int jy, int kz,
+                                            int i0, int i1, int i2) {
+  constexpr int Q = P + 1, L = Q * Q * Q;
+  const int a0 = i0 > P ? 1 : 0, a1 = i1 > P ? 1 : 0, a2 = i2 > P ? 1 : 0;
+  const long e = (long)blk * n_f * n_f * n_f + ((long)(2 * kz + a2) * n_f + (2 * jy + a1)) * n_f + 2 * ix + a0;
+  return (long)__ldg(map_f + e * L + ((i0 - P * a0) * Q + (i1 - P * a1)) * Q + (i2 - P * a2)) - 1;
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) k_h1_prolong_sf(const __grid_constant__ TransferW T, const int32_t *__restrict__ map_f,
+                                                       const int32_t *__restrict__ map_c, int n_par, int n_f,
+                                                       const double *__restrict__ xc, double *__restrict__ xf, int m) {
+  constexpr int Q = P + 1, F = 2 * P + 1, L = Q * Q * Q;
+  const int nc = n_f / 2, nc3 = nc * nc * nc, m2 = 2 * m;
+  const long total = (long)n_par * m2;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int lane2 = (int)(t % m2);
+    const int par = (int)(t / m2);
+    const int blk = par / nc3, rem = par - blk * nc3;
+    const int ix = rem % nc, jy = (rem / nc) % nc, kz = rem / (nc * nc);
+    double c[Q][Q][Q];
+#pragma unroll
+    for (int j0 = 0; j0 < Q; j0++)
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++)
+          c[j0][j1][j2] = xc[((long)__ldg(map_c + (long)par * L + (j0 * Q + j1) * Q + j2) - 1) * m2 + lane2];
+#pragma unroll 1
+    for (int i0 = 0; i0 < F; i0++) {
+      double pl[Q][Q];
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) {
+          double a = 0.0;
+#pragma unroll
+          for (int j0 = 0; j0 < Q; j0++) a = fma(T.W[i0][j0], c[j0][j1][j2], a);
+          pl[j1][j2] = a;
+        }
+#pragma unroll
+      for (int i1 = 0; i1 < F; i1++) {
+        double row[Q];
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) {
+          double a = 0.0;
+#pragma unroll
+          for (int j1 = 0; j1 < Q; j1++) a = fma(T.W[i1][j1], pl[j1][j2], a);
+          row[j2] = a;
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < F; i2++) {
+          double a = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < Q; j2++) a = fma(T.W[i2][j2], row[j2], a);
+          xf[sf_fine_dof<P>(map_f, n_f, blk, ix, jy, kz, i0, i1, i2) * m2 + lane2] = a;
+        }
+      }
+    }
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) k_h1_restrict_sf(const __grid_constant__ TransferW T, const int32_t *__restrict__ map_f,
+                                                        const int32_t *__restrict__ map_c, int n_par, int n_f,
+                                                        const double *__restrict__ invmult_par,
+                                                        const double *__restrict__ rf, double *__restrict__ rc, int m) {
+  constexpr int Q = P + 1, F = 2 * P + 1, L = Q * Q * Q;
+  const int nc = n_f / 2, nc3 = nc * nc * nc, m2 = 2 * m;
+  const long total = (long)n_par * m2;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int lane2 = (int)(t % m2);
+    const int par = (int)(t / m2);
+    const int blk = par / nc3, rem = par - blk * nc3;
+    const int ix = rem % nc, jy = (rem / nc) % nc, kz = rem / (nc * nc);
+    double acc[Q][Q][Q];
+#pragma unroll
+    for (int j0 = 0; j0 < Q; j0++)
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) acc[j0][j1][j2] = 0.0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < F; i0++) {
+      double s2[Q][Q];
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) s2[j1][j2] = 0.0;
+#pragma unroll
+      for (int i1 = 0; i1 < F; i1++) {
+        double s1[Q];
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++) s1[j2] = 0.0;
+#pragma unroll
+        for (int i2 = 0; i2 < F; i2++) {
+          const long g = sf_fine_dof<P>(map_f, n_f, blk, ix, jy, kz, i0, i1, i2);
+          const double r = rf[g * m2 + lane2] * __ldg(invmult_par + g);
+#pragma unroll
+          for (int j2 = 0; j2 < Q; j2++) s1[j2] = fma(T.W[i2][j2], r, s1[j2]);
+        }
+#pragma unroll
+        for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+          for (int j2 = 0; j2 < Q; j2++) s2[j1][j2] = fma(T.W[i1][j1], s1[j2], s2[j1][j2]);
+      }
+#pragma unroll
+      for (int j0 = 0; j0 < Q; j0++)
+#pragma unroll
+        for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+          for (int j2 = 0; j2 < Q; j2++) acc[j0][j1][j2] = fma(T.W[i0][j0], s2[j1][j2], acc[j0][j1][j2]);
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < Q; j0++)
+#pragma unroll
+      for (int j1 = 0; j1 < Q; j1++)
+#pragma unroll
+        for (int j2 = 0; j2 < Q; j2++)
+          atomicAdd(rc + ((long)__ldg(map_c + (long)par * L + (j0 * Q + j1) * Q + j2) - 1) * m2 + lane2, acc[j0][j1][j2]);
+  }
+}
+
+inline unsigned grid_sf(long total) {
+  long g = (total + 127) / 128;
+  const long cap = 148L * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+template <int P>
+void prolong_sf_t(const TransferW &T, const int32_t *mf, const int32_t *mc, int nef, int nf, const D2 *xc, D2 *xf, int m, cudaStream_t s) {
+  const int n_par = nef / 8;
+  k_h1_prolong_sf<P><<<grid_sf((long)n_par * 2 * m), 128, 0, s>>>(T, mf, mc, n_par, nf, reinterpret_cast<const double *>(xc),
+                                                                   reinterpret_cast<double *>(xf), m);
+}
+template <int P>
+void restrict_sf_t(const TransferW &T, const int32_t *mf, const int32_t *mc, int nef, int nf, const double *w, const D2 *rf, D2 *rc, int m, cudaStream_t s) {
+  const int n_par = nef / 8;
+  k_h1_restrict_sf<P><<<grid_sf((long)n_par * 2 * m), 128, 0, s>>>(T, mf, mc, n_par, nf, w, reinterpret_cast<const double *>(rf),
+                                                                    reinterpret_cast<double *>(rc), m);
+}
+
 // Y[row][v] (+)= sum_k val[k] X[col[k]][v]: the nested-mesh transfers as explicit sparse matrices (real weights,
 // complex block vectors).  Prolongation: rows = fine dofs (1 - 27 entries each at p = 2), restriction = its
 // transpose: rows = coarse dofs gathering their fine neighbours - no atomics, every output written once, the
@@ -564,6 +716,7 @@ struct H1Level {
   DevBuf<int32_t> map_h1;
   DevBuf<int> cls;
   DevBuf<double> eps, cpar, diag, jac, invmult;
+  DevBuf<double> invmult_par;         // 1 / (number of parent-element positions holding the dof): sum-factorised restriction
   std::vector<double> eps_h;
   ElemData E{};
   double lmax = 0;
@@ -586,8 +739,11 @@ struct H1Level {
 };
 
 struct H1Multigrid {
+  int kind = 0;                       // coefficient of the level operators: 0 = eps (S0 of the projector), 1 = mu^-1 (auxiliary space)
+  int smooth_degree = 2;              // Chebyshev-Jacobi smoother degree (BLOCH_MG_SMOOTH_DEGREE / BLOCH_AUX_MG_DEGREE)
   std::deque<H1Level> lev;
   Transfer1D T;
+  TransferW TW;
   int m_alloc = 0;
   DevBuf<D2> z, pvec, qvec;           // PCG vectors on the fine level
   DevBuf<double> scal;                // rz | pq | rz_new | rr | alpha | beta  (m each) + 2m sums
@@ -624,10 +780,18 @@ static void alloc_work(H1Multigrid *mg, int m) {
   mg->zero_valid = false;
 }
 
-H1Multigrid *mg_create(bloch_handle_s *h) {
+void launch_csr_apply(const int *ptr, const int32_t *col, const double *val, const D2 *X, D2 *Y, long nrows, int m,
+                      int accumulate, cudaStream_t s) {
+  k_csr_apply<<<grid_for(nrows * m), TPB, 0, s>>>(ptr, col, val, X, Y, nrows, m, accumulate);
+  BLOCH_CUDA(cudaGetLastError());
+}
+
+H1Multigrid *mg_create(bloch_handle_s *h, int kind) {
   const int p = h->p, Q = p + 1;
   if (h->mesh.n_sub % 2 != 0 || h->mesh.n_sub < 2) return nullptr;   // no coarser nested mesh
   H1Multigrid *mg = new H1Multigrid();
+  mg->kind = kind;
+  mg->smooth_degree = kind == 1 ? (int)env_double("BLOCH_AUX_MG_DEGREE", 2.0) : (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
   cudaStream_t s = h->stream;
   // 1-D transfer tables
   for (int a = 0; a < 2; a++)
@@ -636,6 +800,8 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
       detail::lagrange(h->basis.l, 0.5 * (a + h->basis.l[i]), v, dv);
       for (int j = 0; j < Q; j++) mg->T.P[a][i][j] = std::fabs(v[j]) < 1e-15 ? 0.0 : v[j];
     }
+  for (int i = 0; i <= 2 * p; i++)
+    for (int j = 0; j < Q; j++) mg->TW.W[i][j] = i <= p ? mg->T.P[0][i][j] : mg->T.P[1][i - p][j];
   // level 0 = the handle's own mesh
   int n = h->mesh.n_sub;
   mg->lev.emplace_back();
@@ -751,6 +917,28 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
     h_sync(s);
     F.have_csr = true;
   }
+  // parent-position multiplicities for the sum-factorised restriction
+  for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
+    H1Level &F = mg->lev[l];
+    const std::vector<int32_t> &nat_f = l == 0 ? h->maps.h1 : F.maps.h1;
+    const long ne = l == 0 ? h->mesh.n_elem : F.mesh.n_elem;
+    const int LH = h->L_h1, nf = F.n, nc = nf / 2, nc3 = nc * nc * nc, FF = 2 * p + 1;
+    std::vector<double> cnt(F.N0, 0.0);
+    for (long par = 0; par < ne / 8; par++) {
+      const int blk = (int)(par / nc3), rem = (int)(par - (long)blk * nc3);
+      const int ix = rem % nc, jy = (rem / nc) % nc, kz = rem / (nc * nc);
+      for (int i0 = 0; i0 < FF; i0++)
+        for (int i1 = 0; i1 < FF; i1++)
+          for (int i2 = 0; i2 < FF; i2++) {
+            const int a0 = i0 > p, a1 = i1 > p, a2 = i2 > p;
+            const long e = (long)blk * nf * nf * nf + ((long)(2 * kz + a2) * nf + (2 * jy + a1)) * nf + 2 * ix + a0;
+            cnt[nat_f[(size_t)e * LH + (i0 - p * a0) + Q * ((i1 - p * a1) + Q * (i2 - p * a2))] - 1] += 1.0;
+          }
+    }
+    for (double &c : cnt) c = c > 0.0 ? 1.0 / c : 0.0;
+    F.invmult_par.upload(cnt, s);
+    h_sync(s);
+  }
   // multiplicity weights of every level that restricts (all but the coarsest)
   for (size_t l = 0; l + 1 < mg->lev.size(); l++) {
     H1Level &L = mg->lev[l];
@@ -766,6 +954,58 @@ H1Multigrid *mg_create(bloch_handle_s *h) {
 }
 
 void mg_destroy(H1Multigrid *mg) { delete mg; }
+
+long mg_level_size(H1Multigrid *mg, int level) { return level >= 0 && level < (int)mg->lev.size() ? mg->lev[level].N0 : -1; }
+
+// test hook: the transfer between level 0 and level 1 in each of its three implementations
+// (variant 0: explicit CSR matrices, 1: sum-factorised parent kernels, 2: element-wise kernels);
+// dir 0: y(fine) = P x(coarse), dir 1: y(coarse) = P^T x(fine)
+void mg_debug_transfer(H1Multigrid *mg, bloch_handle_s *h, int variant, int dir, const D2 *x, D2 *y, int m) {
+  if (mg->lev.size() < 2) throw std::invalid_argument("no coarse level");
+  H1Level &L = mg->lev[0], &C = mg->lev[1];
+  cudaStream_t s = h->stream;
+  const int32_t *map_f = h->d_map_h1.p, *map_c = C.map_h1.p;
+  const int nef = h->mesh.n_elem;
+  if (dir == 0) {
+    if (variant == 0) {
+      k_csr_apply<<<grid_for(L.N0 * m), TPB, 0, s>>>(L.P_ptr.p, L.P_col.p, L.P_val.p, x, y, L.N0, m, 0);
+    } else if (variant == 1) {
+      switch (h->p) {
+        case 1: prolong_sf_t<1>(mg->TW, map_f, map_c, nef, L.n, x, y, m, s); break;
+        case 2: prolong_sf_t<2>(mg->TW, map_f, map_c, nef, L.n, x, y, m, s); break;
+        case 3: prolong_sf_t<3>(mg->TW, map_f, map_c, nef, L.n, x, y, m, s); break;
+        default: prolong_sf_t<4>(mg->TW, map_f, map_c, nef, L.n, x, y, m, s); break;
+      }
+    } else {
+      switch (h->p) {
+        case 1: prolong_t<1>(mg->T, map_f, map_c, nef, L.n, x, y, m, s); break;
+        case 2: prolong_t<2>(mg->T, map_f, map_c, nef, L.n, x, y, m, s); break;
+        case 3: prolong_t<3>(mg->T, map_f, map_c, nef, L.n, x, y, m, s); break;
+        default: prolong_t<4>(mg->T, map_f, map_c, nef, L.n, x, y, m, s); break;
+      }
+    }
+  } else {
+    BLOCH_CUDA(cudaMemsetAsync(y, 0, sizeof(D2) * C.N0 * m, s));
+    if (variant == 0) {
+      k_csr_apply<<<grid_for(C.N0 * m), TPB, 0, s>>>(L.R_ptr.p, L.R_col.p, L.R_val.p, x, y, C.N0, m, 0);
+    } else if (variant == 1) {
+      switch (h->p) {
+        case 1: restrict_sf_t<1>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, x, y, m, s); break;
+        case 2: restrict_sf_t<2>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, x, y, m, s); break;
+        case 3: restrict_sf_t<3>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, x, y, m, s); break;
+        default: restrict_sf_t<4>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, x, y, m, s); break;
+      }
+    } else {
+      switch (h->p) {
+        case 1: restrict_t<1>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, x, y, m, s); break;
+        case 2: restrict_t<2>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, x, y, m, s); break;
+        case 3: restrict_t<3>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, x, y, m, s); break;
+        default: restrict_t<4>(mg->T, map_f, map_c, nef, L.n, L.invmult.p, x, y, m, s); break;
+      }
+    }
+  }
+  BLOCH_CUDA(cudaGetLastError());
+}
 
 static std::vector<double> cheb_coefs(double lmax, double ratio, int degree);
 
@@ -785,7 +1025,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     const HexMesh &mesh = l == 0 ? h->mesh : L.mesh;
     // coefficient: level 0 = the user's eps, coarser = mean over the 8 children
     if (l == 0) {
-      L.eps_h = h->eps;
+      L.eps_h = mg->kind == 1 ? h->muinv : h->eps;
     } else {
       const H1Level &F = mg->lev[l - 1];
       const int nf = F.n, nc = L.n, n3 = nf * nf * nf;
@@ -810,6 +1050,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     E.n_class = mesh.n_class;
     E.nk = nk;
     E.cpar = L.cpar.p;
+    if (l == 0 && mg->kind == 1) E.eps = h->d_muinv.p;   // stiffness coefficient slot of the scalar kernels
     if (l > 0) {
       E.cls = L.cls.p;
       E.eps = L.eps.p;
@@ -827,7 +1068,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
     L.have_S = !Sl.empty();
     if (L.have_S) L.Sloc.upload(Sl, s);
     L.lmax = 1.05 * bound;
-    L.cheb.upload(cheb_coefs(L.lmax, env_double("BLOCH_MG_SMOOTH_RATIO", 5.0), (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2)), s);
+    L.cheb.upload(cheb_coefs(L.lmax, env_double("BLOCH_MG_SMOOTH_RATIO", 5.0), mg->smooth_degree), s);
     if (l == nl - 1) L.cheb40.upload(cheb_coefs(L.lmax, 2000.0, 40), s);
     DevBuf<double> &dl = L.dloc;
     dl.upload(dloc, s);
@@ -1013,9 +1254,23 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   // explicit-matrix transfers win at orders 1-2 (measured: restrict 83 -> 45 us, prolong + add 79 -> 41 us on FCC
   // order 2 n_sub 8 x 160 columns); at order 3 the coarse rows of the restriction hold up to 343 entries and the
   // element-wise kernels are faster (BCC order 3 n_sub 8: projector 596 vs 696 ms per solve)
+  // default: the sum-factorised parent kernels (k_h1_*_sf: 2604 instead of 21952 multiply-adds per parent at order 3).
+  // BCC order 3 n_sub 8 warm solve 537 -> 399 ms (the element-wise restrict / prolong took 326 / 230 us per call on
+  // 16 columns, 32 % of the solve); FCC order 2 bench workload 50.1 (CSR) -> 52.0 k-points/s.  Order 4 spills, it keeps
+  // the element-wise kernels.
   static const double csr_env = env_double("BLOCH_MG_CSR_TRANSFER", -1.0);
-  const bool use_csr = csr_env < 0.0 ? h->p <= 2 : csr_env != 0.0;
-  if (use_csr && L.have_csr) {
+  static const double sf_env = env_double("BLOCH_MG_SF_TRANSFER", -1.0);
+  const bool use_sf = sf_env < 0.0 ? h->p <= 3 : sf_env != 0.0;
+  const bool use_csr = !use_sf && (csr_env < 0.0 ? h->p <= 2 : csr_env != 0.0);
+  if (use_sf) {
+    BLOCH_CUDA(cudaMemsetAsync(C.b.p, 0, sizeof(D2) * C.N0 * m, s));
+    switch (h->p) {
+      case 1: restrict_sf_t<1>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, L.r.p, C.b.p, m, s); break;
+      case 2: restrict_sf_t<2>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, L.r.p, C.b.p, m, s); break;
+      case 3: restrict_sf_t<3>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, L.r.p, C.b.p, m, s); break;
+      default: restrict_sf_t<4>(mg->TW, map_f, map_c, nef, L.n, L.invmult_par.p, L.r.p, C.b.p, m, s); break;
+    }
+  } else if (use_csr && L.have_csr) {
     k_csr_apply<<<grid_for(C.N0 * m), TPB, 0, s>>>(L.R_ptr.p, L.R_col.p, L.R_val.p, L.r.p, C.b.p, C.N0, m, 0);
   } else {
     BLOCH_CUDA(cudaMemsetAsync(C.b.p, 0, sizeof(D2) * C.N0 * m, s));
@@ -1029,7 +1284,15 @@ static void vcycle(H1Multigrid *mg, bloch_handle_s *h, int l, int m, int deg, do
   h->count_launch(2);
   vcycle(mg, h, l + 1, m, deg, ratio);
   // prolongation + correction
-  if (use_csr && L.have_csr) {
+  if (use_sf) {
+    switch (h->p) {
+      case 1: prolong_sf_t<1>(mg->TW, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      case 2: prolong_sf_t<2>(mg->TW, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      case 3: prolong_sf_t<3>(mg->TW, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+      default: prolong_sf_t<4>(mg->TW, map_f, map_c, nef, L.n, C.x.p, L.d.p, m, s); break;
+    }
+    k_add<<<grid_for(tot), TPB, 0, s>>>(L.x.p, L.d.p, tot);
+  } else if (use_csr && L.have_csr) {
     k_csr_apply<<<grid_for(tot), TPB, 0, s>>>(L.P_ptr.p, L.P_col.p, L.P_val.p, C.x.p, L.x.p, L.N0, m, 1);
   } else {
     switch (h->p) {
@@ -1142,7 +1405,7 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
   alloc_work(mg, m);
   H1Level &F = mg->lev[0];
   const long N0 = F.N0, tot = N0 * m;
-  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const int deg = mg->smooth_degree;
   const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
   ensure_zero_buffers(mg, h, m);
   double *part_rz = mg->part.p, *part_pq = part_rz + PCG_BLOCKS * m, *part_rr = part_pq + PCG_BLOCKS * m;
@@ -1256,7 +1519,7 @@ static int mg_solve_fused(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, 
 void mg_vcycle(H1Multigrid *mg, bloch_handle_s *h, const D2 *b, D2 *x, int m) {
   cudaStream_t s = h->stream;
   alloc_work(mg, m);
-  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const int deg = mg->smooth_degree;
   const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
   static const double fused_max = env_double("BLOCH_MG_FUSED_MAX_ENTRIES", 8.0e5);
   static const bool fused = env_double("BLOCH_MG_FUSED", 1.0) != 0.0;
@@ -1288,7 +1551,7 @@ int mg_solve(H1Multigrid *mg, bloch_handle_s *h, D2 *rhs, D2 *phi, int m, const 
   mg->zero_valid = false;   // this schedule leaves the operator-output buffers dirty
   H1Level &F = mg->lev[0];
   const long N0 = F.N0, tot = N0 * m;
-  const int deg = (int)env_double("BLOCH_MG_SMOOTH_DEGREE", 2);
+  const int deg = mg->smooth_degree;
   const double ratio = env_double("BLOCH_MG_SMOOTH_RATIO", 5.0);
   double *rz = mg->scal.p, *pq = rz + m, *rzn = pq + m, *rr = rzn + m, *alpha = rr + m, *beta = alpha + m;
   double *sums = beta + m;

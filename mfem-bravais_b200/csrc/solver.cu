@@ -334,6 +334,33 @@ __global__ void k_cheb3_first(const double *__restrict__ jac, const D2 *__restri
   }
 }
 
+// smoothing step of the auxiliary-space preconditioner: rr = r - q (q may be null: rr = r), d = c0 * jac .* rr,
+// x = d (acc == 0) or x += d; the residual rr is stored when r_out is given (Chebyshev smoothers of degree >= 2
+// continue with k_cheb_step on it)
+__global__ void k_sm_first(const double *__restrict__ jac, const D2 *__restrict__ r, const D2 *__restrict__ q,
+                           D2 *__restrict__ r_out, D2 *__restrict__ d, D2 *__restrict__ x, double c0, long n, int m,
+                           int nk, int cpk, int acc) {
+  const long total = n * m;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long row = t / m;
+    const double s = c0 * jac[row * nk + (int)(t - row * m) / cpk];
+    D2 rr = r[t];
+    if (q) { const D2 qq = q[t]; rr.x -= qq.x; rr.y -= qq.y; }
+    if (r_out) r_out[t] = rr;
+    const D2 o = make_double2(s * rr.x, s * rr.y);
+    if (d) d[t] = o;
+    if (acc) { D2 xx = x[t]; xx.x += o.x; xx.y += o.y; x[t] = xx; }
+    else x[t] = o;
+  }
+}
+// rr = r - q
+__global__ void k_sub(const D2 *__restrict__ r, const D2 *__restrict__ q, D2 *__restrict__ rr, long total) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const D2 a = r[t], b = q[t];
+    rr[t] = make_double2(a.x - b.x, a.y - b.y);
+  }
+}
+
 // jac[i] = 1 / (dA[i] + sigma * dM[i])   (elementwise over the [n][nk] tables)
 __global__ void k_make_jacobi(const double *dA, const double *dM, double sigma, double *jac, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
@@ -723,6 +750,53 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     prof_end(3);
   };
 
+  // Auxiliary-space preconditioner (what AMS does for the reference, maxwell_bloch.cpp:492-517): symmetric
+  // multiplicative combination of a Chebyshev-Jacobi smoother on A + sigma M with the nodal-space correction
+  // Pi B Pi^H (aux.cu: one H1 multigrid V-cycle per Cartesian component):
+  //     x = S r;  x += Pi B Pi^H (r - (A + sigma M) x);  x += S (r - (A + sigma M) x)
+  // The gradient part of AMS is not needed: the projector that follows removes gradients exactly.  Outer iteration
+  // counts no longer grow with n_sub / order, and one application costs 2 + 2 (s - 1) ND applies + 3 scalar V-cycles
+  // instead of 23 ND applies.
+  const bool aux_on = prob.constrained && aux && use_aux && mg && use_mg;
+  const int sm_degree = std::max(1, (int)env_double("BLOCH_AUX_SMOOTH_DEGREE", 2.0));
+  const double sm_ratio = env_double("BLOCH_AUX_SMOOTH_RATIO", 4.0);
+  auto precondition_aux = [&](const D2 *r_in, D2 *out) {
+    prof_begin(3);
+    prof_in_precond = true;
+    const unsigned g = grid_for(Nl * gs);
+    const double lo = lmax / sm_ratio;
+    const double th = 0.5 * (lmax + lo), de = 0.5 * (lmax - lo), s1 = th / de;
+    // x (+)= S b with b = r_in - q (q == null: b = r_in); uses Tq (residual), Dd (direction), Qb (operator output)
+    auto smooth = [&](const D2 *q, int acc) {
+      if (sm_degree == 1) {
+        k_sm_first<<<g, TPB, 0, s>>>(d_jac.p, r_in, q, nullptr, nullptr, out, 1.0 / th, Nl, gs, K, mb, acc);
+        count_launch();
+        return;
+      }
+      k_sm_first<<<g, TPB, 0, s>>>(d_jac.p, r_in, q, Tq.p, Dd.p, out, 1.0 / th, Nl, gs, K, mb, acc);
+      count_launch();
+      double rho = 1.0 / s1;
+      for (int k = 1; k < sm_degree; k++) {
+        op(Dd.p, gs, Qb.p, gs, gs, 1.0, sigma);
+        const double rho_n = 1.0 / (2.0 * s1 - rho);
+        k_cheb_step<<<g, TPB, 0, s>>>(d_jac.p, Qb.p, Tq.p, Dd.p, out, rho_n * rho, 2.0 * rho_n / de, Nl, gs, K, mb);
+        count_launch();
+        rho = rho_n;
+      }
+    };
+    smooth(nullptr, 0);
+    op(out, gs, Qb.p, gs, gs, 1.0, sigma);
+    k_sub<<<g, TPB, 0, s>>>(r_in, Qb.p, Tq.p, Nl * gs);
+    count_launch();
+    prof_in_precond = false;
+    aux_correct(aux, this, Tq.p, out, gs);
+    prof_in_precond = true;
+    op(out, gs, Qb.p, gs, gs, 1.0, sigma);
+    smooth(Qb.p, 1);
+    prof_in_precond = false;
+    prof_end(3);
+  };
+
   // ---- Rayleigh-Ritz of every k-point on its first kc basis columns ----
   std::vector<D2> hGA((size_t)K * kmax * kmax), hGM((size_t)K * kmax * kmax), hC((size_t)K * kmax * mb);
   std::vector<double> lam((size_t)gs, 0.0), rn((size_t)gs, 0.0);
@@ -968,7 +1042,8 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     if (all_done) break;
     // W = P_proj T R
     t0 = tick();
-    precondition(R.p, Wc.p);
+    if (aux_on) precondition_aux(R.p, Wc.p);
+    else precondition(R.p, Wc.p);
     t_pre += since(t0);
     t0 = tick();
     int its = 0;

@@ -425,6 +425,30 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_debug_apply_h1op(self._h, mode, dptr(x2), dptr(y), x2.shape[0]))
         return y[0] if x.ndim == 1 else y
 
+    def debug_aux(self, mode, x):
+        """Pieces of the auxiliary-space preconditioner (bloch_debug_apply_aux): 0 = Pi, 1 = Pi^T, 2 = V-cycles."""
+        x = np.ascontiguousarray(x, float)
+        x2 = x.reshape(1, -1) if x.ndim == 1 else x
+        nout = self.N if mode == 0 else 3 * self.N_h1
+        y = np.zeros((x2.shape[0], 2 * nout))
+        check(self._L.bloch_debug_apply_aux(self._h, mode, dptr(x2), dptr(y), x2.shape[0]))
+        return y[0] if x.ndim == 1 else y
+
+    def debug_mg_transfer(self, variant, direction, x):
+        """Level 0 <-> 1 transfer of the H1 multigrid (bloch_debug_mg_transfer); x: [nvec, 2 n_in] in [re; im] layout."""
+        nc = C.c_int64()
+        check(self._L.bloch_debug_mg_transfer(self._h, variant, direction, None, None, 0, C.byref(nc)))
+        x = np.ascontiguousarray(x, float)
+        nout = self.N_h1 if direction == 0 else nc.value
+        y = np.zeros((x.shape[0], 2 * nout))
+        check(self._L.bloch_debug_mg_transfer(self._h, variant, direction, dptr(x), dptr(y), x.shape[0], C.byref(nc)))
+        return y
+
+    def mg_coarse_size(self):
+        nc = C.c_int64()
+        check(self._L.bloch_debug_mg_transfer(self._h, 0, 0, None, None, 0, C.byref(nc)))
+        return int(nc.value)
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         check(self._L.bloch_debug_fp64_peak(self._h, C.byref(v)))

@@ -484,6 +484,25 @@ def _assemble_set(gr, sr, gc, sc, nrow, ncol, elmats, cls):
     return A
 
 
+def nodal_interpolation(spaces):
+    """Pi: (H1_p)^3 -> ND_p, the nodal interpolation of continuous vector fields - the 'Pi' matrix HypreAMS builds
+    for the preconditioner the reference creates at maxwell/maxwell_bloch.cpp:492-517 (MFEM: DiscreteLinearOperator
+    with an IdentityInterpolator).  ND dof functional: v -> (J t) . v(x_node).  Columns: component d of H1 node g
+    at d * n_h1 + g.  With a constant vector zeta, Pi [zeta_x phi; zeta_y phi; zeta_z phi] is the reference's
+    Z01 phi (pfem_extras_bloch.cpp:182-258) - the identity the CPU test pins this matrix with."""
+    ref, mesh = spaces.ref, spaces.mesh
+    h1v, _ = ref.h1_shapes(ref.nd_nodes)            # [n_nd_loc, n_h1_loc]
+    em = []
+    for J in mesh.J:
+        E = np.zeros((ref.n_nd, 3 * ref.n_h1))
+        for d in range(3):
+            E[:, d * ref.n_h1:(d + 1) * ref.n_h1] = h1v * J[d, ref.nd_comp][:, None]
+        em.append(E)
+    gc = np.concatenate([spaces.h1_gid + d * spaces.n_h1 for d in range(3)], axis=1)
+    return _assemble_set(spaces.nd_gid, spaces.nd_sign, gc, np.ones_like(gc, dtype=float), spaces.n_nd,
+                         3 * spaces.n_h1, np.array(em), mesh.cls)
+
+
 class BlochOperators:
     """Assembled operators of MaxwellBlochWaveEquation::Setup for one (mesh, p, eps, muinv)
     and, per kappa, the beta/zeta dependent ones."""

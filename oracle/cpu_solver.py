@@ -95,7 +95,7 @@ class Csr:
 
 
 def lobpcg_cpu(ops, nb, tol, max_iter=2000, sigma_scale=1.0, cheb_degree=24, cheb_ratio=300.0,
-               proj_tol=None, seed=1, verbose=False, timing=None, X0=None):
+               proj_tol=None, seed=1, verbose=False, timing=None, X0=None, precond_factory=None):
     """Projected, preconditioned complex block LOBPCG on the assembled operators of `ops` (one kappa).
     X0: starting block (warm start from the previous k-point) or None (seeded random).
     Returns (eigenvalues[nb], iterations, counts, X) with X the final block (for the next warm start)."""
@@ -150,6 +150,9 @@ def lobpcg_cpu(ops, nb, tol, max_iter=2000, sigma_scale=1.0, cheb_degree=24, che
                 x += d
             rho = rho_n
         return x
+
+    if precond_factory is not None:     # experiments with other preconditioners (scratch/aux_proto.py)
+        precond = precond_factory(dict(ops=ops, Ash=Ash, sigma=sigma, jac=jac, cheb=precond, counts=counts))
 
     def project(X, rel):
         rhs = np.ascontiguousarray(GH(M(X)))

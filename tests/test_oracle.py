@@ -139,3 +139,31 @@ def test_field_average_forms_on_constant_fields(name):
         b_rt[s.rt_gid[e]] = s.rt_sign[e] * (eye[s.ref.rt_comp] @ (np.linalg.det(J) * np.linalg.inv(J) @ c))  # n . adj(J) c
     assert np.allclose(L["E"] @ e_nd, mesh.volume * c) and np.allclose(L["B"] @ b_rt, mesh.volume * c)
     assert np.allclose(L["D"] @ e_nd, (eps * vol_e).sum() * c) and np.allclose(L["H"] @ b_rt, (mui * vol_e).sum() * c)
+
+
+@pytest.mark.parametrize("name,n,p", [("CUB", 2, 1), ("FCC", 2, 2), ("BCC", 1, 3), ("HEX", 2, 2)])
+def test_nodal_interpolation_matrix(name, n, p):
+    """Pi: (H1)^3 -> ND of the AMS-type preconditioner (maxwell_bloch.cpp:492-517), pinned by exact identities:
+    Pi (zeta phi) = Z01 phi (the reference's zeta-interpolation of the projector, pfem_extras_bloch.cpp:182-258),
+    constant fields are curl free at Gamma, and their M-norm is the eps-weighted cell volume."""
+    from oracle.bloch_oracle import nodal_interpolation
+    lat = Lattice(name)
+    mesh = Mesh(lat, n)
+    s = Spaces(mesh, p)
+    rng = np.random.default_rng(5)
+    eps = rng.uniform(1, 10, mesh.ne)
+    ops = BlochOperators(s, eps)
+    Pi = nodal_interpolation(s)
+    assert Pi.shape == (s.n_nd, 3 * s.n_h1)
+    kappa = np.array([0.7, -1.1, 0.4])
+    ops.set_kappa(kappa)
+    phi = rng.uniform(-1, 1, s.n_h1)
+    assert np.allclose(Pi @ np.concatenate([z * phi for z in ops.zeta]), ops.Z01 @ phi, atol=1e-13)
+    ops.set_kappa(np.zeros(3))
+    vol_eps = float(np.sum(eps * np.abs(np.linalg.det(mesh.J))[mesh.cls]))
+    for d in range(3):
+        c = np.zeros(3 * s.n_h1)
+        c[d * s.n_h1:(d + 1) * s.n_h1] = 1.0
+        v = Pi @ c
+        assert np.abs(ops.T12 @ v).max() < 1e-12                    # curl of a constant field
+        assert abs(v @ (ops.M1 @ v) - vol_eps) < 1e-11 * vol_eps    # |e_d|^2 integrated with eps
