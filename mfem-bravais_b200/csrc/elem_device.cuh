@@ -271,5 +271,113 @@ __device__ __forceinline__ double s0_item(const Tabs &T, const double *cp, doubl
   return dot;
 }
 
+// ---- S0 element operator with the real and the imaginary part of an (element, vector) item in ADJACENT LANES ----
+// Every tensor contraction of S0_e is complex-by-real, so both parts run the same real code; only the Bloch terms
+// -i kh couple them (partner value by SHFL.BFLY 1).  Per lane: the Q^3 nodal values of its part in a lane-private
+// shared-memory column (entry k at sin[k * STRIDE], overwritten by the mode-space transform) and Q^3 accumulators in
+// registers - half the registers of s0_item, which is what makes order 3 fit (64 accumulators).
+// sgn = +1 for the real lane, -1 for the imaginary lane.  All 32 lanes of the warp must call it.
+// T: a SHARED-MEMORY copy of the 1-D tables (st_TI[r][j], st_Dt[a][t], st_om[i], rows of kMaxP + 1): as kernel
+// parameters they arrive through LDC into registers, ptxas hoists those loads and order 3 spills; shared-memory
+// loads stay behind the compiler fences below.
+struct PairTabs { double TI[kMaxP + 1][kMaxP + 1], Dt[kMaxP][kMaxP + 1], om[kMaxP + 1]; };
+template <int P, int STRIDE>
+__device__ __forceinline__ void s0_pair(const PairTabs &T, const double *cp, double eps, double sgn, double *sin,
+                                        double (&out)[(P + 1) * (P + 1) * (P + 1)]) {
+  constexpr int Q = P + 1;
+  auto IDX = [](int i0, int i1, int i2) { return (i0 * Q + i1) * Q + i2; };
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int sd = d == 0 ? Q * Q : (d == 1 ? Q : 1);
+    const int s1 = d == 0 ? Q : Q * Q, s2 = d == 2 ? Q : 1;
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) {
+        const int base = a * s1 + b * s2;
+        double in[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) in[j] = sin[(base + j * sd) * STRIDE];
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < Q; j++) acc = fma(T.TI[r][j], in[j], acc);
+          sin[(base + r * sd) * STRIDE] = acc;
+        }
+        asm volatile("" ::: "memory");
+      }
+  }
+  const double kh[3] = {sgn * cp[0], sgn * cp[1], sgn * cp[2]};
+  const double *H = cp + 12;
+#pragma unroll
+  for (int k = 0; k < Q * Q * Q; k++) out[k] = 0.0;
+#pragma unroll
+  for (int i0 = 0; i0 < Q; i0++)
+#pragma unroll
+    for (int i1 = 0; i1 < Q; i1++)
+#pragma unroll
+      for (int i2 = 0; i2 < Q; i2++) {
+        const int i[3] = {i0, i1, i2};
+        double eps_here = eps;
+        asm volatile("" : "+d"(eps_here));     // opaque per point: the Q^3 weights are not precomputed into registers
+        const double w = eps_here * T.om[i0] * T.om[i1] * T.om[i2];
+        const double centre_other = __shfl_xor_sync(0xffffffffu, sin[IDX(i0, i1, i2) * STRIDE], 1);
+        double F[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          F[d] = 0.0;
+          if (i[d] < P) {
+            F[d] = kh[d] * centre_other;          // (-i kh u): re <- +kh im, im <- -kh re
+#pragma unroll
+            for (int t = 0; t < Q; t++) {
+              int j[3] = {i0, i1, i2};
+              j[d] = t;
+              F[d] = fma(T.Dt[i[d]][t], sin[IDX(j[0], j[1], j[2]) * STRIDE], F[d]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (i[c] < P) {
+            const double mf = w * (H[3 * c] * F[0] + H[3 * c + 1] * F[1] + H[3 * c + 2] * F[2]);
+            const double mf_other = __shfl_xor_sync(0xffffffffu, mf, 1);
+#pragma unroll
+            for (int t = 0; t < Q; t++) {
+              int j[3] = {i0, i1, i2};
+              j[c] = t;
+              out[IDX(j[0], j[1], j[2])] = fma(T.Dt[i[c]][t], mf, out[IDX(j[0], j[1], j[2])]);
+            }
+            out[IDX(i0, i1, i2)] = fma(-kh[c], mf_other, out[IDX(i0, i1, i2)]);   // (+i kh mf): re <- -kh im, im <- +kh re
+          }
+        }
+        // keeps ptxas from hoisting the shared-memory loads of later points above this one (at order 3 it otherwise
+        // pulls hundreds of them to the top: 255 registers and spills)
+        asm volatile("" ::: "memory");
+      }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int sd = d == 0 ? Q * Q : (d == 1 ? Q : 1);
+    const int s1 = d == 0 ? Q : Q * Q, s2 = d == 2 ? Q : 1;
+#pragma unroll
+    for (int a = 0; a < Q; a++)
+#pragma unroll
+      for (int b = 0; b < Q; b++) {
+        const int base = a * s1 + b * s2;
+        double in[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) in[j] = out[base + j * sd];
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < Q; j++) acc = fma(T.TI[j][r], in[j], acc);
+          out[base + r * sd] = acc;
+        }
+        asm volatile("" ::: "memory");
+      }
+  }
+}
+
 }  // namespace dev
 }  // namespace bloch_b200

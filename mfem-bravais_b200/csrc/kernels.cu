@@ -636,6 +636,60 @@ k_h1_s0_item(const __grid_constant__ Tabs T, const ElemData E, const double2 *__
   }
 }
 
+// The same operator with one LANE PAIR per (element, vector) item (s0_pair: real part in the even lane, imaginary part
+// in the odd lane, Q^3 real accumulators per lane): the register-resident form for order 3, where the complex item
+// of k_h1_s0_item (2 Q^3 = 128 accumulators) does not fit and the cooperative tile kernel k_h1_op<3> reaches 20 % of
+// the fp64 pipe.  Gather / scatter addresses of a pair are adjacent doubles (coalesced 8-byte accesses).
+// index load that the compiler neither hoists nor shares between the gather and the scatter (as __ldg it keeps all
+// Q^3 indices of the element live across the whole item: 64 registers at order 3)
+__device__ __forceinline__ int ld_index_once(const int32_t *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <int P, int NT>
+__global__ void __launch_bounds__(NT)
+k_h1_s0_pair(const __grid_constant__ Tabs T, const ElemData E, const double *__restrict__ X, double *__restrict__ Y,
+             int m, int ldx, int ldy, long n_items, double ca) {
+  using D = Dim<P>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *scol = reinterpret_cast<double *>(smem_raw) + threadIdx.x;
+  PairTabs *sT = reinterpret_cast<PairTabs *>(reinterpret_cast<double *>(smem_raw) + D::LH1 * NT);
+  double *sCP = reinterpret_cast<double *>(sT + 1);
+  for (int i = threadIdx.x; i < cpar_doubles(E); i += NT) sCP[i] = E.cpar[i];
+  for (int i = threadIdx.x; i < (kMaxP + 1) * (kMaxP + 1); i += NT) (&sT->TI[0][0])[i] = (&T.TI[0][0])[i];
+  for (int i = threadIdx.x; i < kMaxP * (kMaxP + 1); i += NT) (&sT->Dt[0][0])[i] = (&T.Dt[0][0])[i];
+  for (int i = threadIdx.x; i < kMaxP + 1; i += NT) sT->om[i] = T.om[i];
+  __syncthreads();
+  const long t = (long)blockIdx.x * NT + threadIdx.x;
+  const bool live = t < 2 * n_items;
+  const long item = live ? t >> 1 : 0;              // idle lanes of the last warp shadow item 0 and store nothing
+  const int part = (int)(t & 1);
+  const int e = (int)(item / m);
+  const int v = (int)(item - (long)e * m);
+  const int32_t *mh = E.map_h1 + (long)e * D::LH1;
+  // gather / scatter in groups of 16 entries behind compiler fences: fully hoisted, the 64 index + address + value
+  // registers of order 3 would not fit next to the accumulators
+  constexpr int GR = 16;
+#pragma unroll
+  for (int k0 = 0; k0 < D::LH1; k0 += GR) {
+#pragma unroll
+    for (int k = k0; k < (k0 + GR < D::LH1 ? k0 + GR : D::LH1); k++)
+      scol[k * NT] = X[2 * ((long)(ld_index_once(mh + k) - 1) * ldx + v) + part];
+    asm volatile("" ::: "memory");
+  }
+  double out[D::LH1];
+  s0_pair<P, NT>(*sT, sCP + kClassParDoubles * vclass(E, E.cls[e], v), ca * E.eps[e], part ? -1.0 : 1.0, scol, out);
+  if (!live) return;
+#pragma unroll
+  for (int k0 = 0; k0 < D::LH1; k0 += GR) {
+#pragma unroll
+    for (int k = k0; k < (k0 + GR < D::LH1 ? k0 + GR : D::LH1); k++)
+      atomicAdd(Y + 2 * ((long)(ld_index_once(mh + k) - 1) * ldy + v) + part, out[k]);
+    asm volatile("" ::: "memory");
+  }
+}
+
 // y[g][v] = sum over the local copies of H1 dof g of the E-vector Z (ptr/loc: dof -> 1-based positions e*L + k)
 __global__ void k_h1_reduce(const int *__restrict__ ptr, const int32_t *__restrict__ loc,
                             const double2 *__restrict__ Z, double2 *__restrict__ Y, long n, int m) {
@@ -697,6 +751,24 @@ cudaError_t h1_op_t(int mode, const Tabs &T, const ElemData &E, const double2 *x
         k_h1_s0_item<P, NT, true><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, ca);
       else
         k_h1_s0_item<P, NT, false><<<(unsigned)((n_items + NT - 1) / NT), NT, sm, s>>>(T, Ek, x, y, nvec, ldx, ldy, n_items, ca);
+      return cudaGetLastError();
+    }
+  }
+  if constexpr (P == 3) {
+    static const int pair_kernel = [] { const char *e = std::getenv("BLOCH_H1_PAIR"); return e ? std::atoi(e) : 1; }();
+    if (mode == 3 && cm == 0.0 && pair_kernel) {
+      constexpr int NT = 64;
+      const size_t sm = (size_t)D::LH1 * NT * sizeof(double) + sizeof(PairTabs) +
+                        (size_t)E.nk * E.n_class * kClassParDoubles * sizeof(double);
+      static bool attr3_of[kMaxDevices] = {};
+      bool &attr3 = attr3_of[current_device_slot()];
+      if (!attr3) {
+        cudaError_t err = cudaFuncSetAttribute(k_h1_s0_pair<P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (err != cudaSuccess) return err;
+        attr3 = true;
+      }
+      k_h1_s0_pair<P, NT><<<(unsigned)((2 * n_items + NT - 1) / NT), NT, sm, s>>>(
+          T, Ek, reinterpret_cast<const double *>(x), reinterpret_cast<double *>(y), nvec, ldx, ldy, n_items, ca);
       return cudaGetLastError();
     }
   }

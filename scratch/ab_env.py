@@ -5,20 +5,19 @@ T, B, K = (sys.argv[1:4] + ["2", "5", "20"])[:3] if len(sys.argv) >= 4 else ("2"
 SETTINGS = [
     {},
     {"BLOCH_MG_SMOOTH_DEGREE": "1"},
-    {"BLOCH_MG_SMOOTH_DEGREE": "3"},
-    {"BLOCH_MG_FUSED_MAX_ENTRIES": "4e6"},
-    {"BLOCH_MG_FUSED_MAX_ENTRIES": "4e6", "BLOCH_H1_EVEC": "0"},
-    {"BLOCH_MG_FUSED_MAX_ENTRIES": "4e6", "BLOCH_H1_EVEC_MAX_ELEMS": "1000000"},
-    {"BLOCH_RR_THREADS": "1"},
-    {"BLOCH_RR_THREADS": "8"},
-    {"BLOCH_CHEB_DEGREE": "16"},
-    {"BLOCH_CHEB_DEGREE": "32"},
-    {"BLOCH_REFRESH_EVERY": "2"},
+    {"BLOCH_LIFT_PROJ_TOL": "0.25"},
+    {"BLOCH_LIFT_X_TOL": "0.25"},
+    {"BLOCH_LIFT_PROJ_TOL": "0.25", "BLOCH_LIFT_X_TOL": "0.25"},
     {"BLOCH_GUARD": "4"},
-    {"BLOCH_LIFT": "0"},
     {"BLOCH_LIFT_TAU": "4"},
-    {"BLOCH_LIFT_PROJ_TOL": "0.3"},
+    {"BLOCH_LIFT_TAU": "16"},
+    {"BLOCH_AUX_SMOOTH_RATIO": "8"},
+    {"BLOCH_AUX_SMOOTH_DEGREE": "3"},
+    {"BLOCH_SIGMA_SCALE": "0.25"},
+    {},
 ]
+if os.environ.get("AB_SETTINGS"):
+    SETTINGS = json.loads(os.environ["AB_SETTINGS"])
 for st in SETTINGS:
     env = dict(os.environ); env.update(st)
     p = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--no-roofline", "--no-n16", "--streams", T, "--batch", B,
