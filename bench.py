@@ -420,6 +420,8 @@ def run_b200(args):
         "config": workload_config(args, N, nk),
         "impl_config": {"handles_per_gpu": T, "k_points_batched_per_handle": B, "slots": T * B,
                         "padded_solves": int(res["wasted"]), "rounds": int(res["rounds"]),
+                        "preconditioner": ("chebyshev-jacobi degree 24" if os.environ.get("BLOCH_PRECOND") == "cheb" else
+                                           "auxiliary space: Chebyshev(2)-Jacobi smoother + Pi (H1)^3 multigrid V-cycles"),
                         "warmup_solves": "each of the %d slots solves the half-step predecessor of its first timed "
                                          "k-point (not in the timed set) before every timed region" % n_warm},
         "e2e": {"value": total_steps / (ms_e2e * 1e-3), "unit": "k-points/s",

@@ -1107,7 +1107,21 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
           const D2 a = A[(size_t)i * w + k * n + j], at = A[(size_t)j * w + k * n + i];
           Am[(size_t)i * n + j] = 0.5 * dense::cplx(a.x + at.x, a.y - at.y);
         }
-      if (h->betas[k] == 0.0)   // singular on constants: lift that single mode
+      if (mg->kind == 1) {
+        // auxiliary-space hierarchy: the ND problem it preconditions is A + sigma M, whose auxiliary operator is
+        // L + sigma * mass.  The mass term only matters on the constant mode (eigenvalue |kappa|^2 of L against
+        // >= (2 pi / a)^2 for every other mode), so it is added there alone, as the rank-one term
+        // sigma * mass(1, 1) / n^2 * 1 1^T on the coarsest level: without it the correction Pi B Pi^H amplifies the
+        // near-constant fields by 1 / |kappa|^2 next to Gamma (CUB order 1 n_sub 16 at kappa = 0.01 (1,1,1):
+        // 20 outer iterations against 9) and is singular at Gamma itself.
+        const double vol23 = std::cbrt(h->mesh.volume) * std::cbrt(h->mesh.volume);
+        double eps_mean = 0.0;
+        for (double e : h->eps) eps_mean += e;
+        eps_mean /= (double)h->eps.size();
+        const double lift = env_double("BLOCH_SIGMA_SCALE", 1.0) / vol23 * h->mesh.volume * eps_mean / ((double)n * n);
+        for (int i = 0; i < n; i++)
+          for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += lift;
+      } else if (h->betas[k] == 0.0)   // singular on constants: lift that single mode
         for (int i = 0; i < n; i++)
           for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += tr / ((double)n * n);
       dense::Mat Lc = Am;
