@@ -18,9 +18,9 @@ for row in csv.DictReader(lines):
     agg[key][1] += v
 tot = sum(v[1] for v in agg.values())
 out = ["# ncu launch list, round 2\n",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 9000 -c 8000 --csv python bench.py --steps 20 --warmup 5 --streams 1 --batch 10 --no-cpu-baseline --no-roofline --no-n16`",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 30000 -c 4000 --csv python bench.py --steps 20 --warmup 5 --streams 1 --batch 10 --no-cpu-baseline --no-roofline --no-n16`",
        "(FCC order 2, n_sub 8, N = 49152, ONE handle iterating 10 k-points together = 160-column block vectors; window inside the timed sweep;",
-       "per-launch times are cold-cache and serialised: compare SHARES.  8000 launches = %.1f ms of kernel time.)\n" % (tot / 1e3),
+       "per-launch times are cold-cache and serialised: compare SHARES.  final round-2 code: auxiliary-space preconditioner, sum-factorised transfers.  The window's launches = %.1f ms of kernel time.)\n" % (tot / 1e3),
        "| kernel | grid | launches | total us | avg us | share |\n|---|---|---|---|---|---|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("| `%s` | %s | %d | %.1f | %.2f | %.1f %% |" % (k[0][:70], k[1], v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
@@ -73,5 +73,31 @@ for f in ["bench_r2.json", "apply_study_r2.json", "bench_reference_r2.json", "co
           "bench_4gpu_r2.json", "bench_8gpu_r2.json", "hex_n1.json", "hex_n2.json", "hex_n4.json", "hex_n8.json", "tb_scan.log", "ab_env_2_5.log"]:
     if os.path.exists(G + f):
         shutil.copy(G + f, "profiles/" + (f if "r2" in f else f.replace(".json", "_r2.json").replace(".log", "_r2.log")))
+# ---- ncu --set full of the kernels added with the auxiliary-space preconditioner ----
+want2 = want + ["launch__grid_size", "launch__block_size", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+md = ["# ncu --set full captures: sum-factorised multigrid transfers and the order-3 lane-pair S0 kernel, round 2\n",
+      "`NCU_RANGE=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:<kernel> -c <n> python scratch/solve_profile.py BCC 8 3`",
+      "(third, warm solve of BCC order 3 n_sub 8, N = 663552, 16 columns; the FCC capture: `scratch/batch_profile.py 8 10`, 160 columns).",
+      "Of the captured launches the one with the largest grid (the fine level) is tabulated.\n"]
+import glob
+def raw_all(rep):
+    r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(r.splitlines()))
+    return [dict(zip(rows[0], zip(row, rows[1]))) for row in rows[2:]]
+for rep in sorted(glob.glob(G + "prof_k_h1_*_r2.ncu-rep")):
+    ms = raw_all(rep)
+    if not ms:
+        continue
+    m = max(ms, key=lambda d: float(d["launch__grid_size"][0].replace(",", "")))
+    md.append("## %s  (`%s`)\n\n| metric | value | unit |\n|---|---|---|" % (m["Kernel Name"][0][:80].replace("void ", "").replace("<unnamed>::", ""), os.path.basename(rep)))
+    for k in want2:
+        if k in m:
+            md.append("| %s | %s | %s |" % (k, m[k][0], m[k][1]))
+    md.append("")
+open("profiles/ncu_mg_aux_r2.md", "w").write("\n".join(md) + "\n")
+for src, dst in [("aux_cmp_final.json", "aux_cmp_r2.json"), ("small_kappa_r2.log", "small_kappa_r2.log"), ("ab_env_aux_r2.log", "ab_env_aux_r2.log"),
+                 ("ab_env_mgdeg_r2.log", "ab_env_mgdeg_r2.log")]:
+    if os.path.exists(G + src):
+        shutil.copy(G + src, "profiles/" + dst)
 print(open("profiles/launches_r2.md").read()[:1800])
 print(json.dumps(traffic, indent=1))
