@@ -141,6 +141,8 @@ struct bloch_handle_s {
   bloch_b200::DevBuf<int> d_cls;
   bloch_b200::DevBuf<double> d_eps, d_muinv, d_cpar;
   bloch_b200::DevBuf<int32_t> d_map_nd, d_map_h1, d_map_rt;
+  bloch_b200::DevBuf<int32_t> d_shared_rows; // ND dofs that are NOT interior to an element (rows the apply reduces into)
+  long n_shared_rows = 0;
   bloch_b200::DevBuf<int> d_tp_ptr;          // transpose of map_nd: dof -> its local copies
   bloch_b200::DevBuf<int32_t> d_tp_loc;      // signed 1-based positions e*L_nd + j
   bloch_b200::DevBuf<D2> d_evec;             // E-vector of the atomic-free apply

@@ -806,6 +806,24 @@ cudaError_t curl_t(const Tabs &T, const ElemData &E, const double2 *x, int ldx, 
 
 }  // namespace
 
+namespace {
+__global__ void k_clear_rows(double2 *__restrict__ y, int ldy, int nvec, const int32_t *__restrict__ rows, long n_rows) {
+  const long total = n_rows * nvec;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long r = t / nvec;
+    y[(long)__ldg(rows + r) * ldy + (int)(t - r * nvec)] = make_double2(0.0, 0.0);
+  }
+}
+}  // namespace
+cudaError_t launch_clear_rows(double2 *y, int ldy, int nvec, const int32_t *rows, long n_rows, cudaStream_t s) {
+  const long total = n_rows * nvec;
+  long g = (total + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  k_clear_rows<<<(unsigned)g, 256, 0, s>>>(y, ldy, nvec, rows, n_rows);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const double2 *x, int ldx,
                             double2 *y, int ldy, int nvec, double ca, double cm, cudaStream_t s,
                             double2 *z) {
@@ -815,6 +833,10 @@ cudaError_t launch_nd_apply(int p, const Tabs &T, const ElemData &E, const doubl
     if (err != cudaSuccess || launched) return err;
     err = launch_nd_item(p, T, E, x, ldx, y, ldy, nvec, ca, cm, s, &launched);
     if (err != cudaSuccess || launched) return err;
+    if (E.fresh_y && E.partial_clear) {   // the kernel below reduces into every row: clear the interior rows as well
+      err = cudaMemset2DAsync(y, sizeof(double2) * ldy, 0, sizeof(double2) * nvec, (size_t)E.n_rows_y, s);
+      if (err != cudaSuccess) return err;
+    }
   }
   static int variant = -1;
   if (variant < 0) { const char *e = std::getenv("BLOCH_ND_WARPS"); variant = e ? std::atoi(e) : 0; }

@@ -53,6 +53,11 @@ struct ElemData {            // device pointers, element order = mesh order
   // other element) are then written with plain stores instead of fp64 reductions: no read-for-ownership of those
   // lines, 3p(p-1)^2 fewer reductions per element (25 % of them at p = 3).  0: y += (accumulating launches).
   int fresh_y = 0;
+  // 1 (only with fresh_y): the caller cleared just the rows of dofs SHARED between elements (launch_clear_rows); the
+  // element-interior rows are left to the plain stores of the lane-pair / six-lane kernels.  The first-generation
+  // kernel reduces into every row, so launch_nd_apply clears all of y itself before falling back to it.
+  int partial_clear = 0;
+  long n_rows_y = 0;                   // rows of y (ND dofs), for that fallback
   const int *cls = nullptr;            // [n_elem]
   const double *eps = nullptr;         // [n_elem]
   const double *muinv = nullptr;       // [n_elem]
@@ -120,6 +125,8 @@ cudaError_t launch_curl(int p, const Tabs &T, const ElemData &E, const double2 *
 
 // ---- layout conversion: boundary [re(N); im(N)] per vector  <->  block [N][nvec] complex ----
 cudaError_t launch_pack(const double *reim, double2 *blk, long n, int nvec, cudaStream_t s);
+// y[rows[i]][0 .. nvec) = 0 for the n_rows listed rows (0-based) of an [n][ldy] block vector
+cudaError_t launch_clear_rows(double2 *y, int ldy, int nvec, const int32_t *rows, long n_rows, cudaStream_t s);
 cudaError_t launch_unpack(const double2 *blk, double *reim, long n, int nvec, cudaStream_t s);
 
 // ---- dense block-vector algebra (tall-skinny), all complex ----
