@@ -441,6 +441,9 @@ void bloch_handle_s::field_averages(int i, double out24[24]) {
 void bloch_handle_s::set_kappas(int n, const double *k3) {
   if (n != nk) {   // the block layout [N][nk * block] changes: no warm start across a change of the batch size
     have_vectors = 0;
+    have_hist = 0;
+    kappas_prev.clear();
+    kappas_prev2.clear();
     have_vectors_s = 0;
     eigenvalues.clear();
     eigenvalues_s.clear();

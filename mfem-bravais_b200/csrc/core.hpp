@@ -161,6 +161,13 @@ struct bloch_handle_s {
   std::vector<double> eigenvalues;  // ascending, [nk][nbands]
   bloch_b200::DevBuf<D2> d_X;       // eigenvectors, block layout [N][nk * block] (column k * block + j)
   int have_vectors = 0;             // number of valid columns per k-point in d_X
+  // sweep history: the eigenvectors of the solve BEFORE the last one and the kappas of the last two solves.  When a
+  // k-point continues a walk along a line (kappa_prev2 -> kappa_prev -> kappa in the same direction, similar steps),
+  // span{X(kappa_prev), X(kappa_prev2)} contains the linear extrapolation of the bands: X(kappa_prev2) enters the
+  // first Rayleigh-Ritz as the P block (solver.cu)
+  bloch_b200::DevBuf<D2> d_Xhist;
+  int have_hist = 0;                // columns per k-point valid in d_Xhist (0: none)
+  std::vector<double> kappas_prev, kappas_prev2;   // [nk][3] of the last / last but one solve
   std::vector<double> init_vecs;    // user supplied [m][2N]
   int n_init = 0;
   bloch_b200::SolverStats stats;

@@ -609,7 +609,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   if (mb > 21) mb = 21;      // 3 mb <= 64 basis columns (Gram kernel), lanes of k_rr_update
   if (3L * mb > N) mb = (int)(N / 3);
   if (nb > mb) throw std::invalid_argument("problem too small for the requested number of bands");
-  if (block != mb) { have_vectors = 0; block = mb; }
+  if (block != mb) { have_vectors = 0; block = mb; if (prob.constrained) have_hist = 0; }
   const int gs = K * mb;          // columns of one basis group (X, W or P) over all k-points
   const int ld = 3 * gs;
   const long Nl = N;
@@ -989,6 +989,29 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
   bool have_P = false;
+  // Sweep history (core.hpp): per k-point, X(kappa_prev2) may serve as the P block of the first Rayleigh-Ritz when this
+  // k-point continues a straight walk.  The direction test excludes a walk that turns back, so the history can never
+  // contain the solution of the k-point being solved (kappa == kappa_prev2 is impossible with same-direction steps).
+  std::vector<char> hist_k(K, 0);
+  bool any_hist = false;
+  if (prob.constrained && warm_block && lift_allowed && have_hist == mb && d_Xhist.n >= (size_t)Nl * gs &&
+      kappas_prev.size() == (size_t)3 * K && kappas_prev2.size() == (size_t)3 * K && env_double("BLOCH_HISTORY", 1.0) != 0.0) {
+    for (int b = 0; b < K; b++) {
+      double d1[3], d2[3], n1 = 0, n2 = 0, dot = 0;
+      for (int d = 0; d < 3; d++) {
+        d1[d] = kappas[3 * b + d] - kappas_prev[3 * b + d];
+        d2[d] = kappas_prev[3 * b + d] - kappas_prev2[3 * b + d];
+        n1 += d1[d] * d1[d]; n2 += d2[d] * d2[d]; dot += d1[d] * d2[d];
+      }
+      // only for finely sampled walks: the extrapolation error is O(step^2) against O(step) of the plain warm start, and
+      // the extra block costs about a third of an iteration - measured on FCC order 2: steps of 1 % / 3 % / 6 % / 12 %
+      // of Gamma-X change the warm iteration count by -2 / -1 / 0 / +1 (profiles/hist_probe_r2.log)
+      const double step_max = env_double("BLOCH_HISTORY_MAX_STEP", 0.03) * 2.0 * M_PI / std::cbrt(mesh.volume);
+      hist_k[b] = n1 > 0 && n2 > 0 && dot > 0.7 * std::sqrt(n1 * n2) && n1 < 9.0 * n2 && n2 < 9.0 * n1 &&
+                  n1 < step_max * step_max;
+      any_hist = any_hist || hist_k[b];
+    }
+  }
   int it = 0;
   std::vector<int> nconv(K, 0), its_k(K, 0);
   std::vector<double> maxres(K, 0.0);
@@ -1059,6 +1082,23 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     BLOCH_CUDA(cudaMemcpy2DAsync(S.p + gs, sizeof(D2) * ld, Wc.p, sizeof(D2) * gs, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
     opA(S.p + gs, ld, AS.p + gs, ld, gs);
     op(S.p + gs, ld, MS.p + gs, ld, gs, 0.0, 1.0);
+    if (it == 0 && any_hist) {
+      // P block of the first iteration = the eigenvectors of the last-but-one k-point of the walk, projected like W
+      // (the lift is on: what is left of their gradient content shows up as high Ritz values)
+      BLOCH_CUDA(cudaMemcpyAsync(Wc.p, d_Xhist.p, sizeof(D2) * Nl * gs, cudaMemcpyDeviceToDevice, s));
+      std::vector<double> htol(K);
+      for (int b = 0; b < K; b++) htol[b] = (hist_k[b] && !frozen[b]) ? lift_ptol : 1e30;
+      int its3 = 0;
+      project_ld(this, Wc.p, gs, gs, htol.data(), 3000, &its3);
+      BLOCH_CUDA(cudaMemcpy2DAsync(S.p + 2 * gs, sizeof(D2) * ld, Wc.p, sizeof(D2) * gs, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
+      opA(S.p + 2 * gs, ld, AS.p + 2 * gs, ld, gs);
+      op(S.p + 2 * gs, ld, MS.p + 2 * gs, ld, gs, 0.0, 1.0);
+      std::vector<unsigned char> up8(K);
+      for (int b = 0; b < K; b++) { up8[b] = hist_k[b] ? 1 : 0; use_p[b] = hist_k[b]; }
+      if (rr_device) BLOCH_CUDA(cudaMemcpyAsync(lw.dusep.p, up8.data(), K, cudaMemcpyHostToDevice, s));
+      h_sync(s);   // up8 / htol are stack temporaries
+      have_P = true;
+    }
     t_op += since(t0);
     t0 = tick();
     rayleigh_ritz(have_P ? 3 * mb : 2 * mb);
@@ -1099,6 +1139,17 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
   eigenvalues.assign((size_t)K * nb, 0.0);
   for (int b = 0; b < K; b++)
     for (int j = 0; j < nb; j++) eigenvalues[(size_t)b * nb + j] = lam[(size_t)b * mb + j];
+  if (prob.constrained) {   // sweep history: the previous solution moves to d_Xhist (pointer swap), kappas shift
+    if (have_vectors == mb && d_X.n >= (size_t)Nl * gs) {
+      std::swap(d_X.p, d_Xhist.p);
+      std::swap(d_X.n, d_Xhist.n);
+      have_hist = mb;
+    } else {
+      have_hist = 0;
+    }
+    kappas_prev2 = kappas_prev;
+    kappas_prev = kappas;
+  }
   d_X.alloc((size_t)Nl * gs);
   BLOCH_CUDA(cudaMemcpy2DAsync(d_X.p, sizeof(D2) * gs, S.p, sizeof(D2) * ld, sizeof(D2) * gs, Nl, cudaMemcpyDeviceToDevice, s));
   have_vectors = mb;
