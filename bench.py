@@ -50,9 +50,9 @@ def parse():
     ap.add_argument("--bands", type=int, default=10)
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--pts-per-segment", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "2")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BLOCH_BENCH_STREAMS", "4")),
                     help="concurrent handles per GPU (independent streams / host threads)")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("BLOCH_BENCH_BATCH", "10")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("BLOCH_BENCH_BATCH", "5")),
                     help="k-points iterated together inside one handle (bloch_set_kappa_batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the config-3 apply study (quick runs)")
@@ -240,8 +240,12 @@ def run_b200(args):
     ks = m.k_path(lat, PATH_LABELS, args.pts_per_segment)
     nk = len(ks)
     cores = os.cpu_count() or 1
-    T = max(1, min(args.streams, max(1, cores // max(1, world))))   # solver threads per rank <= cores per rank
-    B = max(1, args.batch)
+    # solver threads per rank: they sleep while their stream works (blocking waits), 4 of them lose nothing on 2 cores
+    # (profiles/tb_scan3_r2.log), so the cap is two threads per core of this rank's share; capped handles get a
+    # larger batch so that the number of k-points in flight stays the same
+    slots = max(1, args.streams) * max(1, args.batch)
+    T = max(1, min(args.streams, max(1, 2 * cores // max(1, world))))
+    B = max(1, min(16, -(-slots // T)))
     while T * B > args.steps and B > 1:
         B -= 1
     # prefer a batch size that fills every round (no padded repeats): the largest B' in [B/2, B] with steps % (T B') == 0
