@@ -323,6 +323,13 @@ void bloch_handle_s::setup() {
       if (!aux) aux = aux_create(this);
       if (aux) aux_setup(aux, this);
     }
+    if (mg && scalar_ready) {   // scalar H1 problem in use on this handle: its preconditioner hierarchy (kind 2)
+      const char *e_smg = std::getenv("BLOCH_SCALAR_MG");
+      if (!e_smg || std::atoi(e_smg) != 0) {
+        if (!mg_scalar) mg_scalar = mg_create(this, 2);
+        if (mg_scalar) mg_setup(mg_scalar, this);
+      }
+    }
   }
   dirty_coef = dirty_kappa = false;
 }
@@ -722,6 +729,7 @@ int bloch_destroy(bloch_handle h) {
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->mg) mg_destroy(h->mg);
   if (h->aux) aux_destroy(h->aux);
+  if (h->mg_scalar) mg_destroy(h->mg_scalar);
   delete h;
   if (own) cudaStreamDestroy(own);
   return BLOCH_OK;
@@ -1204,6 +1212,7 @@ int bloch_scalar_set_coefs(bloch_handle h, const double *stiffness_k, const doub
   for (int e = 0; e < h->mesh.n_elem; e++) REQUIRE(stiffness_k[e] > 0.0 && mass_m[e] > 0.0, "coefficients must be positive");
   h->eps.assign(stiffness_k, stiffness_k + h->mesh.n_elem);     // M1(k) weight of the gradient form
   h->muinv.assign(mass_m, mass_m + h->mesh.n_elem);             // M0(m)
+  h->scalar_ready = true;
   h->dirty_coef = true;
   return BLOCH_OK;
   API_END

@@ -80,6 +80,7 @@ struct EigProblem {
   const double *diagA = nullptr, *diagM = nullptr;
   double lmax_local = 0;
   bool constrained = false, use_init = false;
+  H1Multigrid *mg_precond = nullptr;   // scalar H1 problem: T = one V-cycle of this hierarchy (kind 2)
   DevBuf<double2> *X = nullptr;
   std::vector<double> *evals = nullptr;
   int *have = nullptr, *blk = nullptr;
@@ -118,6 +119,7 @@ struct bloch_handle_s {
   int use_mg = 1;
   bloch_b200::AuxSpace *aux = nullptr;              // auxiliary nodal space of the ND preconditioner (aux.cu)
   int use_aux = 1;                                  // 0: Chebyshev-Jacobi polynomial only (BLOCH_PRECOND=cheb)
+  bloch_b200::H1Multigrid *mg_scalar = nullptr;     // kind-2 hierarchy: preconditioner of the scalar H1 problem
   bloch_b200::DofMaps maps;
   bloch_b200::Basis1D basis;
   bloch_b200::Tabs tabs;

@@ -739,7 +739,9 @@ struct H1Level {
 };
 
 struct H1Multigrid {
-  int kind = 0;                       // coefficient of the level operators: 0 = eps (S0 of the projector), 1 = mu^-1 (auxiliary space)
+  int kind = 0;                       // level operators: 0 = eps-Laplacian (S0 of the projector), 1 = mu^-1-Laplacian (auxiliary space of the
+                                      // ND preconditioner), 2 = eps-slot Laplacian as preconditioner of the scalar H1 problem; kinds 1, 2 carry the
+                                      // sigma * mass shift on the constant mode of the coarsest level
   int smooth_degree = 2;              // Chebyshev-Jacobi smoother degree (BLOCH_MG_SMOOTH_DEGREE / BLOCH_AUX_MG_DEGREE)
   std::deque<H1Level> lev;
   Transfer1D T;
@@ -1107,7 +1109,7 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
           const D2 a = A[(size_t)i * w + k * n + j], at = A[(size_t)j * w + k * n + i];
           Am[(size_t)i * n + j] = 0.5 * dense::cplx(a.x + at.x, a.y - at.y);
         }
-      if (mg->kind == 1) {
+      if (mg->kind >= 1) {
         // auxiliary-space hierarchy: the ND problem it preconditions is A + sigma M, whose auxiliary operator is
         // L + sigma * mass.  The mass term only matters on the constant mode (eigenvalue |kappa|^2 of L against
         // >= (2 pi / a)^2 for every other mode), so it is added there alone, as the rank-one term
@@ -1115,9 +1117,12 @@ void mg_setup(H1Multigrid *mg, bloch_handle_s *h) {
         // near-constant fields by 1 / |kappa|^2 next to Gamma (CUB order 1 n_sub 16 at kappa = 0.01 (1,1,1):
         // 20 outer iterations against 9) and is singular at Gamma itself.
         const double vol23 = std::cbrt(h->mesh.volume) * std::cbrt(h->mesh.volume);
+        // mass coefficient of the problem the hierarchy preconditions: eps for the ND problem (kind 1), the scalar
+        // problem's m (muinv slot) for kind 2
+        const std::vector<double> &mass_coef = mg->kind == 1 ? h->eps : h->muinv;
         double eps_mean = 0.0;
-        for (double e : h->eps) eps_mean += e;
-        eps_mean /= (double)h->eps.size();
+        for (double e : mass_coef) eps_mean += e;
+        eps_mean /= (double)mass_coef.size();
         const double lift = env_double("BLOCH_SIGMA_SCALE", 1.0) / vol23 * h->mesh.volume * eps_mean / ((double)n * n);
         for (int i = 0; i < n; i++)
           for (int j = 0; j < n; j++) Am[(size_t)i * n + j] += lift;

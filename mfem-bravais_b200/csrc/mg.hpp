@@ -10,7 +10,9 @@ namespace bloch_b200 {
 struct H1Multigrid;
 // builds the nested level hierarchy (topology, transfer tables); nullptr if n_sub is odd.
 // kind 0: level operators S0 = G^H M1(eps) G (the projector's problem); kind 1: the same Bloch Laplacian with
-// mu^-1 as coefficient - the scalar operator of the auxiliary nodal space (H1)^3 of the ND preconditioner (aux.cu)
+// mu^-1 as coefficient - the scalar operator of the auxiliary nodal space (H1)^3 of the ND preconditioner (aux.cu);
+// kind 2: the kind-0 operator as PRECONDITIONER of the scalar H1 eigenproblem (misc/scalar3d.cpp), i.e. with the
+// sigma * mass shift on the constant mode that kind 1 has as well (the projector needs the unshifted S0)
 H1Multigrid *mg_create(bloch_handle_s *h, int kind = 0);
 void mg_destroy(H1Multigrid *mg);
 // per (kappa, coefficients): class tables, restricted coefficients, Jacobi diagonals, coarse inverse

@@ -579,6 +579,7 @@ void bloch_handle_s::solve_scalar() {
   prob.diagM = d_diagM0.p;
   prob.lmax_local = lmax_local_h1;
   prob.constrained = false;
+  if (use_mg && mg_scalar && env_double("BLOCH_SCALAR_MG", 1.0) != 0.0) prob.mg_precond = mg_scalar;   // built by setup()
   prob.X = &d_Xs;
   prob.evals = &eigenvalues_s;
   prob.have = &have_vectors_s;
@@ -794,6 +795,17 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     op(out, gs, Qb.p, gs, gs, 1.0, sigma);
     smooth(Qb.p, 1);
     prof_in_precond = false;
+    prof_end(3);
+  };
+
+  // Scalar H1 variant (misc/scalar3d.cpp:70-85: the reference preconditions with BoomerAMG sweeps): the stiffness operator
+  // A = (grad + i kappa)^H k (grad + i kappa) IS the level-0 operator of the handle's H1 multigrid (coefficient k in the
+  // eps slot), so T = one V-cycle of a hierarchy built on it (kind 2: with the sigma * mass shift on the constant mode, so
+  // that T does not blow up the near-constant fields at small kappa); BCC order 4 n_sub 8, 20 modes: 1.71 -> 0.84 s.
+  const bool mgpre_on = !prob.constrained && prob.mg_precond != nullptr;
+  auto precondition_mg = [&](const D2 *r_in, D2 *out) {
+    prof_begin(3);
+    mg_vcycle(prob.mg_precond, this, r_in, out, gs);
     prof_end(3);
   };
 
@@ -1066,6 +1078,7 @@ void bloch_handle_s::lobpcg(bloch_b200::EigProblem &prob) {
     // W = P_proj T R
     t0 = tick();
     if (aux_on) precondition_aux(R.p, Wc.p);
+    else if (mgpre_on) precondition_mg(R.p, Wc.p);
     else precondition(R.p, Wc.p);
     t_pre += since(t0);
     t0 = tick();

@@ -63,3 +63,29 @@ def test_scalar_eigenvalues(bloch, name, n, p, nm):
     assert np.allclose(lam, ref, rtol=1e-7, atol=1e-9), (lam, ref)
     ev = eq.GetEigenvalues()
     assert len(ev) == 2 * nm and np.allclose(ev[0::2], ev[1::2])
+
+
+@pytest.mark.parametrize("name,n,p,nm,kappa", [("CUB", 4, 1, 6, (0.8, -0.3, 0.5)), ("FCC", 2, 2, 6, (0.8, -0.3, 0.5)),
+                                               ("CUB", 4, 3, 8, (0.2, 0.1, 0.0)), ("CUB", 4, 2, 6, (0.0, 0.0, 0.0))])
+def test_scalar_eigenvalues_with_multigrid_preconditioner(bloch, name, n, p, nm, kappa):
+    """Even n_sub: the scalar solve is preconditioned by one V-cycle of the H1 multigrid (the reference: BoomerAMG sweeps,
+    misc/scalar3d.cpp:70-85).  Same eigenvalues as with the Chebyshev polynomial (BLOCH_SCALAR_MG=0) and as the oracle's
+    dense pencil; the outer iteration count stays in the same range (a V-cycle costs 4 fine-level applies, the polynomial 23)."""
+    import os
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["BLOCH_SCALAR_MG"] = mode
+        try:
+            eq, ops = _pair(bloch, name, n, p)
+            eq.SetKappa(np.array(kappa))
+            eq.SetNumEigs(2 * nm)
+            eq.SetAbsoluteTolerance(1e-9)
+            eq.Setup()
+            eq.Solve()
+            res[mode] = (eq.mode_eigenvalues().copy(), eq.GetSolverStats()["iterations"])
+        finally:
+            del os.environ["BLOCH_SCALAR_MG"]
+    ref = ops.set_kappa(np.array(kappa)).eig_dense(nm)
+    assert np.allclose(res["1"][0], ref, rtol=1e-7, atol=1e-8), (res["1"][0], ref)
+    assert np.allclose(res["1"][0], res["0"][0], rtol=1e-7, atol=1e-8)
+    assert res["1"][1] <= 2 * res["0"][1], (res["1"][1], res["0"][1])
