@@ -614,4 +614,87 @@ private:
   std::vector<double> times_, iters_;
 };
 
+// Mirror of ScalarFloquetWaveEquation (misc/scalar3d.cpp:99-162, 592-898): the scalar H1 Bloch Helmholtz problem
+//     (G - i Z_kappa)^T M1(k) (G - i Z_kappa) u = lambda M0(m) u,      kappa = beta * pi / 180 * zeta,
+// with the phase shift beta in DEGREES and the direction zeta from azimuth / inclination in degrees (:665-669),
+// element-wise constant coefficients k (stiffness) and m (mass).  The reference hands its operators to HypreLOBPCG
+// in the driver (:427-444, preconditioner = BoomerAMG sweeps, :70-85); here Solve() runs the library's block LOBPCG
+// with a geometric-multigrid V-cycle as preconditioner.  nev counts REAL modes (2 per complex mode).
+class ScalarFloquetWaveEquation {
+public:
+  ScalarFloquetWaveEquation(const BravaisLattice &lat, int n_sub, int order, int device = -1) {
+    if (bloch_create(&h_, lat.handle(), n_sub, order, device) != BLOCH_OK) throw Error("bloch_create");
+    int64_t ne, n, nrt, nh1;
+    int nc;
+    bloch_num_elements(h_, &ne, &nc);
+    bloch_num_dofs(h_, &n, &nrt, &nh1);
+    n_elem_ = ne; N_ = nh1;
+    k_.assign((size_t)ne, 1.0);
+    m_.assign((size_t)ne, 1.0);
+  }
+  ~ScalarFloquetWaveEquation() { bloch_destroy(h_); }
+  ScalarFloquetWaveEquation(const ScalarFloquetWaveEquation &) = delete;
+  ScalarFloquetWaveEquation &operator=(const ScalarFloquetWaveEquation &) = delete;
+
+  int64_t GetH1TrueVSize() const { return N_; }          // GetFESpace()->GlobalTrueVSize()
+  int64_t GetNE() const { return n_elem_; }
+  void GetElementCenters(std::vector<double> &xyz) const {
+    xyz.resize(3 * (size_t)n_elem_);
+    check(bloch_element_centers(h_, xyz.data()), "bloch_element_centers");
+  }
+  void SetBeta(double beta_degrees) { beta_ = beta_degrees; explicit_kappa_ = false; }
+  void SetAzimuth(double alpha_a) { alpha_a_ = alpha_a; explicit_kappa_ = false; }
+  void SetInclination(double alpha_i) { alpha_i_ = alpha_i; explicit_kappa_ = false; }
+  // convenience beyond the reference: the Bloch vector itself
+  void SetKappa(const std::vector<double> &kappa) { kappa_ = kappa; explicit_kappa_ = true; }
+  void GetZeta(std::vector<double> &zeta) const {        // scalar3d.cpp:665-669
+    const double d = M_PI / 180.0;
+    zeta = {std::cos(alpha_i_ * d) * std::cos(alpha_a_ * d), std::cos(alpha_i_ * d) * std::sin(alpha_a_ * d), std::sin(alpha_i_ * d)};
+  }
+  void GetKappa(std::vector<double> &kappa) const {
+    if (explicit_kappa_) { kappa = kappa_; return; }
+    GetZeta(kappa);
+    for (double &x : kappa) x *= beta_ * M_PI / 180.0;   // :733 (beta^2 pi^2 / 32400 = (beta pi / 180)^2), :784-785
+  }
+  void SetMassCoef(const std::vector<double> &m_per_elem) { m_ = m_per_elem; }
+  void SetStiffnessCoef(const std::vector<double> &k_per_elem) { k_ = k_per_elem; }
+  void SetNumEigs(int nev) { nev_ = nev; }
+  void SetAbsoluteTolerance(double atol, int max_iter = 1000) { atol_ = atol; max_iter_ = max_iter; }
+  void Setup() {
+    if ((int64_t)k_.size() != n_elem_ || (int64_t)m_.size() != n_elem_) throw std::invalid_argument("coefficient arrays must have one entry per element");
+    check(bloch_scalar_set_coefs(h_, k_.data(), m_.data()), "bloch_scalar_set_coefs");
+    check(bloch_scalar_set_num_modes(h_, (nev_ + 1) / 2), "bloch_scalar_set_num_modes");
+    check(bloch_set_tol(h_, atol_, max_iter_), "bloch_set_tol");
+    std::vector<double> kappa;
+    GetKappa(kappa);
+    check(bloch_set_kappa(h_, kappa.data()), "bloch_set_kappa");
+    check(bloch_setup(h_), "Setup");
+  }
+  void Solve() { check(bloch_scalar_solve(h_), "Solve"); }
+  void GetEigenvalues(std::vector<double> &eigenvalues) {   // nev values, each complex mode twice
+    const int nb = (nev_ + 1) / 2;
+    std::vector<double> lam(nb);
+    check(bloch_scalar_get_eigenvalues(h_, lam.data(), nb), "GetEigenvalues");
+    eigenvalues.resize(nev_);
+    for (int i = 0; i < nev_; i++) eigenvalues[i] = lam[i / 2];
+  }
+  // GetAOperator()->Mult / GetMOperator()->Mult on [re; im] vectors of length 2 N
+  void MultA(const std::vector<double> &x, std::vector<double> &y) { y.resize(x.size()); check(bloch_scalar_apply(h_, 0, x.data(), y.data(), 1), "MultA"); }
+  void MultM(const std::vector<double> &x, std::vector<double> &y) { y.resize(x.size()); check(bloch_scalar_apply(h_, 1, x.data(), y.data(), 1), "MultM"); }
+  void GetSolverStats(int &iterations, double &seconds) {
+    bloch_stats st;
+    bloch_get_stats(h_, &st);
+    iterations = st.iterations;
+    seconds = st.solve_seconds;
+  }
+
+private:
+  bloch_handle h_ = nullptr;
+  int64_t n_elem_ = 0, N_ = 0;
+  int nev_ = 5, max_iter_ = 1000;                  // scalar3d.cpp:291, 431
+  double beta_ = 1.0, alpha_a_ = 0.0, alpha_i_ = 90.0, atol_ = 1e-6;   // class defaults of :593-595, tolerance :432
+  bool explicit_kappa_ = false;
+  std::vector<double> kappa_, k_, m_;
+};
+
 }  // namespace bloch_b200

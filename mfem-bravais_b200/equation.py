@@ -512,6 +512,20 @@ class ScalarFloquetWaveEquation:
         self._zeta = np.asarray(zeta, float)
         self._push_kappa()
 
+    def SetAzimuth(self, alpha_a_degrees):
+        """direction of the phase shift from azimuth / inclination in degrees (scalar3d.cpp:109-110, 665-669)"""
+        self._alpha_a = float(alpha_a_degrees)
+        self._push_angles()
+
+    def SetInclination(self, alpha_i_degrees):
+        self._alpha_i = float(alpha_i_degrees)
+        self._push_angles()
+
+    def _push_angles(self):
+        d = np.pi / 180.0
+        a, i = getattr(self, "_alpha_a", 0.0), getattr(self, "_alpha_i", 90.0)      # class defaults, scalar3d.cpp:594-595
+        self.SetZeta([np.cos(i * d) * np.cos(a * d), np.cos(i * d) * np.sin(a * d), np.sin(i * d)])
+
     def SetKappa(self, kappa):
         self._eq.SetKappa(kappa)
 

@@ -114,3 +114,30 @@ def test_cpp_driver_batched_walk_equals_sequential(bloch, tmp_path):
         assert ra[:2] == rb[:2]                                           # counters, labels, blank lines between paths
         if len(ra) > 2:
             assert np.allclose([float(x) for x in ra[2:]], [float(x) for x in rb[2:]], rtol=1e-5, atol=1e-5)
+
+
+def test_cpp_scalar3d_driver_matches_the_python_mirror(bloch):
+    """scalar3d_b200 (C++ ScalarFloquetWaveEquation mirror + the reference's flags and coefficients,
+    misc/scalar3d.cpp:280-557) prints the eigenvalues the Python mirror computes for the same problem."""
+    exe = os.path.join(ROOT, "mfem-bravais_b200", "lib", "scalar3d_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    r = subprocess.run([exe, "-bl", "3", "-o", "2", "-sr", "0", "-pr", "2", "-nev", "8", "-b", "40", "-az", "20", "-inc", "30"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("Eigenvalues:")][0]
+    ev = np.array(line.split()[1:], float)
+    assert ev.shape == (8,) and np.allclose(ev[0::2], ev[1::2])
+    L = bloch.BravaisLattice("BCC")
+    eq = bloch.ScalarFloquetWaveEquation(L, 4, 2)
+    r2 = np.linalg.norm(eq.element_centers(), axis=1)
+    eq.SetMassCoef(np.where(r2 <= 0.5, 10.0, 1.0))
+    eq.SetStiffnessCoef(np.where(r2 <= 0.5, 5.0, 0.1))
+    eq.SetBeta(40.0)
+    eq.SetAzimuth(20.0)
+    eq.SetInclination(30.0)
+    eq.SetNumEigs(8)
+    eq.SetAbsoluteTolerance(1e-6)
+    eq.Setup()
+    eq.Solve()
+    assert np.allclose(ev, eq.GetEigenvalues(), rtol=1e-6, atol=1e-8), (ev, eq.GetEigenvalues())

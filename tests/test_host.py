@@ -340,3 +340,50 @@ int main(int argc, char **argv) {
     for a, b in ((zp, zc), (zc, zp)):
         coef = np.linalg.lstsq(a, b, rcond=None)[0]
         assert np.linalg.norm(a @ coef - b) < 1e-9 * np.linalg.norm(b)
+
+
+def test_scalar_wrapper_cpp_and_python_agree_on_the_bloch_vector(bloch, tmp_path):
+    """ScalarFloquetWaveEquation mirrors (C++ header and Python): kappa = beta pi / 180 * zeta(azimuth, inclination)
+    as in misc/scalar3d.cpp:665-669, 733; sizes from the topology-only handle; Solve() without a device fails loudly."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "s.cpp"
+    src.write_text(r'''
+#include "maxwell_bloch_b200.hpp"
+#include <cstdlib>
+using namespace bloch_b200;
+int main(int argc, char **argv) {
+  BravaisLattice L(std::atoi(argv[1]));
+  ScalarFloquetWaveEquation eq(L, 2, 3, BLOCH_DEVICE_NONE);
+  std::vector<double> z, k;
+  eq.GetZeta(z);                                   // class defaults: azimuth 0, inclination 90 -> (0, 0, 1)
+  std::printf("%.17g %.17g %.17g\n", z[0], z[1], z[2]);
+  eq.SetBeta(75.0); eq.SetAzimuth(30.0); eq.SetInclination(20.0);
+  eq.GetKappa(k);
+  std::printf("%.17g %.17g %.17g\n", k[0], k[1], k[2]);
+  std::printf("%lld %lld\n", (long long)eq.GetH1TrueVSize(), (long long)eq.GetNE());
+  try { eq.Setup(); eq.Solve(); std::printf("solved\n"); } catch (const std::exception &ex) { std::printf("error\n"); }
+  return 0;
+}
+''')
+    exe = str(tmp_path / "s")
+    libdir = os.path.join(root, "mfem-bravais_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), str(src), "-L" + libdir,
+                           "-lbloch_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    from mfem_bravais_b200 import capi
+    out = subprocess.check_output([exe, str(capi.LATTICE_TYPES["BCC"])]).decode().split("\n")
+    z = np.array(out[0].split(), float)
+    k = np.array(out[1].split(), float)
+    nh1, ne = (int(x) for x in out[2].split())
+    assert np.allclose(z, [0.0, 0.0, 1.0], atol=1e-15)
+    d = np.pi / 180.0
+    zeta = np.array([np.cos(20 * d) * np.cos(30 * d), np.cos(20 * d) * np.sin(30 * d), np.sin(20 * d)])
+    assert np.allclose(k, 75.0 * d * zeta, rtol=1e-14)
+    assert out[3] == "error"                          # no CPU path
+    L = bloch.BravaisLattice("BCC")
+    eq = bloch.ScalarFloquetWaveEquation(L, 2, 3, device=-2)
+    assert (eq.N, eq.n_elem) == (nh1, ne)
+    eq.SetBeta(75.0)
+    eq.SetAzimuth(30.0)
+    eq.SetInclination(20.0)
+    assert np.allclose(eq._eq._kappa_set, k, rtol=1e-14)
