@@ -4,10 +4,13 @@
 //
 //   * block LOBPCG on m complex vectors (the reference's 2m real ones), basis S = [X W P] kept in
 //     ONE row-major array [N][3m] so both Gram matrices are a single tall-skinny contraction each;
-//   * preconditioner T = Chebyshev polynomial in D^-1 (A + sigma M) (Jacobi D from the same
-//     element kernels); eigenvalues do not depend on T, only the iteration count does;
-//   * constraint G^H M x = 0 imposed by projecting W (and the initial block) with a block
-//     Jacobi-PCG on S0 = G^H M G whose per-column scalars live on the device.
+//   * preconditioner T = auxiliary-space cycle for A + sigma M (Chebyshev-Jacobi smoother + nodal (H1)^3
+//     correction Pi B Pi^H by multigrid V-cycles, aux.cu; precondition_aux below), or a degree-24 Chebyshev
+//     polynomial in D^-1 (A + sigma M) (BLOCH_PRECOND=cheb, odd n_sub); the scalar H1 problem uses one V-cycle
+//     of its own hierarchy.  Eigenvalues do not depend on T, only the iteration count does;
+//   * constraint G^H M x = 0 imposed by projecting W (and the initial block) with a block PCG on
+//     S0 = G^H M G preconditioned by a geometric-multigrid V-cycle (mg.cu; Jacobi-PCG fallback, proj_cg.cu),
+//     relaxed by the gradient lift once a k-point is warm.
 // On the affine WS meshes (C - iZ)(G - iZ0) = 0 holds exactly, so the projected residual equals
 // the plain residual and the convergence test is || A x - lambda M x ||_2 <= atol like hypre's.
 #include <algorithm>
