@@ -167,3 +167,49 @@ def test_nodal_interpolation_matrix(name, n, p):
         v = Pi @ c
         assert np.abs(ops.T12 @ v).max() < 1e-12                    # curl of a constant field
         assert abs(v @ (ops.M1 @ v) - vol_eps) < 1e-11 * vol_eps    # |e_d|^2 integrated with eps
+
+
+def _precond_condition(name, n, p, kappa=(0.9, 0.4, 0.2)):
+    """cond of P T (A + sigma M) on the divergence-free space for T = auxiliary-space cycle (exact auxiliary solves)
+    and for T = one damped Jacobi sweep, on the oracle's assembled matrices"""
+    from oracle.bloch_oracle import nodal_interpolation
+    lat = Lattice(name)
+    mesh = Mesh(lat, n)
+    s = Spaces(mesh, p)
+    ops = BlochOperators(s, mesh.sphere_eps()).set_kappa(np.array(kappa))
+    ops1 = BlochOperators(s, np.ones(mesh.ne)).set_kappa(np.array(kappa))
+    A, M, G = ops.A_c().toarray(), ops.M_c().toarray(), ops.G_c().toarray()
+    sigma = 1.0 / mesh.volume ** (2.0 / 3.0)
+    Ash = A + sigma * M
+    Pi = nodal_interpolation(s).toarray()
+    n0 = s.n_h1
+    Li = np.linalg.inv(ops1.S0_c().toarray() + sigma * ops.M0.toarray())
+    Z = np.zeros((3 * n0, 3 * n0), complex)
+    for d in range(3):
+        Z[d * n0:(d + 1) * n0, d * n0:(d + 1) * n0] = Li
+    dj = 1.0 / np.diag(Ash).real
+    lmax = np.linalg.eigvalsh((np.sqrt(dj)[:, None] * Ash) * np.sqrt(dj)[None, :]).max()
+    S = np.diag(dj / (0.625 * lmax))
+    I = np.eye(len(A))
+    X = S.copy()                                    # x = S r; x += Pi L^-1 Pi^T (r - A x); x += S (r - A x)
+    X = X + Pi @ Z @ Pi.T @ (I - Ash @ X)
+    X = X + S @ (I - Ash @ X)
+    P = I - G @ np.linalg.solve(G.conj().T @ M @ G, G.conj().T @ M)
+
+    def cond(T):
+        w = np.linalg.eigvals(P @ T @ Ash @ P)
+        w = np.sort(w.real[np.abs(w) > 1e-8 * np.abs(w).max()])
+        return w.max() / w.min()
+    return cond(X), cond(S)
+
+
+def test_auxiliary_space_preconditioner_is_mesh_and_order_independent():
+    """The algorithm behind csrc/aux.cu on the oracle's matrices (the role of HypreAMS, maxwell_bloch.cpp:492-517):
+    smoother + Pi L^-1 Pi^T followed by the divergence projector gives cond(P T (A + sigma M)) ~ 1.5 - 2.3 whatever the
+    mesh, the order and the lattice, where a Jacobi sweep alone degrades like h^-2."""
+    res = {c: _precond_condition(*c) for c in [("CUB", 2, 1), ("CUB", 4, 1), ("FCC", 2, 1), ("CUB", 2, 2)]}
+    for c, (ka, kj) in res.items():
+        assert ka < 3.0, (c, ka)
+        assert kj > 5.0 * ka, (c, ka, kj)
+    assert res[("CUB", 4, 1)][1] > 2.5 * res[("CUB", 2, 1)][1]          # Jacobi: 16 -> 54
+    assert res[("CUB", 4, 1)][0] < 1.5 * res[("CUB", 2, 1)][0]          # auxiliary space: 1.6 -> 1.8
