@@ -234,6 +234,10 @@ int bloch_debug_apply_h1op(bloch_handle h, int mode, const double *x, double *y,
  *   mode 0: y(2 N) = Pi u   (nodal interpolation (H1)^3 -> ND);  mode 1: y(2 * 3 N_h1) = Pi^T x(2 N);
  *   mode 2: y = B u, one multigrid V-cycle per component for (grad + i kappa)^H mu^-1 (grad + i kappa) */
 int bloch_debug_apply_aux(bloch_handle h, int mode, const double *x, double *y, int nvec);
+/* The matrix Pi itself in CSR form (rows = ND dofs, column d * N_h1 + node, real weights): host code only, also on
+ * BLOCH_DEVICE_NONE handles, so that it can be compared with an assembled interpolation without a GPU.
+ * rowptr == NULL: only *nnz is returned; otherwise rowptr[N + 1], col[nnz], val[nnz] are filled. */
+int bloch_debug_pi_matrix(bloch_handle h, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val);
 /* Test hook for the nested-mesh transfers of the projector's H1 multigrid (no counterpart in the reference, whose
  * MINRES has no hierarchy): level 0 (the handle's mesh) <-> level 1 (n_sub / 2) in each implementation -
  * variant 0 explicit CSR, 1 sum-factorised parent kernels, 2 element-wise kernels; dir 0: y(2 N_h1) = P x(2 n_coarse),

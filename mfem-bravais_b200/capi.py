@@ -98,6 +98,7 @@ SIGNATURES = {
     "bloch_scalar_apply": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "bloch_debug_apply_h1op": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "bloch_debug_apply_aux": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
+    "bloch_debug_pi_matrix": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp]),
     "bloch_debug_mg_transfer": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.POINTER(C.c_int64)]),
     "bloch_debug_fp64_peak": (C.c_int, [_vp, _dp]),
 }

@@ -38,14 +38,9 @@ struct AuxSpace {
   ~AuxSpace() { if (mg) mg_destroy(mg); }
 };
 
-AuxSpace *aux_create(bloch_handle_s *h) {
-  if (h->p > 3) return nullptr;
-  H1Multigrid *mg = mg_create(h, 1);
-  if (!mg) return nullptr;
-  AuxSpace *ax = new AuxSpace();
-  ax->mg = mg;
-  ax->N = h->N;
-  ax->N0 = h->N0;
+// Pi in CSR form (rows = ND dofs, column d * N0 + node): pure host code on the handle's mesh, maps and 1-D tables, so
+// the matrix can be checked against the oracle without a device (bloch_debug_pi_matrix, tests/test_host.py)
+void aux_build_pi(const bloch_handle_s *h, std::vector<int> &ptr, std::vector<int32_t> &col, std::vector<double> &val) {
   const int p = h->p, Q = p + 1, nb = p * Q * Q, LN = h->L_nd, LH = h->L_h1;
   const long N = h->N, N0 = h->N0;
   const std::vector<int32_t> &nd = h->maps.nd, &h1 = h->maps.h1;
@@ -56,9 +51,9 @@ AuxSpace *aux_create(bloch_handle_s *h) {
       const long g = std::labs((long)nd[(size_t)e * LN + j]) - 1;
       if (rep[g] < 0) rep[g] = e * LN + j;
     }
-  std::vector<int> ptr(N + 1, 0);
-  std::vector<int32_t> col;
-  std::vector<double> val;
+  ptr.assign(N + 1, 0);
+  col.clear();
+  val.clear();
   col.reserve((size_t)N * 3 * Q);
   val.reserve((size_t)N * 3 * Q);
   for (long g = 0; g < N; g++) {
@@ -86,6 +81,21 @@ AuxSpace *aux_create(bloch_handle_s *h) {
     }
     ptr[g + 1] = (int)col.size();
   }
+}
+
+AuxSpace *aux_create(bloch_handle_s *h) {
+  if (h->p > 3) return nullptr;
+  H1Multigrid *mg = mg_create(h, 1);
+  if (!mg) return nullptr;
+  AuxSpace *ax = new AuxSpace();
+  ax->mg = mg;
+  ax->N = h->N;
+  ax->N0 = h->N0;
+  const long N = h->N, N0 = h->N0;
+  std::vector<int> ptr;
+  std::vector<int32_t> col;
+  std::vector<double> val;
+  aux_build_pi(h, ptr, col, val);
   // transpose by counting sort
   std::vector<int> tptr(3 * N0 + 1, 0);
   for (int32_t cidx : col) tptr[cidx + 1]++;

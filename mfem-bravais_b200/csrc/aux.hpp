@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <vector>
+
 struct bloch_handle_s;
 
 namespace bloch_b200 {
@@ -9,6 +12,8 @@ struct AuxSpace;
 // Pi / Pi^T matrices + the mu^-1 multigrid hierarchy; nullptr when the mesh has no nested coarser level (odd n_sub)
 AuxSpace *aux_create(bloch_handle_s *h);
 void aux_destroy(AuxSpace *ax);
+// the nodal interpolation Pi: (H1_p)^3 -> ND_p in CSR form (host only; works on topology-only handles)
+void aux_build_pi(const bloch_handle_s *h, std::vector<int> &ptr, std::vector<int32_t> &col, std::vector<double> &val);
 // per (kappa batch, coefficients): level operators of the auxiliary multigrid
 void aux_setup(AuxSpace *ax, bloch_handle_s *h);
 // y (+)= Pi u3: u3 is [3 N0][m] (component blocks), y is [N][m]

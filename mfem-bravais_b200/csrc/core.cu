@@ -1018,6 +1018,26 @@ int bloch_debug_apply_aux(bloch_handle h, int mode, const double *x, double *y, 
   API_END
 }
 
+// test hook (host only, also on topology-only handles): the nodal interpolation Pi of the auxiliary-space preconditioner
+// in CSR form.  rowptr == NULL: only *nnz is returned.
+int bloch_debug_pi_matrix(bloch_handle h, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val) {
+  API_BEGIN
+  REQUIRE(h && nnz, "null argument");
+  REQUIRE(h->p <= 3, "the Nedelec space supports orders 1..3");
+  std::vector<int> ptr;
+  std::vector<int32_t> c;
+  std::vector<double> v;
+  aux_build_pi(h, ptr, c, v);
+  *nnz = (int64_t)c.size();
+  if (!rowptr) return BLOCH_OK;
+  REQUIRE(col && val, "null argument");
+  for (size_t i = 0; i < ptr.size(); i++) rowptr[i] = ptr[i];
+  std::memcpy(col, c.data(), sizeof(int32_t) * c.size());
+  std::memcpy(val, v.data(), sizeof(double) * v.size());
+  return BLOCH_OK;
+  API_END
+}
+
 // test hook: nested-mesh transfer of the H1 multigrid between the handle's mesh and the next coarser one in its three
 // implementations (variant 0 CSR, 1 sum-factorised, 2 element-wise); dir 0: y(2 N0) = P x(2 N0c), dir 1: y(2 N0c) = P^T x(2 N0)
 int bloch_debug_mg_transfer(bloch_handle h, int variant, int dir, const double *x, double *y, int nvec, int64_t *n_coarse) {

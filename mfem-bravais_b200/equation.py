@@ -434,6 +434,19 @@ class MaxwellBlochWaveEquation:
         check(self._L.bloch_debug_apply_aux(self._h, mode, dptr(x2), dptr(y), x2.shape[0]))
         return y[0] if x.ndim == 1 else y
 
+    def pi_matrix(self):
+        """Nodal interpolation Pi: (H1)^3 -> ND of the auxiliary-space preconditioner as scipy CSR [N, 3 N_h1]
+        (bloch_debug_pi_matrix; host only, works on topology-only handles)."""
+        import scipy.sparse as sp
+        nnz = C.c_int64()
+        check(self._L.bloch_debug_pi_matrix(self._h, C.byref(nnz), None, None, None), "bloch_debug_pi_matrix")
+        ptr = np.zeros(self.N + 1, np.int64)
+        col = np.zeros(nnz.value, np.int32)
+        val = np.zeros(nnz.value)
+        check(self._L.bloch_debug_pi_matrix(self._h, C.byref(nnz), ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                            col.ctypes.data_as(C.POINTER(C.c_int32)), dptr(val)), "bloch_debug_pi_matrix")
+        return sp.csr_matrix((val, col, ptr), shape=(self.N, 3 * self.N_h1))
+
     def debug_mg_transfer(self, variant, direction, x):
         """Level 0 <-> 1 transfer of the H1 multigrid (bloch_debug_mg_transfer); x: [nvec, 2 n_in] in [re; im] layout."""
         nc = C.c_int64()

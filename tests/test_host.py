@@ -387,3 +387,19 @@ int main(int argc, char **argv) {
     eq.SetAzimuth(30.0)
     eq.SetInclination(20.0)
     assert np.allclose(eq._eq._kappa_set, k, rtol=1e-14)
+
+
+@pytest.mark.parametrize("name,n,p", [("CUB", 2, 1), ("CUB", 1, 2), ("FCC", 2, 2), ("BCC", 1, 3), ("HEX", 2, 2), ("FCC", 1, 3)])
+def test_nodal_interpolation_of_the_product_equals_the_oracle(bloch, name, n, p):
+    """Pi: (H1)^3 -> ND of the auxiliary-space preconditioner (csrc/aux.cu, host code) on a topology-only handle against
+    the oracle's assembled interpolation on the product's dof maps (incl. one-element periodic meshes)."""
+    from helpers import oracle_on_product_maps
+    from oracle.bloch_oracle import nodal_interpolation
+    L = bloch.BravaisLattice(name)
+    eq = bloch.MaxwellBlochWaveEquation(L, n, p, device=-2)
+    ops, _ = oracle_on_product_maps(eq, name, n, p, np.ones(eq.n_elem))
+    Pi = nodal_interpolation(ops.sp_)
+    P2 = eq.pi_matrix()
+    assert P2.shape == Pi.shape == (eq.N, 3 * eq.N_h1)
+    assert abs(Pi - P2).max() < 1e-14
+    assert P2.nnz <= eq.N * 3 * (p + 1)
